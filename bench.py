@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py — proposals/sec of the JMODT hot path on B200 (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path of the same work
+
+A "step" is one pass of the hot path over one batch of `--frames` synthetic KITTI-shaped frames per GPU
+(16 384 points, 128 proposals per frame).  The workload names which part of the path is measured; see
+DESIGN.md for the exact op list and shapes of each workload.
+
+The CPU arm and the cpu_baseline leg are the only places that execute oracle/ (as the reported baseline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PTS, N_ROI, ROI_PTS, FEAT_C = 16384, 128, 512, 128
+RPN_NPOINTS = [4096, 1024, 256, 64]                       # config.py:75
+RPN_RADII = [[0.1, 0.5], [0.5, 1.0], [1.0, 2.0], [2.0, 4.0]]   # config.py:76
+RPN_NSAMPLE = [[16, 32]] * 4                              # config.py:77
+FP_CHANNELS = [512, 512, 256, 128]                        # features interpolated at FP levels 3..0 (known side)
+RCNN_NPOINTS, RCNN_RADII, RCNN_NSAMPLE = [128, 32], [0.2, 0.4], [64, 64]   # config.py:133-136
+NMS_BINS = [6300, 2700]                                   # proposal_layer.py:66-70 with PRE_NMS_TOP_N=9000
+ROIPOOL_BYTES_PER_FRAME = N_PTS * (12 + (FEAT_C + 2) * 4) + N_ROI * ROI_PTS * (3 + FEAT_C + 2) * 4  # 43.6 MB
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step (BASELINE config 3 uses 8)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ops", choices=["ops"])
+    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (host side, pinned for the e2e leg)
+# ------------------------------------------------------------------------------------------------
+def make_inputs(first_frame, frames):
+    from jmodt_b200 import synth
+    batch = synth.make_batch(first_frame, frames, with_image=False)
+    rng = np.random.default_rng(99 + first_frame)
+    feats = rng.standard_normal((frames, N_PTS, FEAT_C + 2), dtype=np.float32)     # [mask, depth, 128 rpn feats]
+    # RPN proposals before NMS: 9000 boxes around the rois, scores random (two distance bins)
+    nms_boxes, nms_scores = [], []
+    for n in NMS_BINS:
+        base = batch["rois"][:, rng.integers(0, N_ROI, n)]                           # (B, n, 7)
+        jitter = rng.normal(0, 0.3, base.shape).astype(np.float32)
+        jitter[..., 3:6] *= 0.1
+        nms_boxes.append((base + jitter).astype(np.float32))
+        nms_scores.append(rng.uniform(size=(frames, n)).astype(np.float32))
+    return {"pts": batch["pts"], "rois": batch["rois"], "feats": feats,
+            "nms_boxes": nms_boxes, "nms_scores": nms_scores,
+            "fp_feats": [rng.standard_normal((frames, c, m), dtype=np.float32)
+                         for c, m in zip(FP_CHANNELS, [64, 256, 1024, 4096])]}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+class OpsSuite:
+    """Every jmodt/ops call one inference frame makes (RPN set-abstraction / feature-propagation point ops,
+    proposal NMS, RoI pooling + canonical transform, RCNN-level sampling/grouping queries, tracker IoU),
+    at the real network's shapes, batched over `frames` frames.  Dense MLPs are not part of this workload."""
+
+    def __init__(self, dev, frames):
+        import torch
+        from jmodt_b200.iou3d import iou3d_cuda, iou3d_utils
+        from jmodt_b200.pointnet2 import pointnet2_utils as pu
+        from jmodt_b200.roipool3d import roipool3d_utils as ru
+        self.torch, self.pu, self.ru, self.iou, self.iouc = torch, pu, ru, iou3d_utils, iou3d_cuda
+        self.dev, self.frames = dev, frames
+        self.launches = 0
+        self.kernel_ms = {}
+        self.timing = False
+
+    def _t(self, name, fn, launches=1):
+        self.launches += launches
+        if not self.timing:
+            return fn()
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.kernel_ms.setdefault(name, []).append((e0, e1))
+        return out
+
+    def step(self, d):
+        torch, pu = self.torch, self.pu
+        B = self.frames
+        xyz = d["pts"]
+        lv_xyz = [xyz]
+        # ---- RPN backbone point ops (pointnet2_modules.py:20-63, backbone.py:159-185)
+        for lvl in range(4):
+            cur = lv_xyz[-1]
+            idx = self._t(f"fps_L{lvl}", lambda: pu.farthest_point_sample(cur, RPN_NPOINTS[lvl]))
+            new_xyz = self._t("gather", lambda: pu.gather_operation(cur.transpose(1, 2).contiguous(), idx)
+                              ).transpose(1, 2).contiguous()
+            for r, ns in zip(RPN_RADII[lvl], RPN_NSAMPLE[lvl]):
+                self._t(f"ball_query_L{lvl}", lambda: pu.ball_query(r, ns, cur, new_xyz))
+            lv_xyz.append(new_xyz)
+        # ---- feature propagation point ops (pointnet2_modules.py:146-152)
+        for k, lvl in enumerate([3, 2, 1, 0]):
+            unknown, known = lv_xyz[lvl], lv_xyz[lvl + 1]
+            dist, idx = self._t(f"three_nn_L{lvl}", lambda: pu.three_nn(unknown, known))
+            dist_recip = 1.0 / (dist + 1e-8)
+            weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+            self._t(f"three_interpolate_L{lvl}", lambda: pu.three_interpolate(d["fp_feats"][k], idx, weight))
+        # ---- proposal NMS (proposal_layer.py:59-121): two distance bins per frame, axis-aligned
+        keeps = []
+        for bi in range(B):
+            for boxes, scores in zip(d["nms_bev"], d["nms_scores"]):
+                order = scores[bi].sort(0, descending=True)[1]
+                sb = boxes[bi][order].contiguous()
+                keeps.append(self._t("nms_normal", lambda: self.iouc.nms_device(sb, 0.8, False, max_keep=N_ROI), 2))
+        # ---- RoI pooling + canonical transform (proposal_target_layer.py:99-115)
+        pooled, empty = self._t("roipool3d", lambda: self.ru.roipool3d_gpu_canonical(xyz, d["feats"], d["rois"], 0.2,
+                                                                                      sampled_pt_num=ROI_PTS))
+        # ---- RCNN set-abstraction point ops over B*M proposals (rcnn.py:190-193)
+        cur = pooled.view(B * N_ROI, ROI_PTS, 3 + FEAT_C + 2)[:, :, 0:3].contiguous()
+        for npnt, r, ns in zip(RCNN_NPOINTS, RCNN_RADII, RCNN_NSAMPLE):
+            c = cur
+            idx = self._t(f"fps_rcnn_{npnt}", lambda: pu.farthest_point_sample(c, npnt))
+            new_xyz = self._t("gather", lambda: pu.gather_operation(c.transpose(1, 2).contiguous(), idx)
+                              ).transpose(1, 2).contiguous()
+            self._t(f"ball_query_rcnn_{npnt}", lambda: pu.ball_query(r, ns, c, new_xyz))
+            cur = new_xyz
+        # ---- tracker-side geometry: 3-D IoU between consecutive frames' boxes and final rotated NMS
+        ious = []
+        for bi in range(0, B - 1, 2):
+            ious.append(self._t("boxes_iou3d", lambda: self.iou.boxes_iou3d_gpu(d["rois"][bi], d["rois"][bi + 1])))
+        fin = self._t("nms_rotated", lambda: self.iouc.nms_device(d["final_bev"], 0.1, True), 2)
+        return {"empty": empty, "keep_num": torch.stack([k[1] for k in keeps]), "iou": ious,
+                "final_num": fin[1], "pooled": pooled}
+
+
+def to_device(host, dev, torch, non_blocking=True):
+    from jmodt_b200 import box_utils
+    d = {"pts": host["pts"].to(dev, non_blocking=non_blocking),
+         "rois": host["rois"].to(dev, non_blocking=non_blocking),
+         "feats": host["feats"].to(dev, non_blocking=non_blocking),
+         "fp_feats": [t.to(dev, non_blocking=non_blocking) for t in host["fp_feats"]],
+         "nms_scores": [t.to(dev, non_blocking=non_blocking) for t in host["nms_scores"]]}
+    nb = [t.to(dev, non_blocking=non_blocking) for t in host["nms_boxes"]]
+    d["nms_bev"] = [box_utils.boxes3d_to_bev_torch(t.view(-1, 7)).view(t.shape[0], t.shape[1], 5) for t in nb]
+    d["final_bev"] = box_utils.boxes3d_to_bev_torch(d["rois"][0]).contiguous()
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from jmodt_b200 import _lib
+    _lib.lib()  # fail loudly if the CUDA library is missing: there is no fallback
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.frames
+    # frames shard across ranks: rank r owns frames [r*B, (r+1)*B) of the synthetic sequence (weak scaling)
+    host_np = make_inputs(rank * B, B)
+    host = {k: ([torch.from_numpy(x).pin_memory() for x in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
+            for k, v in host_np.items()}
+    suite = OpsSuite(dev, B)
+    d = to_device(host, dev, torch)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        suite.step(d)
+    barrier()
+    suite.launches = 0
+    suite.timing = True
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    barrier()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                    # L2 flush, outside the per-step event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        suite.step(d)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    launches = suite.launches
+    kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in suite.kernel_ms.items()}
+    kernel_calls = {k: len(v) / args.steps for k, v in suite.kernel_ms.items()}
+    suite.timing = False
+
+    # ---- e2e: same work through the public API with HOST (pinned) inputs and a host read of the results
+    def e2e_step():
+        dd = to_device(host, dev, torch)
+        out = suite.step(dd)
+        res = [out["empty"].cpu(), out["keep_num"].cpu(), out["final_num"].cpu()] + [x.cpu() for x in out["iou"]]
+        return res
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, args.steps // 2)
+    e0.record()
+    for _ in range(n_e2e):
+        res = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / n_e2e
+    h2d = sum(int(np.prod(x.shape)) * 4 for k, v in host_np.items() for x in (v if isinstance(v, list) else [v]))
+    d2h = sum(int(t.numel() * t.element_size()) for t in res)
+
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    proposals_per_step = world * B * N_ROI
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        rp_ms = kernel_ms.get("roipool3d", float("nan"))
+        achieved = ROIPOOL_BYTES_PER_FRAME * B / (rp_ms * 1e-3) / 1e9
+        out = {
+            "metric": "proposals/sec (16k pts, 128 RoI/frame)", "value": proposals_per_step / (ms_per_step * 1e-3),
+            "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "jmodt/ops suite (BASELINE config 2 op list at the real network shapes): FPS x6, "
+                                   "ball_query x10, three_nn/three_interpolate x4, nms_normal x2/frame, "
+                                   "roipool3d+canonical, boxes_iou3d, rotated nms",
+                       "frames_per_gpu_per_step": B, "points_per_frame": N_PTS, "rois_per_frame": N_ROI,
+                       "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event pair)",
+                       "timing": "sum of per-step CUDA-event pairs on torch's current stream (the launching stream)"},
+            "e2e": {"value": proposals_per_step / (e2e_ms * 1e-3), "unit": "proposals/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "roipool3d_kernel<true>", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": ROIPOOL_BYTES_PER_FRAME * B, "kernel_ms": rp_ms},
+            "kernel_ms_per_call": kernel_ms, "kernel_calls_per_step": kernel_calls,
+            "wall_s_timed_region": wall_s,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            out["cpu_baseline"] = cpu_reference(min(args.cpu_sample_frames, B), threads=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the same op list (the reference has no CPU path for these ops
+# except roipool3d, whose reference C++ is used through oracle/_ref when it is available)
+# ------------------------------------------------------------------------------------------------
+def cpu_frame(inp, bi, cref, ref_roipool):
+    pts = inp["pts"][bi:bi + 1]
+    lv = [pts]
+    for lvl in range(4):
+        cur = lv[-1]
+        idx = cref.fps(cur, RPN_NPOINTS[lvl])
+        new_xyz = np.take_along_axis(cur, idx.astype(np.int64)[..., None].repeat(3, -1), 1)
+        for r, ns in zip(RPN_RADII[lvl], RPN_NSAMPLE[lvl]):
+            cref.ball_query(r, ns, cur, new_xyz)
+        lv.append(new_xyz)
+    for k, lvl in enumerate([3, 2, 1, 0]):
+        d2, idx = cref.three_nn(lv[lvl], lv[lvl + 1])
+        dist = np.sqrt(d2)
+        rec = 1.0 / (dist + 1e-8)
+        w = (rec / rec.sum(2, keepdims=True)).astype(np.float32)
+        cref.three_interpolate(inp["fp_feats"][k][bi:bi + 1], idx, w)
+    for boxes, scores in zip(inp["nms_boxes"], inp["nms_scores"]):
+        order = np.argsort(-scores[bi], kind="stable")
+        cref.nms_sorted(cref.boxes3d_to_bev(boxes[bi])[order], 0.8, False)
+    enlarged = cref.enlarge_box3d(inp["rois"][bi], 0.2)
+    if ref_roipool is not None:
+        import torch
+        pp = torch.zeros(N_ROI, ROI_PTS, 3); pf = torch.zeros(N_ROI, ROI_PTS, FEAT_C + 2)
+        pe = torch.zeros(N_ROI, dtype=torch.long)
+        ref_roipool(torch.from_numpy(pts[0]), torch.from_numpy(enlarged), torch.from_numpy(inp["feats"][bi]), pp, pf, pe)
+        pooled_xyz = pp.numpy()
+    else:
+        pooled, _ = cref.roipool3d(pts, inp["feats"][bi:bi + 1], enlarged[None], ROI_PTS)
+        pooled_xyz = pooled[0, :, :, :3]
+    cur = np.ascontiguousarray(pooled_xyz)
+    for npnt, r, ns in zip(RCNN_NPOINTS, RCNN_RADII, RCNN_NSAMPLE):
+        idx = cref.fps(cur, npnt)
+        new_xyz = np.take_along_axis(cur, idx.astype(np.int64)[..., None].repeat(3, -1), 1)
+        cref.ball_query(r, ns, cur, new_xyz)
+        cur = new_xyz
+    cref.boxes_iou3d(inp["rois"][bi], inp["rois"][min(bi + 1, inp["rois"].shape[0] - 1)])
+    cref.nms_sorted(cref.boxes3d_to_bev(inp["rois"][0]), 0.1, True)
+
+
+def _ref_roipool_cpu():
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import _load_ref
+        ns = _load_ref()
+        return None if ns is None else ns.roipool3d_cuda.roipool3d_cpu
+    except Exception:
+        return None
+
+
+def cpu_reference(frames, threads):
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cref
+    cref.build()
+    ref_rp = _ref_roipool_cpu()
+    inp = make_inputs(0, frames)
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for bi in range(frames):
+            cpu_frame(inp, bi, cref, ref_rp)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda bi: cpu_frame(inp, bi, cref, ref_rp), range(frames)))
+    dt = time.perf_counter() - t0
+    return {"value": frames * N_ROI / dt, "unit": "proposals/s", "cores": threads,
+            "kind": "port" if ref_rp is None else "port+reference(roipool3d_cpu)",
+            "sample": f"{frames} frame(s) of the same op list, oracle C restatement"
+                      + (", roipool3d through the reference's own roipool3d_cpu (oracle/_ref)" if ref_rp else ""),
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames_per_step = max(1, min(threads, 8))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(1, 1)
+    steps = max(1, min(args.steps, 3))
+    secs = []
+    for _ in range(steps):
+        base = cpu_reference(frames_per_step, threads)   # inputs are generated outside its timed region
+        secs.append(base["seconds"])
+    dt = float(np.mean(secs))
+    value = frames_per_step * N_ROI / dt
+    base.update({"value": value, "cores": threads,
+                 "sample": f"{frames_per_step} frames per step on {threads} host threads (one frame per thread); " + base["sample"]})
+    print(json.dumps({
+        "impl": "reference", "metric": "proposals/sec (16k pts, 128 RoI/frame)", "value": value,
+        "unit": "proposals/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "jmodt/ops suite on the host CPU (same op list and shapes as the B200 arm)",
+                   "frames_per_step": frames_per_step, "points_per_frame": N_PTS, "rois_per_frame": N_ROI},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

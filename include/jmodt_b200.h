@@ -1,0 +1,151 @@
+/*
+ * jmodt_b200.h — C ABI of libjmodt_b200.so, the B200 (sm_100a) implementation of the JMODT
+ * per-frame hot path.  This is the drop-in boundary: plain pointers and sizes, no torch
+ * types.  Every device pointer is a CUDA device pointer valid on the CURRENT device of the
+ * calling thread (set it with jmb_set_device); `stream` is a cudaStream_t passed as void*.
+ *
+ * Conventions (differences from the reference shims are deliberate and listed here):
+ *   - every entry point returns 0 on success or a negative JMB_ERR_* code; nothing ever
+ *     calls exit() (the reference launchers do: e.g. ball_query_gpu.cu:62-66);
+ *   - kernels are enqueued on `stream` and the call returns immediately; no entry point
+ *     allocates, frees or synchronises (the reference does: roipool3d_kernel.cu:214-232,
+ *     iou3d.cpp:87-96); scratch memory is passed in by the caller, sized by the
+ *     matching *_workspace_bytes() query;
+ *   - outputs are fully written by the kernels, so callers need not zero-initialise them
+ *     (the reference requires it for ball_query idx and roipool3d outputs).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef JMODT_B200_H
+#define JMODT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define JMB_API __attribute__((visibility("default")))
+#else
+#define JMB_API
+#endif
+
+#define JMB_OK 0
+#define JMB_ERR_INVALID_ARG (-1) /* null pointer, negative size, unsupported shape */
+#define JMB_ERR_CUDA (-2)        /* a CUDA runtime call or kernel launch failed   */
+#define JMB_ERR_WORKSPACE (-3)   /* workspace missing or too small               */
+
+/* ABI version (bumped when a signature changes). */
+JMB_API int jmb_version(void);
+/* Message describing the last error on the calling thread ("" if none). */
+JMB_API const char *jmb_last_error(void);
+/* cudaSetDevice for this library's runtime instance; call once per thread before use. */
+JMB_API int jmb_set_device(int device);
+/* Number of SMs of the current device (used by callers to size batches). */
+JMB_API int jmb_sm_count(void);
+
+/* ---- pointnet2 (jmodt/ops/pointnet2/src/pointnet2_api.cpp:10-24) ------------------------ */
+
+/* replaces ball_query_wrapper_fast (ball_query.cpp:14-25) -> ball_query_gpu.cu:9-67.
+ * new_xyz (b,m,3), xyz (b,n,3) fp32; idx (b,m,nsample) int32, fully written
+ * (rows with no neighbour are all 0). */
+JMB_API int jmb_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                   const float *xyz, int *idx, void *stream);
+
+/* replaces group_points_wrapper_fast (group_points.cpp:24-35) -> group_points_gpu.cu:47-86.
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
+JMB_API int jmb_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream);
+
+/* replaces group_points_grad_wrapper_fast (group_points.cpp:10-21) -> group_points_gpu.cu:8-44.
+ * grad_points (b,c,n) must be zero-initialised by the caller (it is accumulated into). */
+JMB_API int jmb_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, void *stream);
+
+/* replaces gather_points_wrapper_fast (sampling.cpp:11-21) -> sampling_gpu.cu:8-44. */
+JMB_API int jmb_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                      float *out, void *stream);
+
+/* replaces gather_points_grad_wrapper_fast (sampling.cpp:24-35) -> sampling_gpu.cu:46-83.
+ * grad_points (b,c,n) must be zero-initialised by the caller. */
+JMB_API int jmb_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                           const int *idx, float *grad_points, void *stream);
+
+/* replaces farthest_point_sampling_wrapper (sampling.cpp:38-46) -> sampling_gpu.cu:93-253.
+ * dataset (b,n,3); temp (b,n) is an OUTPUT here (final min-distances, identical to what the
+ * reference leaves in it) and may be NULL; it need not be pre-filled with 1e10.
+ * idxs (b,m) int32.  Tie-breaking reproduces the reference block reduction exactly. */
+JMB_API int jmb_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
+                                int *idxs, void *stream);
+
+/* replaces three_nn_wrapper_fast (interpolate.cpp:15-25) -> interpolate_gpu.cu:9-74.
+ * dist2 (b,n,3) SQUARED distances, idx (b,n,3). */
+JMB_API int jmb_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                 int *idx, void *stream);
+
+/* replaces three_interpolate_wrapper_fast (interpolate.cpp:28-40) -> interpolate_gpu.cu:77-117. */
+JMB_API int jmb_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream);
+
+/* replaces three_interpolate_grad_wrapper_fast (interpolate.cpp:42-53) -> interpolate_gpu.cu:120-160.
+ * grad_points (b,c,m) must be zero-initialised by the caller. */
+JMB_API int jmb_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, void *stream);
+
+/* ---- roipool3d (jmodt/ops/roipool3d/src/roipool3d.cpp:198-203) --------------------------- */
+
+/* replaces roipool3d_gpu (roipool3d.cpp:48-79) -> roipool3dLauncher (roipool3d_kernel.cu:209-237).
+ * xyz (batch,pts_num,3), boxes3d (batch,boxes_num,7) ALREADY ENLARGED, pts_feature
+ * (batch,pts_num,feat_len) -> pooled_features (batch,boxes_num,sampled,3+feat_len),
+ * pooled_empty_flag (batch,boxes_num) int32.  Both outputs are fully written (empty boxes
+ * get an all-zero block and flag 1). */
+JMB_API int jmb_roipool3d(int batch, int pts_num, int boxes_num, int feat_len, int sampled,
+                  const float *xyz, const float *boxes3d, const float *pts_feature,
+                  float *pooled_features, int *pooled_empty_flag, void *stream);
+
+/* Eval-branch RoI pooling fused with the canonical transform
+ * (proposal_target_layer.py:99-115 + kitti_utils.py:46-64,152-162): boxes3d are the RAW
+ * rois (x, y_bottom, z, h, w, l, ry); they are enlarged by pool_extra_width in-kernel, and
+ * the pooled xyz are centred on the roi and rotated by ry about y. */
+JMB_API int jmb_roipool3d_canonical(int batch, int pts_num, int boxes_num, int feat_len, int sampled,
+                            float pool_extra_width, const float *xyz, const float *boxes3d,
+                            const float *pts_feature, float *pooled_features,
+                            int *pooled_empty_flag, void *stream);
+
+/* ---- iou3d (jmodt/ops/iou3d/src/iou3d.cpp:170-175) --------------------------------------- */
+
+/* replaces boxes_overlap_bev_gpu (iou3d.cpp:31-50) -> iou3d_kernel.cu:223-234,355-365.
+ * boxes (n,5) [x1,y1,x2,y2,ry] -> ans (na,nb). */
+JMB_API int jmb_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *boxes_b,
+                          float *ans_overlap, void *stream);
+
+/* replaces boxes_iou_bev_gpu (iou3d.cpp:52-71) -> iou3d_kernel.cu:236-248,367-373. */
+JMB_API int jmb_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou,
+                      void *stream);
+
+/* boxes_iou3d_gpu (iou3d_utils.py:22-54) as one kernel: boxes (n,7) [x,y,z,h,w,l,ry]. */
+JMB_API int jmb_boxes_iou3d(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou,
+                    void *stream);
+
+/* Scratch bytes needed by jmb_nms / jmb_nms_normal for n boxes. */
+JMB_API size_t jmb_nms_workspace_bytes(int n);
+
+/* replaces nms_gpu (iou3d.cpp:73-118) -> nms_kernel (iou3d_kernel.cu:250-292) + host sweep.
+ * boxes (n,5) sorted by descending score.  Unlike the reference, the greedy sweep runs on
+ * the device: keep (n) int64 and num_keep (1) int32 are DEVICE pointers; nothing is copied
+ * to the host.  max_keep > 0 stops the sweep after that many boxes are kept (the callers
+ * only use the first RPN_POST_NMS_TOP_N, proposal_layer.py:113); 0 means no limit. */
+JMB_API int jmb_nms(int n, const float *boxes, float thresh, int64_t *keep, int *num_keep, int max_keep,
+            void *workspace, size_t workspace_bytes, void *stream);
+
+/* replaces nms_normal_gpu (iou3d.cpp:121-166) -> nms_normal_kernel (iou3d_kernel.cu:306-348). */
+JMB_API int jmb_nms_normal(int n, const float *boxes, float thresh, int64_t *keep, int *num_keep,
+                   int max_keep, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMODT_B200_H */

@@ -1,0 +1,283 @@
+// three_nn / three_interpolate (+grad) and group_points (+grad) for sm_100a.
+//
+// Replaces three_nn_kernel_fast, three_interpolate_kernel_fast, three_interpolate_grad_kernel_fast
+// (reference jmodt/ops/pointnet2/src/interpolate_gpu.cu:9-52, 77-97, 120-142) and
+// group_points_kernel_fast / group_points_grad_kernel_fast (group_points_gpu.cu:47-66, 8-25).
+//
+// three_nn: the reference keeps its running bests in fp64 (:30) purely as storage for fp32
+// values; comparing the widened floats is the same as comparing floats, so fp32 registers
+// give identical results (1e40 becomes +inf, which is also what the reference stores when
+// fewer than three known points exist).  Selection is the three smallest (d2, index) pairs
+// in lexicographic order — strict '<' while scanning in ascending index order (:37-48) —
+// so the known set can be split between SPLIT lanes and merged exactly.
+#include "common.cuh"
+
+namespace jmb {
+
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 1024;  // known points per shared-memory tile (16 KB as float4)
+
+struct Top3 {
+    float d1, d2, d3;
+    int i1, i2, i3;
+};
+
+// insert (d,k) with k larger than every index already present (ascending scan)
+__device__ __forceinline__ void top3_push(Top3 &t, float d, int k) {
+    if (d < t.d3) {
+        if (d < t.d1) {
+            t.d3 = t.d2; t.i3 = t.i2; t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = k;
+        } else if (d < t.d2) {
+            t.d3 = t.d2; t.i3 = t.i2; t.d2 = d; t.i2 = k;
+        } else {
+            t.d3 = d; t.i3 = k;
+        }
+    }
+}
+
+// lexicographic (d, idx) insert for merging partial results of different index ranges
+__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+__device__ __forceinline__ void top3_merge_one(Top3 &t, float d, int k) {
+    if (lex_less(d, k, t.d3, t.i3)) {
+        if (lex_less(d, k, t.d1, t.i1)) {
+            t.d3 = t.d2; t.i3 = t.i2; t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = k;
+        } else if (lex_less(d, k, t.d2, t.i2)) {
+            t.d3 = t.d2; t.i3 = t.i2; t.d2 = d; t.i2 = k;
+        } else {
+            t.d3 = d; t.i3 = k;
+        }
+    }
+}
+
+// SPLIT consecutive lanes share one unknown point; lane s scans tile entries s, s+SPLIT, ...
+template <int SPLIT>
+__global__ void __launch_bounds__(NN_THREADS)
+three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                float *__restrict__ dist2, int *__restrict__ idx) {
+    __shared__ float4 s_known[NN_TILE];
+    const int b = blockIdx.y;
+    constexpr int PTS_PER_CTA = NN_THREADS / SPLIT;
+    const int sub = threadIdx.x % SPLIT;
+    const int p = blockIdx.x * PTS_PER_CTA + threadIdx.x / SPLIT;
+    const bool valid = p < n;
+    const float *kn = known + (size_t)b * m * 3;
+
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (valid) {
+        const float *u = unknown + ((size_t)b * n + p) * 3;
+        ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
+    }
+    Top3 t;
+    t.d1 = t.d2 = t.d3 = __int_as_float(0x7f800000);  // (float)1e40
+    t.i1 = t.i2 = t.i3 = 0;
+    // the reference leaves index 0 in unused slots; for the lexicographic merge the padding
+    // must sort after every real candidate, which +inf already guarantees (real d2 < inf).
+
+    for (int t0 = 0; t0 < m; t0 += NN_TILE) {
+        const int tn = min(NN_TILE, m - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < tn; k += NN_THREADS) {
+            const float *q = kn + (size_t)(t0 + k) * 3;
+            s_known[k] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = sub; k < tn; k += SPLIT) {
+            const float4 q = s_known[k];
+            const float d = dist2_ref(ux - q.x, uy - q.y, uz - q.z);
+            top3_push(t, d, t0 + k);
+        }
+    }
+
+    if (SPLIT > 1) {
+        // butterfly merge across the SPLIT lanes that share this unknown point
+#pragma unroll
+        for (int off = 1; off < SPLIT; off <<= 1) {
+            const float e1 = __shfl_xor_sync(0xffffffffu, t.d1, off);
+            const float e2 = __shfl_xor_sync(0xffffffffu, t.d2, off);
+            const float e3 = __shfl_xor_sync(0xffffffffu, t.d3, off);
+            const int j1 = __shfl_xor_sync(0xffffffffu, t.i1, off);
+            const int j2 = __shfl_xor_sync(0xffffffffu, t.i2, off);
+            const int j3 = __shfl_xor_sync(0xffffffffu, t.i3, off);
+            // +inf padding carries index 0 on both sides; skip it so it cannot displace
+            // a real (inf, k) candidate — real distances are finite for finite inputs.
+            if (e1 < __int_as_float(0x7f800000)) top3_merge_one(t, e1, j1);
+            if (e2 < __int_as_float(0x7f800000)) top3_merge_one(t, e2, j2);
+            if (e3 < __int_as_float(0x7f800000)) top3_merge_one(t, e3, j3);
+        }
+    }
+    if (valid && sub == 0) {
+        float *dd = dist2 + ((size_t)b * n + p) * 3;
+        int *ii = idx + ((size_t)b * n + p) * 3;
+        dd[0] = t.d1; dd[1] = t.d2; dd[2] = t.d3;
+        ii[0] = t.i1; ii[1] = t.i2; ii[2] = t.i3;
+    }
+}
+
+constexpr int TI_CH = 8;  // channels handled by one thread (idx / weight reuse)
+
+// out[b,c,p] = fma(w2,f2, fma(w0,f0, fl(w1*f1)))  — order read from the reference SASS
+__global__ void __launch_bounds__(256)
+three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points,
+                         const int *__restrict__ idx, const float *__restrict__ weight,
+                         float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int *id = idx + ((size_t)b * n + p) * 3;
+    const float *w = weight + ((size_t)b * n + p) * 3;
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const int c0 = blockIdx.y * TI_CH;
+#pragma unroll
+    for (int cc = 0; cc < TI_CH; ++cc) {
+        const int ci = c0 + cc;
+        if (ci < c) {
+            const float *src = points + ((size_t)b * c + ci) * m;
+            const float v = __fmaf_rn(w2, __ldg(src + i2),
+                                      __fmaf_rn(w0, __ldg(src + i0), __fmul_rn(w1, __ldg(src + i1))));
+            out[((size_t)b * c + ci) * n + p] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out,
+                              const int *__restrict__ idx, const float *__restrict__ weight,
+                              float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int *id = idx + ((size_t)b * n + p) * 3;
+    const float *w = weight + ((size_t)b * n + p) * 3;
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const int c0 = blockIdx.y * TI_CH;
+#pragma unroll
+    for (int cc = 0; cc < TI_CH; ++cc) {
+        const int ci = c0 + cc;
+        if (ci < c) {
+            const float g = __ldg(grad_out + ((size_t)b * c + ci) * n + p);
+            float *dst = grad_points + ((size_t)b * c + ci) * m;
+            atomicAdd(dst + i0, __fmul_rn(g, w0));
+            atomicAdd(dst + i1, __fmul_rn(g, w1));
+            atomicAdd(dst + i2, __fmul_rn(g, w2));
+        }
+    }
+}
+
+constexpr int GP_CH = 8;
+
+__global__ void __launch_bounds__(256)
+group_points_kernel(int c, int n, long long per_batch, const float *__restrict__ points,
+                    const int *__restrict__ idx, float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (point, sample) pair
+    if (e >= per_batch) return;
+    const int src = __ldg(idx + (size_t)b * per_batch + e);
+    const int c0 = blockIdx.y * GP_CH;
+#pragma unroll
+    for (int cc = 0; cc < GP_CH; ++cc) {
+        const int ci = c0 + cc;
+        if (ci < c)
+            out[((size_t)b * c + ci) * per_batch + e] = __ldg(points + ((size_t)b * c + ci) * n + src);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+group_points_grad_kernel(int c, int n, long long per_batch, const float *__restrict__ grad_out,
+                         const int *__restrict__ idx, float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_batch) return;
+    const int dst = __ldg(idx + (size_t)b * per_batch + e);
+    const int c0 = blockIdx.y * GP_CH;
+#pragma unroll
+    for (int cc = 0; cc < GP_CH; ++cc) {
+        const int ci = c0 + cc;
+        if (ci < c)
+            atomicAdd(grad_points + ((size_t)b * c + ci) * n + dst,
+                      __ldg(grad_out + ((size_t)b * c + ci) * per_batch + e));
+    }
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                            float *dist2, int *idx, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && n >= 0 && m >= 0, "three_nn: negative size");
+    if (b == 0 || n == 0) return JMB_OK;
+    JMB_REQUIRE(unknown && dist2 && idx && (known || m == 0), "three_nn: null pointer");
+    JMB_REQUIRE(b <= 65535, "three_nn: batch %d exceeds grid.y limit", b);
+    cudaStream_t st = (cudaStream_t)stream;
+    // split the known set across lanes when there are too few unknown points to fill the GPU
+    const long long pts = (long long)b * n;
+    if (pts >= 148LL * 1024) {
+        dim3 grid(div_up(n, NN_THREADS), b);
+        three_nn_kernel<1><<<grid, NN_THREADS, 0, st>>>(n, m, unknown, known, dist2, idx);
+    } else if (pts >= 148LL * 256) {
+        dim3 grid(div_up(n, NN_THREADS / 4), b);
+        three_nn_kernel<4><<<grid, NN_THREADS, 0, st>>>(n, m, unknown, known, dist2, idx);
+    } else {
+        dim3 grid(div_up(n, NN_THREADS / 16), b);
+        three_nn_kernel<16><<<grid, NN_THREADS, 0, st>>>(n, m, unknown, known, dist2, idx);
+    }
+    return check_launch("three_nn");
+}
+
+extern "C" int jmb_three_interpolate(int b, int c, int m, int n, const float *points,
+                                     const int *idx, const float *weight, float *out, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, "three_interpolate: negative size");
+    if (b == 0 || c == 0 || n == 0) return JMB_OK;
+    JMB_REQUIRE(points && idx && weight && out, "three_interpolate: null pointer");
+    JMB_REQUIRE(b <= 65535 && div_up(c, TI_CH) <= 65535, "three_interpolate: grid limit");
+    dim3 grid(div_up(n, 256), div_up(c, TI_CH), b);
+    three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+    return check_launch("three_interpolate");
+}
+
+extern "C" int jmb_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                          const int *idx, const float *weight, float *grad_points,
+                                          void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, "three_interpolate_grad: negative size");
+    if (b == 0 || c == 0 || n == 0) return JMB_OK;
+    JMB_REQUIRE(grad_out && idx && weight && grad_points, "three_interpolate_grad: null pointer");
+    JMB_REQUIRE(b <= 65535 && div_up(c, TI_CH) <= 65535, "three_interpolate_grad: grid limit");
+    dim3 grid(div_up(n, 256), div_up(c, TI_CH), b);
+    three_interpolate_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx,
+                                                                          weight, grad_points);
+    return check_launch("three_interpolate_grad");
+}
+
+extern "C" int jmb_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                                const int *idx, float *out, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "group_points: negative size");
+    if (b == 0 || c == 0 || npoints == 0 || nsample == 0) return JMB_OK;
+    JMB_REQUIRE(points && idx && out, "group_points: null pointer");
+    const long long per_batch = (long long)npoints * nsample;
+    JMB_REQUIRE(b <= 65535 && div_up(c, GP_CH) <= 65535, "group_points: grid limit");
+    dim3 grid((unsigned)div_up_ll(per_batch, 256), div_up(c, GP_CH), b);
+    group_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, per_batch, points, idx, out);
+    return check_launch("group_points");
+}
+
+extern "C" int jmb_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                                     const float *grad_out, const int *idx, float *grad_points,
+                                     void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "group_points_grad: negative size");
+    if (b == 0 || c == 0 || npoints == 0 || nsample == 0) return JMB_OK;
+    JMB_REQUIRE(grad_out && idx && grad_points, "group_points_grad: null pointer");
+    const long long per_batch = (long long)npoints * nsample;
+    JMB_REQUIRE(b <= 65535 && div_up(c, GP_CH) <= 65535, "group_points_grad: grid limit");
+    dim3 grid((unsigned)div_up_ll(per_batch, 256), div_up(c, GP_CH), b);
+    group_points_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, per_batch, grad_out, idx,
+                                                                     grad_points);
+    return check_launch("group_points_grad");
+}

@@ -1,0 +1,191 @@
+// 3-D RoI point pooling for sm_100a — one fused kernel.
+//
+// Replaces roipool3dLauncher (reference jmodt/ops/roipool3d/src/roipool3d_kernel.cu:209-237):
+//   K10 assign_pts_to_box3d (:97-120)  writes a (B,N,M) int flag tensor (8.4 MB / frame),
+//   K11 get_pooled_idx      (:123-160) ONE THREAD per box scans 16 384 flags with stride-M reads,
+//   K12 roipool3d_forward   (:163-194) one thread copies a whole 133-float row,
+//   plus cudaMalloc x2 / cudaFree x2 (implicit device syncs) per call.
+// Here one CTA owns one (frame, box): its 8 warps test disjoint, contiguous slices of the
+// point cloud and compact the hits in index order with ballot/popcount (no flag tensor, no
+// scratch allocation); the per-warp lists are concatenated, wrapped around exactly like
+// :152-158, and the rows are then copied by whole warps with coalesced reads and writes.
+// Outputs are fully written, so the caller's .zero_() pass (roipool3d_utils.py:22-24,
+// 35 MB / frame) is not needed.
+//
+// The in-box predicate follows the SASS of the reference kernel (see oracle/jmodt_oracle.c):
+// float libdevice cosf/sinf, x_rot = fma(dz,-sina, fl(dx*cosa)), z_rot = fma(dx,sina, fl(dz*cosa)),
+// cy = float(double(bottom_y) - double(h)/2).
+#include "common.cuh"
+
+namespace jmb {
+
+constexpr int RP_WARPS = 8;
+constexpr int RP_THREADS = RP_WARPS * 32;
+
+struct BoxTest {
+    float cx, cy, cz, hh, hl, hw, cosa, sina;
+    __device__ __forceinline__ bool inside(float x, float y, float z) const {
+        const float dx = x - cx;
+        if (fabsf(dx) > 10.0f) return false;
+        if (fabsf(y - cy) > hh) return false;
+        const float dz = z - cz;
+        if (fabsf(dz) > 10.0f) return false;
+        const float x_rot = __fmaf_rn(dz, -sina, __fmul_rn(dx, cosa));
+        const float z_rot = __fmaf_rn(dx, sina, __fmul_rn(dz, cosa));
+        return (x_rot >= -hl) & (x_rot <= hl) & (z_rot >= -hw) & (z_rot <= hw);
+    }
+};
+
+// CANON: also apply the eval-branch canonical transform of
+// proposal_target_layer.py:107-112 (centre on the roi, rotate by ry about y), with the box
+// enlarged in-kernel as kitti_utils.enlarge_box3d (kitti_utils.py:152-162) does.
+template <bool CANON>
+__global__ void __launch_bounds__(RP_THREADS)
+roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float extra,
+                 const float *__restrict__ xyz, const float *__restrict__ boxes3d,
+                 const float *__restrict__ pts_feature, float *__restrict__ pooled,
+                 int *__restrict__ empty_flag) {
+    extern __shared__ int rp_smem[];
+    int *s_final = rp_smem;                 // [sampled]
+    int *s_warp = rp_smem + sampled;        // [RP_WARPS][sampled]
+    __shared__ int s_cnt[RP_WARPS];
+
+    const int box = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    const float *bx = boxes3d + ((size_t)b * boxes_num + box) * 7;
+    float bx0 = __ldg(bx), by = __ldg(bx + 1), bz0 = __ldg(bx + 2), bh = __ldg(bx + 3),
+          bw = __ldg(bx + 4), bl = __ldg(bx + 5), ry = __ldg(bx + 6);
+    const float roi_y = by;
+    if (CANON) {
+        const float e2 = extra * 2;  // python: extra_width * 2, then cast to the tensor dtype
+        bh = __fadd_rn(bh, e2); bw = __fadd_rn(bw, e2); bl = __fadd_rn(bl, e2);
+        by = __fadd_rn(by, extra);
+    }
+    BoxTest T;
+    T.cx = bx0; T.cz = bz0;
+    T.cy = (float)((double)by - (double)bh / 2.0);
+    T.hh = bh * 0.5f; T.hl = bl * 0.5f; T.hw = bw * 0.5f;
+    T.cosa = cosf(ry); T.sina = sinf(ry);
+
+    // ---- phase 1: ordered compaction, one contiguous slice of the cloud per warp ----------
+    const float *pts = xyz + (size_t)b * pts_num * 3;
+    const int seg = ((pts_num + RP_WARPS * 32 - 1) / (RP_WARPS * 32)) * 32;
+    const int beg = warp * seg, end = min(pts_num, beg + seg);
+    int *mine = s_warp + (size_t)warp * sampled;
+    int cnt = 0;
+    for (int p0 = beg; p0 < end && cnt < sampled; p0 += 32) {
+        const int p = p0 + (int)lane;
+        bool hit = false;
+        if (p < end) {
+            const float *q = pts + (size_t)p * 3;
+            hit = T.inside(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt + __popc(mk & lt_mask);
+        if (hit && pos < sampled) mine[pos] = p;
+        cnt += __popc(mk);
+    }
+    cnt = min(cnt, sampled);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+
+    int total = 0, my_off = 0;
+#pragma unroll
+    for (int w = 0; w < RP_WARPS; ++w) {
+        if (w == warp) my_off = total;
+        total += s_cnt[w];
+    }
+    const int have = min(total, sampled);
+    for (int i = lane; i < cnt; i += 32)
+        if (my_off + i < sampled) s_final[my_off + i] = mine[i];
+    __syncthreads();
+
+    const int row = 3 + feat_len;
+    float *dst_box = pooled + ((size_t)b * boxes_num + box) * (size_t)sampled * row;
+    if (threadIdx.x == 0) empty_flag[(size_t)b * boxes_num + box] = (have == 0) ? 1 : 0;
+
+    float ox = 0.f, oy = 0.f, oz = 0.f, rc = 1.f, rs = 0.f;
+    if (CANON) { ox = bx0; oy = roi_y; oz = bz0; rc = T.cosa; rs = T.sina; }
+
+    if (have == 0) {
+        // reference: the caller's zero-init survives (roipool3d_kernel.cu:177-179); with the
+        // canonical transform the (0,0,0) xyz of every row is still shifted and rotated
+        // (proposal_target_layer.py:109-112 applies to all rows).
+        float zx = 0.f, zy = 0.f, zz = 0.f;
+        if (CANON) {
+            const float tx = 0.f - ox, tz = 0.f - oz;
+            zy = 0.f - oy;
+            zx = __fmaf_rn(tz, -rs, __fmul_rn(tx, rc));
+            zz = __fmaf_rn(tz, rc, __fmul_rn(tx, rs));
+        }
+        const size_t nflt = (size_t)sampled * row;
+        for (size_t e = threadIdx.x; e < nflt; e += RP_THREADS) {
+            const int j = (int)(e % row);
+            dst_box[e] = j == 0 ? zx : (j == 1 ? zy : (j == 2 ? zz : 0.f));
+        }
+        return;
+    }
+
+    // ---- phase 2: row copies, one warp per row, wrap-around duplicates (:152-158) ---------
+    const float *feat = pts_feature + (size_t)b * pts_num * feat_len;
+    for (int s = warp; s < sampled; s += RP_WARPS) {
+        const int src = s_final[s < have ? s : s % have];
+        float *dst = dst_box + (size_t)s * row;
+        const float *f = feat + (size_t)src * feat_len;
+        if (lane < 3) {
+            const float *q = pts + (size_t)src * 3;
+            float v = __ldg(q + lane);
+            if (CANON) {
+                const float tx = __ldg(q) - ox, tz = __ldg(q + 2) - oz;
+                // rotate_pc_along_y_torch: x' = x*cos - z*sin ; z' = x*sin + z*cos
+                if (lane == 0) v = __fmaf_rn(tz, -rs, __fmul_rn(tx, rc));
+                else if (lane == 1) v = v - oy;
+                else v = __fmaf_rn(tz, rc, __fmul_rn(tx, rs));
+            }
+            dst[lane] = v;
+        }
+        for (int j = lane; j < feat_len; j += 32) dst[3 + j] = __ldg(f + j);
+    }
+}
+
+static int launch_roipool(bool canon, int batch, int pts_num, int boxes_num, int feat_len,
+                          int sampled, float extra, const float *xyz, const float *boxes3d,
+                          const float *pts_feature, float *pooled, int *empty_flag, void *stream) {
+    JMB_REQUIRE(batch >= 0 && pts_num >= 0 && boxes_num >= 0 && feat_len >= 0 && sampled >= 0,
+                "roipool3d: negative size");
+    if (batch == 0 || boxes_num == 0) return JMB_OK;
+    JMB_REQUIRE(xyz || pts_num == 0, "roipool3d: null xyz");
+    JMB_REQUIRE(boxes3d && empty_flag, "roipool3d: null pointer");
+    JMB_REQUIRE(sampled == 0 || pooled, "roipool3d: null output");
+    JMB_REQUIRE(feat_len == 0 || pts_feature || pts_num == 0, "roipool3d: null features");
+    JMB_REQUIRE(batch <= 65535, "roipool3d: batch %d exceeds grid.y limit", batch);
+    const size_t smem = (size_t)(RP_WARPS + 1) * sampled * sizeof(int);
+    JMB_REQUIRE(smem <= 200 * 1024, "roipool3d: sampled_pt_num %d too large", sampled);
+    auto kern = canon ? roipool3d_kernel<true> : roipool3d_kernel<false>;
+    if (smem > 48 * 1024)
+        JMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(boxes_num, batch);
+    kern<<<grid, RP_THREADS, smem, (cudaStream_t)stream>>>(pts_num, boxes_num, feat_len, sampled, extra,
+                                                          xyz, boxes3d, pts_feature, pooled, empty_flag);
+    return check_launch("roipool3d");
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_roipool3d(int batch, int pts_num, int boxes_num, int feat_len, int sampled,
+                             const float *xyz, const float *boxes3d, const float *pts_feature,
+                             float *pooled_features, int *pooled_empty_flag, void *stream) {
+    return jmb::launch_roipool(false, batch, pts_num, boxes_num, feat_len, sampled, 0.f, xyz, boxes3d,
+                               pts_feature, pooled_features, pooled_empty_flag, stream);
+}
+
+extern "C" int jmb_roipool3d_canonical(int batch, int pts_num, int boxes_num, int feat_len,
+                                       int sampled, float pool_extra_width, const float *xyz,
+                                       const float *boxes3d, const float *pts_feature,
+                                       float *pooled_features, int *pooled_empty_flag, void *stream) {
+    return jmb::launch_roipool(true, batch, pts_num, boxes_num, feat_len, sampled, pool_extra_width,
+                               xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, stream);
+}
