@@ -160,7 +160,7 @@ template <int T, int PPT>
 static int launch_fps(int b, int n, int m, int bs, int log2bs, int S, const float *dataset,
                       float *temp, int *idxs, cudaStream_t st) {
     const size_t smem = (size_t)3 * T * PPT * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // static smem (reduction scratch) counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(fps_kernel<T, PPT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
