@@ -145,6 +145,23 @@ JMB_API int jmb_nms(int n, const float *boxes, float thresh, int64_t *keep, int 
 JMB_API int jmb_nms_normal(int n, const float *boxes, float thresh, int64_t *keep, int *num_keep,
                    int max_keep, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- dense MLP layers on tcgen05 tensor cores ------------------------------------------- */
+
+/* One 1x1-conv layer  Y[g] = act(W . X[g] + bias)  of a SharedMLP / Conv1d stack (reference
+ * jmodt/ops/pointnet2/pytorch_utils.py:6-33,127-198; run through cuDNN there).  Channel-first:
+ * X[g] (K, N), Y[g] (M, N).  wpack holds W split into bf16 hi/lo chunk images (jmodt_b200/tc.py
+ * pack_weights); products are accumulated in fp32 as W_hi.X_hi + W_lo.X_hi + W_hi.X_lo.
+ *   mode 0: x is dense (G, K, N) with the given group / row strides (in elements).
+ *   mode 1: fused QueryAndGroup / GroupAll (pointnet2_utils.py:231-290): column n of group g is
+ *           point idx[g][n] (or n % n_pts if idx is NULL); rows 0-2 are xyz[g][point] - centres[g][n / nsample]
+ *           (no centring if centres is NULL), rows 3.. are x[g][k-3][point] with x = feats (G, K-3, n_pts).
+ *   out_mode 0: y (G, M, N);  out_mode 1: max over each `pool` consecutive columns -> y (G, M, N / pool)
+ *           (the set-abstraction max-pool, pointnet2_modules.py:50-52). */
+JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
+                             const float *x, long long x_group_stride, int x_row_stride, const int *idx,
+                             const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
+                             int pool, int relu, float *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

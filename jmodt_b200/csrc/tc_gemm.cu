@@ -1,0 +1,392 @@
+// Pointwise (1x1-conv) MLP layer on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//     Y[g] = act( W · X[g] + bias )        W: (M, K) fp32,  X[g]: (K, N) channel-first,  Y[g]: (M, N)
+//
+// This is the building block of SharedMLP / Conv1d stacks (reference
+// jmodt/ops/pointnet2/pytorch_utils.py:6-33,127-198 run through cuDNN) in the layout the reference
+// already uses — channel-first (B, C, npoint, nsample) — so no transposes are needed: W is the A
+// operand (K-major), X is the B operand in MN-major form (n contiguous), and one accumulator row per
+// TMEM lane is one OUTPUT CHANNEL.  That makes the per-channel bias a per-thread scalar and turns the
+// set-abstraction max-pool over nsample (pointnet2_modules.py:50-52) into a max over a thread's own
+// registers — the (B, C, npoint, nsample) activation of the last layer is never written.
+//
+// fp32-grade results from bf16 tensor cores: every fp32 operand is split x = hi + lo (two bf16), and
+// the product is accumulated in fp32 as  W_hi·X_hi + W_lo·X_hi + W_hi·X_lo  (the dropped lo·lo term and
+// the split residuals are <= 2^-16 relative per product).  The reference's own cuDNN path uses single
+// TF32 (10-bit mantissa) by default; the 3-term split is ~64x more accurate than that.
+//
+// Prologues:  dense X from global memory, or the fused grouping of QueryAndGroup / GroupAll
+// (pointnet2_utils.py:241-290): X[k][n] = xyz[idx[n]][k] - centre[n / nsample][k] for k < 3 and
+// feats[k-3][idx[n]] otherwise — the 549 MB/frame grouped tensor of RCNN SA0 is never materialised.
+//
+// Structure: persistent CTAs of 5 warps.  Warps 0-3 stage operands (W chunk images by one 16 KB
+// cp.async.bulk, X chunks by vector loads + in-register bf16 split) into an mbarrier ring and run the
+// epilogue; warp 4 lane 0 issues tcgen05.mma and signals through tcgen05.commit.  64 KB smem + 128 TMEM
+// columns per CTA -> 3 CTAs per SM, so one CTA's epilogue overlaps another's MMAs.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace jmb {
+
+constexpr int TC_BM = 128;      // output channels per tile  (TMEM lanes)
+constexpr int TC_BN = 128;      // columns per tile          (TMEM columns)
+constexpr int TC_BK = 32;       // K per pipeline stage
+constexpr int TC_STAGES = 2;
+constexpr int TC_IMG = TC_BM * TC_BK * 2;          // bytes of one bf16 operand chunk image (8 KB)
+constexpr int TC_STAGE_BYTES = 4 * TC_IMG;         // W_hi, W_lo, X_hi, X_lo
+constexpr int TC_THREADS = 160;
+constexpr uint32_t TC_LBO = 2048, TC_SBO = 128;    // byte strides of the canonical no-swizzle layouts
+
+struct TcGemmParams {
+    const __nv_bfloat16 *wpack;   // [Mt][Kc][2][TC_IMG/2] chunk images (see pack_weights in tc.py)
+    const float *bias;            // [Mt*128] (zero padded), may be null
+    int M, K, Mt, Kc;
+    int G, N;                     // groups, columns per group
+    int mode;                     // 0 dense, 1 grouped gather
+    const float *x;               // dense: (G, K, N)   gather: feats (G, K-3, n_pts)
+    long long x_group_stride;     // elements
+    int x_row_stride;             // elements between consecutive k rows
+    const int *idx;               // gather: (G, N) point index per column (null: column n -> point n % n_pts)
+    const float *xyz;             // gather: (G, n_pts, 3)
+    const float *centres;         // gather: (G, N / nsample, 3) or null (GroupAll: no centring)
+    int nsample, n_pts;
+    int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool)
+    int pool, relu;
+    float *y;
+};
+
+// ---- thin PTX wrappers ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    // no-swizzle canonical layout: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version(1) <<46
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// kind::f16, BF16 x BF16 -> F32, M=128, N=128, A K-major, B MN-major
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (bf16 hi, bf16 lo) with hi + lo ~= x to 2^-17; packs two values per 32-bit word
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+    const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+__global__ void __launch_bounds__(TC_THREADS)
+tc_gemm_kernel(const TcGemmParams p) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_acc_full, s_acc_empty;
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&s_full[s], 129); mbar_init(&s_empty[s], 1); }  // 128 producers + thread 0's expect_tx arrive
+        mbar_init(&s_acc_full, 1);
+        mbar_init(&s_acc_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"((uint32_t)TC_BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    const int Nt = (p.N + TC_BN - 1) / TC_BN;
+    const long long total_tiles = (long long)p.G * Nt * p.Mt;
+    uint32_t chunk_ctr = 0;  // global k-chunk counter: stage = ctr % STAGES, phase = (ctr / STAGES) & 1
+    uint32_t tile_ctr = 0;
+
+    if (warp < 4) {
+        // =============================== producers + epilogue ===============================
+        const int t = threadIdx.x;
+        const int kk = t & 7;               // k row inside a group of 8
+        const int ng = warp * 4 + ((t >> 3) & 3);   // n group of 8 columns inside the tile
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
+            const int mt = (int)(tile % p.Mt);
+            const long long gn = tile / p.Mt;
+            const int nt = (int)(gn % Nt);
+            const int g = (int)(gn / Nt);
+            const int n0 = nt * TC_BN + ng * 8;  // first of this thread's 8 columns
+
+            // per-tile gather state
+            int pidx[8];
+            float cen[3] = {0.f, 0.f, 0.f};
+            if (p.mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + j;
+                    pidx[j] = 0;
+                    if (n < p.N) pidx[j] = p.idx ? __ldg(p.idx + (size_t)g * p.N + n) : (n % p.n_pts);
+                }
+            }
+            const float *xg = p.x + (size_t)g * p.x_group_stride;
+
+            for (int kc = 0; kc < p.Kc; ++kc, ++chunk_ctr) {
+                const int s = chunk_ctr % TC_STAGES;
+                const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
+                mbar_wait(&s_empty[s], ph ^ 1);
+                uint8_t *stage = tc_smem + (size_t)s * TC_STAGE_BYTES;
+                if (t == 0) {
+                    mbar_arrive_expect_tx(&s_full[s], 2 * TC_IMG);
+                    bulk_g2s(stage, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG, 2 * TC_IMG, &s_full[s]);
+                }
+                uint8_t *xhi = stage + 2 * TC_IMG, *xlo = stage + 3 * TC_IMG;
+#pragma unroll
+                for (int kb = 0; kb < TC_BK / 8; ++kb) {
+                    const int k = kc * TC_BK + kb * 8 + kk;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                    if (k < p.K) {
+                        if (p.mode == 0) {
+                            const float *row = xg + (size_t)k * p.x_row_stride + n0;
+                            if (n0 + 8 <= p.N && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                                const float4 a = __ldg(reinterpret_cast<const float4 *>(row));
+                                const float4 b = __ldg(reinterpret_cast<const float4 *>(row) + 1);
+                                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (n0 + j < p.N) v[j] = __ldg(row + j);
+                            }
+                        } else if (k < 3) {
+                            const float *pts = p.xyz + (size_t)g * p.n_pts * 3;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int n = n0 + j;
+                                if (n < p.N) {
+                                    float c = 0.f;
+                                    if (p.centres) c = __ldg(p.centres + ((size_t)g * (p.N / p.nsample) + n / p.nsample) * 3 + k);
+                                    v[j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), c);
+                                }
+                            }
+                        } else {
+                            const float *row = xg + (size_t)(k - 3) * p.x_row_stride;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (n0 + j < p.N) v[j] = __ldg(row + pidx[j]);
+                        }
+                    }
+                    uint4 h, l;
+                    split2(v[0], v[1], h.x, l.x);
+                    split2(v[2], v[3], h.y, l.y);
+                    split2(v[4], v[5], h.z, l.z);
+                    split2(v[6], v[7], h.w, l.w);
+                    const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)kb * TC_LBO + (uint32_t)kk * 16;
+                    *reinterpret_cast<uint4 *>(xhi + off) = h;
+                    *reinterpret_cast<uint4 *>(xlo + off) = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(&s_full[s]);
+            }
+
+            // ---- epilogue: one output channel per thread ----
+            mbar_wait(&s_acc_full, tile_ctr & 1);
+            tc_fence_after();
+            const int m = mt * TC_BM + warp * 32 + lane;
+            const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            if (p.out_mode == 0) {
+                float *yrow = p.y + ((size_t)g * p.M + m) * p.N + (size_t)nt * TC_BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (m < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float o = v[j] + bias;
+                            if (p.relu) o = fmaxf(o, 0.f);
+                            v[j] = o;
+                        }
+                        const int ncol = nt * TC_BN + c0;
+                        if (ncol + 32 <= p.N && ((reinterpret_cast<uintptr_t>(yrow + c0) & 15u) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ncol + j < p.N) yrow[c0 + j] = v[j];
+                        }
+                    }
+                }
+            } else {
+                const int groups_per_row = p.N / p.pool;
+                float *yrow = p.y + ((size_t)g * p.M + m) * groups_per_row;
+                float run = -INFINITY;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nt * TC_BN + c0 + j;
+                        if (n < p.N) {
+                            float o = v[j] + bias;
+                            if (p.relu) o = fmaxf(o, 0.f);
+                            run = fmaxf(run, o);
+                            if ((n + 1) % p.pool == 0) {
+                                if (m < p.M) {
+                                    // a pooling window may span several column tiles (pool > 128): combine with atomics-free
+                                    // read-modify-write is unnecessary because windows never exceed a tile when pool <= 128
+                                    yrow[n / p.pool] = run;
+                                }
+                                run = -INFINITY;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&s_acc_empty);
+        }
+    } else {
+      if (lane == 0) {
+        // =============================== MMA issuer ===============================
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
+            mbar_wait(&s_acc_empty, (tile_ctr & 1) ^ 1);
+            tc_fence_after();
+            for (int kc = 0; kc < p.Kc; ++kc, ++chunk_ctr) {
+                const int s = chunk_ctr % TC_STAGES;
+                const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
+                mbar_wait(&s_full[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(tc_smem + (size_t)s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int k16 = 0; k16 < TC_BK / 16; ++k16) {
+                    const uint32_t koff = (uint32_t)k16 * 2 * TC_LBO;
+                    const uint64_t whi = make_smem_desc(base + koff), wlo = make_smem_desc(base + TC_IMG + koff);
+                    const uint64_t xhi = make_smem_desc(base + 2 * TC_IMG + koff), xlo = make_smem_desc(base + 3 * TC_IMG + koff);
+                    umma_ss(tmem_base, whi, xhi, (kc | k16) != 0);
+                    umma_ss(tmem_base, wlo, xhi, 1);
+                    umma_ss(tmem_base, whi, xlo, 1);
+                }
+                umma_commit(&s_empty[s]);
+            }
+            umma_commit(&s_acc_full);
+        }
+      }
+      __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+    }
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
+                                        const float *x, long long x_group_stride, int x_row_stride, const int *idx,
+                                        const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
+                                        int pool, int relu, float *y, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(M > 0 && K > 0 && G >= 0 && N >= 0, "tc_mlp_layer: bad sizes");
+    if (G == 0 || N == 0) return JMB_OK;
+    JMB_REQUIRE(wpack && x && y, "tc_mlp_layer: null pointer");
+    JMB_REQUIRE(mode == 0 || mode == 1, "tc_mlp_layer: bad mode");
+    JMB_REQUIRE(mode == 0 || (xyz && n_pts > 0 && K >= 3 && (centres == nullptr || (nsample > 0 && N % nsample == 0))),
+                "tc_mlp_layer: gather mode needs xyz / nsample");
+    JMB_REQUIRE(out_mode == 0 || (pool > 0 && pool <= TC_BN && TC_BN % pool == 0 && N % pool == 0),
+                "tc_mlp_layer: pool must divide 128 and N");
+    TcGemmParams p;
+    p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
+    p.M = M; p.K = K; p.Mt = div_up(M, TC_BM); p.Kc = div_up(K, TC_BK);
+    p.G = G; p.N = N; p.mode = mode; p.x = x; p.x_group_stride = x_group_stride; p.x_row_stride = x_row_stride;
+    p.idx = idx; p.xyz = xyz; p.centres = centres; p.nsample = nsample; p.n_pts = n_pts;
+    p.out_mode = out_mode; p.pool = pool; p.relu = relu; p.y = y;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        JMB_CUDA(cudaGetDevice(&dev));
+        JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        JMB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long tiles = (long long)G * div_up(N, TC_BN) * p.Mt;
+    const int grid = (int)(tiles < (long long)sms * 3 ? tiles : (long long)sms * 3);
+    tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("tc_mlp_layer");
+}

@@ -1,0 +1,85 @@
+"""Host side of the tcgen05 MLP layer (jmodt_b200/csrc/tc_gemm.cu): weight packing and launch helpers.
+
+Weights are split once into bf16 hi/lo and rearranged into the exact shared-memory image the kernel's
+A-operand descriptors expect (K-major, no-swizzle core matrices of 8 rows x 16 bytes), so a pipeline
+stage is filled with ONE contiguous 16 KB bulk copy.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BM, BK = 128, 32
+
+
+class PackedLayer:
+    """bf16 hi/lo chunk images of one layer's weight (+ fp32 bias, zero padded to a multiple of 128)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool):
+        w = weight.detach().reshape(weight.shape[0], -1).float()
+        self.M, self.K = w.shape
+        Mt, Kc = -(-self.M // BM), -(-self.K // BK)
+        wp = torch.zeros(Mt * BM, Kc * BK, dtype=torch.float32, device=w.device)
+        wp[: self.M, : self.K] = w
+        hi = wp.to(torch.bfloat16)
+        lo = (wp - hi.float()).to(torch.bfloat16)
+
+        def image(t):  # (Mt*128, Kc*32) -> [Mt][Kc][k8=4][m8=16][mr=8][kr=8]
+            return t.view(Mt, 16, 8, Kc, 4, 8).permute(0, 3, 4, 1, 2, 5)
+
+        self.wpack = torch.stack((image(hi), image(lo)), dim=2).contiguous()  # [Mt][Kc][2][4][16][8][8]
+        b = torch.zeros(Mt * BM, dtype=torch.float32, device=w.device)
+        if bias is not None:
+            b[: self.M] = bias.detach().float()
+        self.bias = b
+        self.relu = bool(relu)
+
+
+def fold_conv_bn(conv, bn=None):
+    """Eval-mode BatchNorm folded into the preceding 1x1 conv: returns (weight (Cout, Cin), bias (Cout))."""
+    w = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None]
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None = None,
+              pool: int = 0) -> torch.Tensor:
+    """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0."""
+    assert x.dim() == 3 and x.is_contiguous() and x.dtype == torch.float32
+    G, K, N = x.shape
+    assert K == layer.K
+    shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
+    y = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
+    st = _lib.stream_and_device(x)
+    _lib.check(_lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
+                                           x.data_ptr(), K * N, N, None, None, None, 0, 0,
+                                           1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
+               "tc_mlp_layer")
+    return y
+
+
+def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tensor | None,
+                        idx: torch.Tensor | None, centres: torch.Tensor | None, nsample: int,
+                        *, pool: int = 0) -> torch.Tensor:
+    """First SharedMLP layer fused with QueryAndGroup / GroupAll (pointnet2_utils.py:231-290).
+    xyz (G, n_pts, 3); feats (G, C, n_pts) or None; idx (G, npoint, nsample) int32 or None (GroupAll);
+    centres (G, npoint, 3) or None.  Returns (G, M, npoint * nsample) (or pooled)."""
+    G, n_pts, _ = xyz.shape
+    C = 0 if feats is None else feats.shape[1]
+    assert layer.K == 3 + C
+    N = idx.shape[1] * idx.shape[2] if idx is not None else n_pts
+    shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
+    y = torch.empty(shape, dtype=torch.float32, device=xyz.device)
+    st = _lib.stream_and_device(xyz)
+    fx = feats if feats is not None else xyz  # never dereferenced for rows >= 3 when C == 0
+    _lib.check(_lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, layer.K, G, N, 1,
+                                           fx.data_ptr(), C * n_pts, n_pts, _lib.ptr(idx), xyz.data_ptr(),
+                                           _lib.ptr(centres), nsample if centres is not None else 0, n_pts,
+                                           1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
+               "tc_mlp_layer(grouped)")
+    return y
