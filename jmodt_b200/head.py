@@ -1,0 +1,206 @@
+"""Region-proposal fusion head: the per-proposal RCNN network and the link / start-end heads.
+
+Mirror of the reference `RCNN` module (jmodt/detection/modeling/rcnn.py:11-134 construction, :158-202 and
+:288-289 eval forward) with the same sub-module names and state_dict keys, so a reference checkpoint's
+`rcnn_net.*` tensors load key for key.  forward() is the sm_100a path only: RoI pooling + canonical
+transform (one kernel), FPS / ball-query kernels, and every 1x1-conv layer on tcgen05 tensor cores
+(jmodt_b200/csrc/tc_gemm.cu) with the grouping fused into the first layer's operand staging and the
+max-pool fused into the last layer's epilogue.  There is no torch/cuDNN fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import tc
+from .pointnet2 import pointnet2_utils as pu
+from .pointnet2 import pytorch_utils as pt_utils
+from .pointnet2.pointnet2_modules import PointnetSAModule
+from .roipool3d import roipool3d_utils
+
+
+@dataclass
+class HeadConfig:
+    """The cfg.RCNN / cfg.REID values the head depends on (reference jmodt/config.py:100-168)."""
+    use_intensity: bool = False          # RCNN.USE_INTENSITY
+    use_mask: bool = True                # RCNN.USE_MASK
+    use_depth: bool = True               # RCNN.USE_DEPTH
+    pool_extra_width: float = 0.2        # RCNN.POOL_EXTRA_WIDTH
+    num_points: int = 512                # RCNN.NUM_POINTS
+    xyz_up_layer: List[int] = field(default_factory=lambda: [128, 128])
+    sa_npoints: List[int] = field(default_factory=lambda: [128, 32, -1])
+    sa_radius: List[float] = field(default_factory=lambda: [0.2, 0.4, 100])
+    sa_nsample: List[int] = field(default_factory=lambda: [64, 64, 64])
+    sa_mlps: List[List[int]] = field(default_factory=lambda: [[128, 128, 128], [128, 128, 256], [256, 256, 512]])
+    cls_fc: List[int] = field(default_factory=lambda: [512, 512])
+    reg_fc: List[int] = field(default_factory=lambda: [512, 512])
+    link_fc: List[int] = field(default_factory=lambda: [512, 512])
+    se_fc: List[int] = field(default_factory=lambda: [512, 512])
+    loc_scope: float = 1.5
+    loc_bin_size: float = 0.5
+    num_head_bin: int = 9
+    dp_ratio: float = 0.0
+    use_bn: bool = False
+
+    @property
+    def reg_channel(self) -> int:       # rcnn.py:72-76 with LOC_Y_BY_BIN=False
+        per_loc_bin_num = int(self.loc_scope / self.loc_bin_size) * 2
+        return per_loc_bin_num * 4 + self.num_head_bin * 2 + 3 + 1
+
+
+def _fc_stack(c_in: int, hidden: List[int], c_out: int, bn: bool, dp: float) -> nn.Sequential:
+    """Conv1d stack with a Dropout inserted at index 1, exactly as rcnn.py:45-53 builds cls/reg/link/se."""
+    layers, pre = [], c_in
+    for h in hidden:
+        layers.append(pt_utils.Conv1d(pre, h, bn=bn))
+        pre = h
+    layers.append(pt_utils.Conv1d(pre, c_out, activation=None))
+    if dp >= 0:
+        layers.insert(1, nn.Dropout(dp))
+    return nn.Sequential(*layers)
+
+
+def _pack_stack(seq) -> List[tc.PackedLayer]:
+    """Fold every conv(+BN)(+ReLU) block of a SharedMLP / Conv1d stack into a PackedLayer."""
+    packed = []
+    for blk in seq:
+        if isinstance(blk, nn.Dropout):
+            assert blk.p == 0.0 or not blk.training
+            continue
+        bn = blk.bn.bn if hasattr(blk, "bn") else None
+        w, b = tc.fold_conv_bn(blk.conv, bn)
+        packed.append(tc.PackedLayer(w, b, relu=hasattr(blk, "activation")))
+    return packed
+
+
+def run_stack(packed: List[tc.PackedLayer], x: torch.Tensor, pool: int = 0) -> torch.Tensor:
+    for i, layer in enumerate(packed):
+        x = tc.mlp_layer(layer, x, pool=pool if i == len(packed) - 1 else 0)
+    return x
+
+
+class RCNN(nn.Module):
+    def __init__(self, num_classes: int = 2, input_channels: int = 128, use_xyz: bool = True, mode: str = "TEST",
+                 cfg: HeadConfig | None = None):
+        super().__init__()
+        self.cfg = cfg = cfg or HeadConfig()
+        self.mode = mode
+        self.rcnn_input_channel = 3 + int(cfg.use_intensity) + int(cfg.use_mask) + int(cfg.use_depth)
+        self.xyz_up_layer = pt_utils.SharedMLP([self.rcnn_input_channel] + cfg.xyz_up_layer, bn=cfg.use_bn)
+        c_out = cfg.xyz_up_layer[-1]
+        self.merge_down_layer = pt_utils.SharedMLP([c_out * 2, c_out], bn=cfg.use_bn)
+
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels
+        for k in range(len(cfg.sa_npoints)):
+            mlps = [channel_in] + list(cfg.sa_mlps[k])
+            npoint = cfg.sa_npoints[k] if cfg.sa_npoints[k] != -1 else None
+            self.SA_modules.append(PointnetSAModule(npoint=npoint, radius=cfg.sa_radius[k], nsample=cfg.sa_nsample[k],
+                                                    mlp=mlps, use_xyz=use_xyz, bn=cfg.use_bn))
+            channel_in = mlps[-1]
+        cls_channel = 1 if num_classes == 2 else num_classes
+        self.cls_layer = _fc_stack(channel_in, cfg.cls_fc, cls_channel, cfg.use_bn, cfg.dp_ratio)
+        self.reg_layer = _fc_stack(channel_in, cfg.reg_fc, cfg.reg_channel, cfg.use_bn, cfg.dp_ratio)
+        self.link_layer = _fc_stack(channel_in, cfg.link_fc, 1, cfg.use_bn, cfg.dp_ratio)
+        self.se_layer = _fc_stack(channel_in, cfg.se_fc, 1, cfg.use_bn, cfg.dp_ratio)
+        self.init_weights()
+        self._packed = None
+
+    def init_weights(self):  # rcnn.py:116-134, weight_init='xavier'
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv1d)):
+                nn.init.xavier_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        nn.init.normal_(self.reg_layer[-1].conv.weight, mean=0, std=0.001)
+
+    # ---- packing ----------------------------------------------------------------------------
+    def pack(self):
+        """(Re)build the tensor-core weight images from the current parameters (call after loading weights)."""
+        self._packed = {
+            "xyz_up": _pack_stack(self.xyz_up_layer), "merge_down": _pack_stack(self.merge_down_layer),
+            "sa": [_pack_stack(sa.mlps[0]) for sa in self.SA_modules],
+            "cls": _pack_stack(self.cls_layer), "reg": _pack_stack(self.reg_layer),
+            "link": _pack_stack(self.link_layer), "se": _pack_stack(self.se_layer),
+        }
+        return self._packed
+
+    @property
+    def packed(self):
+        return self._packed if self._packed is not None else self.pack()
+
+    # ---- forward ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def pool_rois(self, input_data):
+        """ProposalTargetLayer.forward eval branch (proposal_target_layer.py:17-34, 99-115)."""
+        cfg = self.cfg
+        extra = [input_data["seg_mask"].unsqueeze(2)]
+        if cfg.use_depth:
+            extra.append((input_data["pts_depth"] / 70.0 - 0.5).unsqueeze(2))
+        pts_feature = torch.cat(extra + [input_data["rpn_features"]], dim=2)
+        pooled, empty = roipool3d_utils.roipool3d_gpu_canonical(input_data["rpn_xyz"], pts_feature,
+                                                                input_data["roi_boxes3d"], cfg.pool_extra_width,
+                                                                sampled_pt_num=cfg.num_points)
+        return pooled.view(-1, pooled.shape[2], pooled.shape[3]), empty
+
+    @torch.no_grad()
+    def forward_points(self, pts_input: torch.Tensor):
+        """rcnn.py:172-202 on pts_input (G, 512, 3 + extra + C): returns rcnn_cls (G,1), rcnn_reg (G,46), rcnn_feat (G,512,1)."""
+        P = self.packed
+        cin = self.rcnn_input_channel
+        xyz = pts_input[..., 0:3].contiguous()
+        xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()                   # (G, 5, 512)
+        rpn_feature = pts_input[..., cin:].transpose(1, 2)                                # (G, 128, 512)
+        xyz_feature = run_stack(P["xyz_up"], xyz_input)
+        merged = run_stack(P["merge_down"], torch.cat((xyz_feature, rpn_feature), dim=1).contiguous())
+        l_xyz, l_feat = xyz, merged
+        for sa, packed in zip(self.SA_modules, P["sa"]):
+            grouper = sa.groupers[0]
+            if sa.npoint is not None:
+                fidx = pu.farthest_point_sample(l_xyz, sa.npoint)
+                new_xyz = pu.gather_operation(l_xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+                idx = pu.ball_query(grouper.radius, grouper.nsample, l_xyz, new_xyz)
+                h = tc.grouped_first_layer(packed[0], l_xyz, l_feat, idx, new_xyz, grouper.nsample)
+                pool = grouper.nsample
+            else:                                                                         # GroupAll
+                new_xyz = None
+                h = tc.grouped_first_layer(packed[0], l_xyz, l_feat, None, None, 0)
+                pool = l_xyz.shape[1]
+            for i, layer in enumerate(packed[1:]):
+                h = tc.mlp_layer(layer, h, pool=pool if i == len(packed) - 2 else 0)
+            l_xyz, l_feat = new_xyz, h
+        # heads: one column per proposal
+        feat_t = l_feat.squeeze(-1).t().contiguous().unsqueeze(0)                         # (1, 512, G)
+        rcnn_cls = run_stack(P["cls"], feat_t)[0].t().contiguous()                        # (G, 1)
+        rcnn_reg = run_stack(P["reg"], feat_t)[0].t().contiguous()                        # (G, 46)
+        return rcnn_cls, rcnn_reg, l_feat
+
+    @torch.no_grad()
+    def forward(self, input_data):
+        """Eval path of rcnn.py:158-202,288-289.  input_data: rpn_xyz (B,N,3), rpn_features (B,N,C),
+        seg_mask (B,N), pts_depth (B,N), roi_boxes3d (B,M,7)."""
+        pts_input, empty = self.pool_rois(input_data)
+        rcnn_cls, rcnn_reg, feat = self.forward_points(pts_input)
+        return {"rcnn_cls": rcnn_cls, "rcnn_reg": rcnn_reg, "rcnn_feat": feat, "pooled_empty_flag": empty}
+
+
+@torch.no_grad()
+def affinity(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
+    """Link and start/end scores between two sets of proposal features (reference tracker.py:81-112; the
+    training twin is rcnn.py:239-258).  pred_features (P, 512), det_features (D, 512) ->
+    link_scores (P, D) = (softmax_row + softmax_col) / 2, start (D,), end (P,) (after sigmoid),
+    plus the raw link logits (P, D)."""
+    P, D = pred_features.shape[0], det_features.shape[0]
+    packed = rcnn.packed
+    pt, dt = pred_features.t().contiguous(), det_features.t().contiguous()               # (512, P), (512, D)
+    cor = (pt.unsqueeze(2) - dt.unsqueeze(1)).abs()                                       # (512, P, D)
+    logits = run_stack(packed["link"], cor.view(1, -1, P * D))[0].view(P, D)
+    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
+    start_in = cor.mean(dim=1).unsqueeze(0).contiguous()                                  # (1, 512, D)
+    end_in = cor.mean(dim=2).unsqueeze(0).contiguous()                                    # (1, 512, P)
+    start = torch.sigmoid(run_stack(packed["se"], start_in)).flatten()
+    end = torch.sigmoid(run_stack(packed["se"], end_in)).flatten()
+    return link, start, end, logits

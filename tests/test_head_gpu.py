@@ -1,0 +1,88 @@
+"""Fusion head (per-proposal RCNN network, link / start-end affinity) on tcgen05 vs the torch fp32 restatement
+of the reference forward (oracle/modules_ref.py, TF32 disabled).  north_star tolerance: logits within 1e-4
+relative (normwise: max abs error / max abs reference)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _rel(got, want):
+    return (got.double() - want.double()).abs().max().item() / (want.double().abs().max().item() + 1e-12)
+
+
+def _frame_inputs(cuda, B, seed):
+    from jmodt_b200 import synth
+    batch = synth.make_batch(seed, B, with_image=False)
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.from_numpy(batch["pts"]).to(cuda)
+    return {"rpn_xyz": pts, "rpn_features": torch.randn(B, 16384, 128, generator=g).to(cuda),
+            "seg_mask": (torch.rand(B, 16384, generator=g) > 0.5).float().to(cuda),
+            "pts_depth": torch.norm(pts, p=2, dim=2), "roi_boxes3d": torch.from_numpy(batch["rois"]).to(cuda)}
+
+
+def test_rcnn_head_matches_torch_reference(cuda):
+    from jmodt_b200.head import RCNN
+    from jmodt_b200.pointnet2 import pointnet2_utils as pu
+    from oracle import modules_ref
+    torch.manual_seed(0)
+    rcnn = RCNN().to(cuda).eval()
+    with torch.no_grad():
+        for p in rcnn.parameters():            # biases are zero-initialised in the reference; make them matter
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    rcnn.pack()
+    inp = _frame_inputs(cuda, 1, 3)
+    inp["roi_boxes3d"] = inp["roi_boxes3d"][:, :24].contiguous()
+    pts_input, empty = rcnn.pool_rois(inp)
+    assert pts_input.shape == (24, 512, 133)
+    cls, reg, feat = rcnn.forward_points(pts_input)
+    with torch.no_grad():
+        wcls, wreg, wfeat = modules_ref.rcnn_forward_points(rcnn, pts_input, pu.farthest_point_sample, pu.ball_query)
+    assert cls.shape == (24, 1) and reg.shape == (24, 46) and feat.shape == (24, 512, 1)
+    assert _rel(feat, wfeat) < 1e-4, _rel(feat, wfeat)
+    assert _rel(cls, wcls) < 1e-4, _rel(cls, wcls)
+    assert _rel(reg, wreg) < 1e-4, _rel(reg, wreg)
+    out = rcnn(inp)
+    assert torch.equal(out["rcnn_feat"], feat) and out["pooled_empty_flag"].shape == (1, 24)
+
+
+def test_affinity_matches_torch_reference(cuda):
+    from jmodt_b200.head import RCNN, affinity
+    from oracle import modules_ref
+    torch.manual_seed(1)
+    rcnn = RCNN().to(cuda).eval()
+    with torch.no_grad():
+        for p in rcnn.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    rcnn.pack()
+    g = torch.Generator().manual_seed(5)
+    for P, D in [(128, 128), (37, 50), (1, 3)]:
+        pf = torch.randn(P, 512, generator=g).abs().to(cuda)     # rcnn_feat is post-ReLU / max-pool: non-negative
+        df = (pf[torch.randint(0, P, (D,), generator=g)] + 0.1 * torch.randn(D, 512, generator=g).to(cuda)).abs()
+        link, start, end, logits = affinity(rcnn, pf, df)
+        with torch.no_grad():
+            wl, ws, we, wlog = modules_ref.affinity(rcnn.link_layer, rcnn.se_layer, pf, df)
+        assert link.shape == (P, D) and start.shape == (D,) and end.shape == (P,)
+        assert _rel(logits, wlog) < 1e-4, _rel(logits, wlog)
+        assert _rel(link, wl) < 1e-4 and _rel(start, ws) < 1e-4 and _rel(end, we) < 1e-4
+
+
+def test_state_dict_keys_match_reference_layout(cuda):
+    from jmodt_b200.head import RCNN
+    keys = set(RCNN().state_dict())
+    for k in ["xyz_up_layer.layer0.conv.weight", "xyz_up_layer.layer1.conv.bias", "merge_down_layer.layer0.conv.weight",
+              "SA_modules.0.mlps.0.layer0.conv.weight", "SA_modules.2.mlps.0.layer2.conv.bias",
+              "cls_layer.0.conv.weight", "cls_layer.2.conv.weight", "cls_layer.3.conv.bias",
+              "reg_layer.3.conv.weight", "link_layer.0.conv.weight", "link_layer.3.conv.weight", "se_layer.2.conv.bias"]:
+        assert k in keys, k
+    assert RCNN().reg_layer[-1].conv.weight.shape == (46, 512, 1)
