@@ -162,6 +162,13 @@ JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K,
                              const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
                              int pool, int relu, float *y, void *stream);
 
+/* ---- LI-Fusion image feature sampling ---------------------------------------------------- */
+
+/* replaces feature_gather (jmodt/detection/modeling/backbone.py:79-89): bilinear grid_sample with
+ * align_corners=True and zero padding.  fmap (b,c,h,w), xy (b,n,2) in [-1,1] -> out (b,c,n). */
+JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *fmap, const float *xy,
+                               float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,8 +287,11 @@ tc_gemm_kernel(const TcGemmParams p) {
                     }
                 }
             } else {
+                // max-pool over windows of `pool` columns (pool divides 128; windows never straddle a tile).
+                // N % pool == 0, so a window is either fully inside [0, N) or fully outside.
                 const int groups_per_row = p.N / p.pool;
-                float *yrow = p.y + ((size_t)g * p.M + m) * groups_per_row;
+                float *yrow = p.y + ((size_t)g * p.M + m) * groups_per_row + (size_t)(nt * TC_BN) / p.pool;
+                const int sub = p.pool < 32 ? p.pool : 32;      // window length inside one 32-column chunk
                 float run = -INFINITY;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TC_BN; c0 += 32) {
@@ -296,19 +299,26 @@ tc_gemm_kernel(const TcGemmParams p) {
                     tmem_ld32(taddr + c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int n = nt * TC_BN + c0 + j;
-                        if (n < p.N) {
-                            float o = v[j] + bias;
-                            if (p.relu) o = fmaxf(o, 0.f);
-                            run = fmaxf(run, o);
-                            if ((n + 1) % p.pool == 0) {
-                                if (m < p.M) {
-                                    // a pooling window may span several column tiles (pool > 128): combine with atomics-free
-                                    // read-modify-write is unnecessary because windows never exceed a tile when pool <= 128
-                                    yrow[n / p.pool] = run;
-                                }
-                                run = -INFINITY;
-                            }
+                        const float o = v[j] + bias;
+                        v[j] = p.relu ? fmaxf(o, 0.f) : o;
+                    }
+                    if (sub == 32) {
+                        float mx = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                        run = fmaxf(run, mx);
+                        if ((c0 + 32) % p.pool == 0) {
+                            const int w = (c0 + 32) / p.pool - 1;
+                            if (m < p.M && nt * TC_BN + c0 < p.N) yrow[w] = run;
+                            run = -INFINITY;
+                        }
+                    } else {
+                        for (int w0 = 0; w0 < 32; w0 += sub) {
+                            float mx = -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j >= w0 && j < w0 + sub) mx = fmaxf(mx, v[j]);
+                            if (m < p.M && nt * TC_BN + c0 + w0 < p.N) yrow[(c0 + w0) / p.pool] = mx;
                         }
                     }
                 }

@@ -1,0 +1,399 @@
+"""RPN backbone with LI-Fusion, RPN heads, proposal layer and the PointRCNN wrapper — the callers of the
+hot path, mirrored from the reference with the same sub-module
+names / state_dict keys:
+
+    PointNet2MSG, BasicBlock, IALayer, AttentionFusion, feature_gather   jmodt/detection/modeling/backbone.py
+    RPN                                                                  jmodt/detection/modeling/rpn.py
+    ProposalLayer, decode_bbox_target                                    jmodt/detection/layers/proposal_layer.py,
+                                                                         jmodt/utils/bbox_transform.py:27-260
+    PointRCNN                                                            jmodt/detection/modeling/point_rcnn.py
+
+Inference only.  Point-cloud ops and every 1x1-conv / Linear layer on the point path run on this package's
+sm_100a kernels.  The 3x3 image conv / deconv stack (backbone.py:15-30,130-139,187-193) stays on cuDNN: it is
+row (f)1 of SURVEY §8 ("next"), outside the hot-path scope of this round.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, box_utils, tc
+from .head import RCNN, HeadConfig, affinity
+from .iou3d import iou3d_cuda
+from .pointnet2 import pytorch_utils as pt_utils
+from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+
+
+@dataclass
+class RpnConfig:
+    """cfg.RPN / cfg.LI_FUSION / cfg.EVAL values used at inference (reference jmodt/config.py:34-98, 200-208)."""
+    input_channels: int = 0
+    sa_npoints: List[int] = field(default_factory=lambda: [4096, 1024, 256, 64])
+    sa_radius: List[List[float]] = field(default_factory=lambda: [[0.1, 0.5], [0.5, 1.0], [1.0, 2.0], [2.0, 4.0]])
+    sa_nsample: List[List[int]] = field(default_factory=lambda: [[16, 32]] * 4)
+    sa_mlps: List[List[List[int]]] = field(default_factory=lambda: [[[16, 16, 32], [32, 32, 64]],
+                                                                    [[64, 64, 128], [64, 96, 128]],
+                                                                    [[128, 196, 256], [128, 196, 256]],
+                                                                    [[256, 256, 512], [256, 384, 512]]])
+    fp_mlps: List[List[int]] = field(default_factory=lambda: [[128, 128], [256, 256], [512, 512], [512, 512]])
+    cls_fc: List[int] = field(default_factory=lambda: [128])
+    reg_fc: List[int] = field(default_factory=lambda: [128])
+    dp_ratio: float = 0.5
+    use_bn: bool = True
+    loc_scope: float = 3.0
+    loc_bin_size: float = 0.5
+    num_head_bin: int = 12
+    score_thresh: float = 0.2
+    li_fusion: bool = True
+    img_channels: List[int] = field(default_factory=lambda: [3, 64, 128, 256, 512])
+    point_channels: List[int] = field(default_factory=lambda: [96, 256, 512, 1024])
+    deconv_reduce: List[int] = field(default_factory=lambda: [16, 16, 16, 16])
+    deconv_kernels: List[int] = field(default_factory=lambda: [2, 4, 8, 16])
+    img_features_channel: int = 128
+    nms_type: str = "normal"
+    pre_nms_top_n: int = 9000
+    post_nms_top_n: int = 100
+    nms_thresh: float = 0.8
+    mean_size: tuple = (1.52563191462, 1.62856739989, 3.88311640418)
+
+    @property
+    def reg_channel(self) -> int:       # rpn.py:32-37 with LOC_XZ_FINE
+        return int(self.loc_scope / self.loc_bin_size) * 2 * 4 + self.num_head_bin * 2 + 3 + 1
+
+
+def feature_gather(feature_map: torch.Tensor, xy: torch.Tensor) -> torch.Tensor:
+    """backbone.py:79-89 on the sm_100a kernel: feature_map (B,C,H,W), xy (B,N,2) in [-1,1] -> (B,C,N)."""
+    B, C, H, W = feature_map.shape
+    N = xy.shape[1]
+    fm, g = feature_map.float().contiguous(), xy.contiguous()
+    out = torch.empty((B, C, N), dtype=torch.float32, device=fm.device)
+    st = _lib.stream_and_device(fm)
+    _lib.check(_lib.lib().jmb_feature_gather(B, C, H, W, N, fm.data_ptr(), g.data_ptr(), out.data_ptr(), st),
+               "feature_gather")
+    return out
+
+
+class BasicBlock(nn.Module):
+    """backbone.py:15-30 (cuDNN; image stack is out of this round's scope)."""
+
+    def __init__(self, in_channels, out_channels, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=2 * stride, padding=1, bias=False)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.bn1(self.conv1(x))))
+
+
+class IALayer(nn.Module):
+    """backbone.py:33-58"""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.ic, self.pc = channels
+        rc = self.pc // 4
+        self.conv1 = nn.Sequential(nn.Conv1d(self.ic, self.pc, 1), nn.BatchNorm1d(self.pc), nn.ReLU())
+        self.fc1 = nn.Linear(self.ic, rc)
+        self.fc2 = nn.Linear(self.pc, rc)
+        self.fc3 = nn.Linear(rc, 1)
+        self._packed = None
+
+    def train(self, mode: bool = True):
+        self._packed = None
+        return super().train(mode)
+
+    def pack(self):
+        w, b = tc.fold_conv_bn(self.conv1[0], self.conv1[1])
+        self._packed = {"conv1": tc.PackedLayer(w, b, True),
+                        "fc1": tc.PackedLayer(self.fc1.weight, self.fc1.bias, False),
+                        "fc2": tc.PackedLayer(self.fc2.weight, self.fc2.bias, False),
+                        "fc3": tc.PackedLayer(self.fc3.weight, self.fc3.bias, False)}
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, img_feas, point_feas):
+        P = self._packed or self.pack()
+        img_feas, point_feas = img_feas.contiguous(), point_feas.contiguous()
+        ri = tc.mlp_layer(P["fc1"], img_feas)                       # (B, rc, N)
+        rp = tc.mlp_layer(P["fc2"], point_feas)
+        att = torch.sigmoid(tc.mlp_layer(P["fc3"], torch.tanh(ri + rp)))   # (B, 1, N)
+        return tc.mlp_layer(P["conv1"], img_feas) * att
+
+
+class AttentionFusion(nn.Module):
+    """backbone.py:61-76"""
+
+    def __init__(self, img_in_channels, pc_in_channels, out_channels):
+        super().__init__()
+        self.IA_Layer = IALayer(channels=[img_in_channels, pc_in_channels])
+        self.conv1 = nn.Conv1d(pc_in_channels + pc_in_channels, out_channels, 1)
+        self.bn1 = nn.BatchNorm1d(out_channels)
+        self._packed = None
+
+    def train(self, mode: bool = True):
+        self._packed = None
+        return super().train(mode)
+
+    @torch.no_grad()
+    def forward(self, point_features, img_features):
+        if self._packed is None:
+            w, b = tc.fold_conv_bn(self.conv1, self.bn1)
+            self._packed = tc.PackedLayer(w, b, True)
+        img_features = self.IA_Layer(img_features, point_features)
+        return tc.mlp_layer(self._packed, torch.cat([point_features, img_features], dim=1).contiguous())
+
+
+class PointNet2MSG(nn.Module):
+    """backbone.py:92-198"""
+
+    def __init__(self, input_channels=0, use_xyz=True, cfg: RpnConfig | None = None):
+        super().__init__()
+        self.cfg = cfg = cfg or RpnConfig()
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels
+        skip_channel_list = [input_channels]
+        channel_out = 0
+        for k in range(len(cfg.sa_npoints)):
+            mlps = [[channel_in] + list(m) for m in cfg.sa_mlps[k]]
+            channel_out = sum(m[-1] for m in mlps)
+            self.SA_modules.append(PointnetSAModuleMSG(npoint=cfg.sa_npoints[k], radii=cfg.sa_radius[k],
+                                                       nsamples=cfg.sa_nsample[k], mlps=mlps, use_xyz=use_xyz,
+                                                       bn=cfg.use_bn))
+            skip_channel_list.append(channel_out)
+            channel_in = channel_out
+        if cfg.li_fusion:
+            self.Img_Block = nn.ModuleList()
+            self.Fusion_Conv = nn.ModuleList()
+            self.DeConv = nn.ModuleList()
+            for i in range(len(cfg.img_channels) - 1):
+                self.Img_Block.append(BasicBlock(cfg.img_channels[i], cfg.img_channels[i + 1], stride=1))
+                self.Fusion_Conv.append(AttentionFusion(cfg.img_channels[i + 1], cfg.point_channels[i],
+                                                        cfg.point_channels[i]))
+                self.DeConv.append(nn.ConvTranspose2d(cfg.img_channels[i + 1], cfg.deconv_reduce[i],
+                                                      kernel_size=cfg.deconv_kernels[i], stride=cfg.deconv_kernels[i]))
+            self.image_fusion_conv = nn.Conv2d(sum(cfg.deconv_reduce), cfg.img_features_channel // 4, kernel_size=1)
+            self.image_fusion_bn = nn.BatchNorm2d(cfg.img_features_channel // 4)
+            self.final_fusion_img_point = AttentionFusion(cfg.img_features_channel // 4, cfg.img_features_channel,
+                                                          cfg.img_features_channel)
+        self.FP_modules = nn.ModuleList()
+        for k in range(len(cfg.fp_mlps)):
+            pre_channel = cfg.fp_mlps[k + 1][-1] if k + 1 < len(cfg.fp_mlps) else channel_out
+            self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(cfg.fp_mlps[k])))
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    @torch.no_grad()
+    def image_features(self, image):
+        """The cuDNN image stack: the four Img_Block maps and the fused de-convolved map
+        (backbone.py:170,187-193).  Out of the hot-path scope."""
+        maps, x = [], image
+        for blk in self.Img_Block:
+            x = blk(x)
+            maps.append(x)
+        de = torch.cat([dc(m) for dc, m in zip(self.DeConv, maps)], dim=1)
+        fused = F.relu(self.image_fusion_bn(self.image_fusion_conv(de)))
+        return maps, fused
+
+    @torch.no_grad()
+    def forward(self, pc, image=None, xy=None, image_maps=None):
+        """image_maps = (maps, fused) from image_features() may be passed to skip the image stack."""
+        xyz, features = self._break_up_pc(pc)
+        l_xyz, l_features, l_xy = [xyz], [features], [xy]
+        if self.cfg.li_fusion and image_maps is None:
+            image_maps = self.image_features(image)
+        for i, sa in enumerate(self.SA_modules):
+            li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i])
+            if self.cfg.li_fusion:
+                li_xy = torch.gather(l_xy[i], 1, li_index.long().unsqueeze(-1).repeat(1, 1, 2))
+                img_gather = feature_gather(image_maps[0][i], li_xy)
+                li_features = self.Fusion_Conv[i](li_features, img_gather)
+                l_xy.append(li_xy)
+            l_xyz.append(li_xyz)
+            l_features.append(li_features)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        if self.cfg.li_fusion:
+            l_features[0] = self.final_fusion_img_point(l_features[0], feature_gather(image_maps[1], xy))
+        return l_xyz[0], l_features[0]
+
+
+class RPN(nn.Module):
+    """rpn.py:13-87"""
+
+    def __init__(self, use_xyz=True, mode="TEST", cfg: RpnConfig | None = None):
+        super().__init__()
+        self.cfg = cfg = cfg or RpnConfig()
+        self.backbone_net = PointNet2MSG(input_channels=cfg.input_channels, use_xyz=use_xyz, cfg=cfg)
+
+        def head(hidden, c_out):
+            layers, pre = [], cfg.fp_mlps[0][-1]
+            for h in hidden:
+                layers.append(pt_utils.Conv1d(pre, h, bn=cfg.use_bn))
+                pre = h
+            layers.append(pt_utils.Conv1d(pre, c_out, activation=None))
+            if cfg.dp_ratio >= 0:
+                layers.insert(1, nn.Dropout(cfg.dp_ratio))
+            return nn.Sequential(*layers)
+
+        self.rpn_cls_layer = head(cfg.cls_fc, 1)
+        self.rpn_reg_layer = head(cfg.reg_fc, cfg.reg_channel)
+        self.proposal_layer = ProposalLayer(mode=mode, cfg=cfg)
+        nn.init.constant_(self.rpn_cls_layer[2].conv.bias, -np.log((1 - 0.01) / 0.01))    # rpn.py:62-64
+        nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
+        self._packed = None
+
+    def train(self, mode: bool = True):
+        self._packed = None
+        return super().train(mode)
+
+    @torch.no_grad()
+    def forward(self, input_data, image_maps=None):
+        from .head import _pack_stack, run_stack
+        if self._packed is None:
+            self._packed = (_pack_stack(self.rpn_cls_layer), _pack_stack(self.rpn_reg_layer))
+        xyz, feats = self.backbone_net(input_data["pts_input"], input_data.get("img"), input_data.get("pts_xy"),
+                                       image_maps=image_maps)
+        rpn_cls = run_stack(self._packed[0], feats).transpose(1, 2).contiguous()     # (B, N, 1)
+        rpn_reg = run_stack(self._packed[1], feats).transpose(1, 2).contiguous()     # (B, N, 76)
+        return {"rpn_cls": rpn_cls, "rpn_reg": rpn_reg, "backbone_xyz": xyz, "backbone_features": feats}
+
+
+def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size):
+    """bbox_transform.py:27-260 for the configuration the detector runs with: BBOX_AVG_BY_BIN=True,
+    get_xz_fine=True, get_y_by_bin=False, RY_WITH_BIN=False, get_ry_fine=False (config.py:193-208).
+    roi_box3d (N, 3|7), pred_reg (N, C) -> (N, 7) [x, y, z, h, w, l, ry]."""
+    per_loc_bin_num = int(loc_scope / loc_bin_size) * 2
+    nb = per_loc_bin_num
+    pred_x_bin = F.softmax(pred_reg[:, 0:nb], 1)
+    pred_z_bin = F.softmax(pred_reg[:, nb:2 * nb], 1)
+    centers = (torch.arange(nb, device=pred_reg.device).float() * loc_bin_size + loc_bin_size / 2 - loc_scope)
+    pred_x_abs = centers + pred_reg[:, 2 * nb:3 * nb] * loc_bin_size
+    pred_z_abs = centers + pred_reg[:, 3 * nb:4 * nb] * loc_bin_size
+    pos_x = (pred_x_abs * pred_x_bin).sum(dim=1)
+    pos_z = (pred_z_abs * pred_z_bin).sum(dim=1)
+    start = 4 * nb
+    pos_y = roi_box3d[:, 1] + pred_reg[:, start]
+    start += 1
+    ry_bin = torch.argmax(pred_reg[:, start:start + num_head_bin], dim=1)
+    ry_res_norm = torch.gather(pred_reg[:, start + num_head_bin:start + 2 * num_head_bin], 1,
+                               ry_bin.unsqueeze(1)).squeeze(1)
+    angle_per_class = (2 * np.pi) / num_head_bin
+    ry = (ry_bin.float() * angle_per_class + ry_res_norm * (angle_per_class / 2)) % (2 * np.pi)
+    ry[ry > np.pi] -= 2 * np.pi
+    size_l = start + 2 * num_head_bin
+    size_res_norm = pred_reg[:, size_l:size_l + 3]
+    hwl = size_res_norm * anchor_size + anchor_size
+    roi_center = roi_box3d[:, 0:3]
+    shift_ret = torch.cat((pos_x.view(-1, 1), pos_y.view(-1, 1), pos_z.view(-1, 1), hwl, ry.view(-1, 1)), dim=1)
+    ret = shift_ret
+    if roi_box3d.shape[1] == 7:
+        roi_ry = roi_box3d[:, 6]
+        ret = box_utils.rotate_pc_along_y_torch(shift_ret.unsqueeze(1), -roi_ry).squeeze(1)
+        ret[:, 6] += roi_ry
+    ret[:, [0, 2]] += roi_center[:, [0, 2]]
+    return ret
+
+
+class ProposalLayer(nn.Module):
+    """proposal_layer.py:10-121 (distance-based proposal, axis-aligned or rotated NMS on the device)."""
+
+    def __init__(self, mode="TEST", cfg: RpnConfig | None = None):
+        super().__init__()
+        self.mode, self.cfg = mode, cfg or RpnConfig()
+
+    @torch.no_grad()
+    def forward(self, rpn_scores, rpn_reg, xyz):
+        cfg = self.cfg
+        B = xyz.shape[0]
+        mean_size = torch.tensor(cfg.mean_size, dtype=torch.float32, device=xyz.device)
+        proposals = decode_bbox_target(xyz.view(-1, 3), rpn_reg.view(-1, rpn_reg.shape[-1]), cfg.loc_scope,
+                                       cfg.loc_bin_size, cfg.num_head_bin, mean_size)
+        proposals[:, 1] += proposals[:, 3] / 2
+        proposals = proposals.view(B, -1, 7)
+        _, sorted_idxs = torch.sort(rpn_scores, dim=1, descending=True)
+        ret_bbox3d = rpn_scores.new_zeros(B, cfg.post_nms_top_n, 7)
+        ret_scores = rpn_scores.new_zeros(B, cfg.post_nms_top_n)
+        for k in range(B):
+            s, p = self.distance_based_proposal(rpn_scores[k], proposals[k], sorted_idxs[k])
+            ret_bbox3d[k, :p.size(0)] = p
+            ret_scores[k, :p.size(0)] = s
+        return ret_bbox3d, ret_scores
+
+    def distance_based_proposal(self, scores, proposals, order):
+        cfg = self.cfg
+        nms_range_list = [0, 40.0, 80.0]
+        pre_top_n_list = [0, int(cfg.pre_nms_top_n * 0.7), cfg.pre_nms_top_n - int(cfg.pre_nms_top_n * 0.7)]
+        post_top_n_list = [0, int(cfg.post_nms_top_n * 0.7), cfg.post_nms_top_n - int(cfg.post_nms_top_n * 0.7)]
+        scores_ordered, proposals_ordered = scores[order], proposals[order]
+        dist = proposals_ordered[:, 2]
+        first_mask = (dist > nms_range_list[0]) & (dist <= nms_range_list[1])
+        out_s, out_p = [], []
+        for i in range(1, len(nms_range_list)):
+            dist_mask = (dist > nms_range_list[i - 1]) & (dist <= nms_range_list[i])
+            if dist_mask.sum() != 0:
+                cur_scores = scores_ordered[dist_mask][:pre_top_n_list[i]]
+                cur_proposals = proposals_ordered[dist_mask][:pre_top_n_list[i]]
+            else:
+                if i == 1:
+                    continue
+                cur_scores = scores_ordered[first_mask][pre_top_n_list[i - 1]:][:pre_top_n_list[i]]
+                cur_proposals = proposals_ordered[first_mask][pre_top_n_list[i - 1]:][:pre_top_n_list[i]]
+            boxes_bev = box_utils.boxes3d_to_bev_torch(cur_proposals).contiguous()
+            # cur_scores are already sorted (a masked slice of a sorted list); the reference re-sorts them
+            # (iou3d_utils.py:82), which is the identity for distinct scores.
+            sorder = cur_scores.sort(0, descending=True)[1]
+            keep, num = iou3d_cuda.nms_device(boxes_bev[sorder].contiguous(), cfg.nms_thresh,
+                                              cfg.nms_type == "rotate", max_keep=post_top_n_list[i])
+            keep_idx = sorder[keep[:int(num.item())]]
+            out_s.append(cur_scores[keep_idx])
+            out_p.append(cur_proposals[keep_idx])
+        return torch.cat(out_s, dim=0), torch.cat(out_p, dim=0)
+
+
+class PointRCNN(nn.Module):
+    """point_rcnn.py:9-72 (eval path)."""
+
+    def __init__(self, num_classes=2, use_xyz=True, mode="TEST", rpn_cfg: RpnConfig | None = None,
+                 head_cfg: HeadConfig | None = None):
+        super().__init__()
+        self.mode = mode
+        self.rpn = RPN(use_xyz=use_xyz, mode=mode, cfg=rpn_cfg)
+        self.rcnn_net = RCNN(num_classes=num_classes, input_channels=128, use_xyz=use_xyz, mode=mode, cfg=head_cfg)
+
+    @torch.no_grad()
+    def forward(self, input_data, image_maps=None, rois=None):
+        """input_data: pts_input (B,N,3), img (B,3,384,1280), pts_xy (B,N,2).  `rois` (B,M,7) may be injected
+        to bypass the proposal layer."""
+        output = {}
+        rpn_output = self.rpn(input_data, image_maps=image_maps)
+        output.update(rpn_output)
+        backbone_xyz, backbone_features = rpn_output["backbone_xyz"], rpn_output["backbone_features"]
+        rpn_scores_raw = rpn_output["rpn_cls"][:, :, 0]
+        seg_mask = (torch.sigmoid(rpn_scores_raw) > self.rpn.cfg.score_thresh).float()
+        pts_depth = torch.norm(backbone_xyz, p=2, dim=2)
+        if rois is None:
+            rois, roi_scores_raw = self.rpn.proposal_layer(rpn_scores_raw, rpn_output["rpn_reg"], backbone_xyz)
+            output["roi_scores_raw"] = roi_scores_raw
+        output["rois"] = rois
+        output["seg_result"] = seg_mask
+        rcnn_input = {"rpn_xyz": backbone_xyz, "rpn_features": backbone_features.permute(0, 2, 1),
+                      "seg_mask": seg_mask, "roi_boxes3d": rois, "pts_depth": pts_depth}
+        output.update(self.rcnn_net(rcnn_input))
+        return output
+
+    @torch.no_grad()
+    def pair_affinity(self, rcnn_feat, rois_per_frame):
+        """Link / start-end scores between consecutive frames (t, t+1) of a batch: rcnn_feat (B*M, 512, 1)."""
+        f = rcnn_feat.view(-1, rois_per_frame, rcnn_feat.shape[1])
+        return [affinity(self.rcnn_net, f[i], f[i + 1]) for i in range(0, f.shape[0] - 1, 2)]

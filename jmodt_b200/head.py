@@ -117,6 +117,10 @@ class RCNN(nn.Module):
                     nn.init.constant_(m.bias, 0)
         nn.init.normal_(self.reg_layer[-1].conv.weight, mean=0, std=0.001)
 
+    def train(self, mode: bool = True):
+        self._packed = None
+        return super().train(mode)
+
     # ---- packing ----------------------------------------------------------------------------
     def pack(self):
         """(Re)build the tensor-core weight images from the current parameters (call after loading weights)."""

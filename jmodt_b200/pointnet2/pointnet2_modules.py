@@ -15,6 +15,24 @@ import torch.nn.functional as F
 
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
+from .. import tc
+
+
+def _use_fused(module: nn.Module) -> bool:
+    """Inference (eval mode, no autograd) runs the fused tcgen05 path; training keeps the differentiable
+    composition of the individual ops."""
+    return bool(getattr(module, "fused", True)) and not module.training and not torch.is_grad_enabled()
+
+
+def pack_shared_mlp(mlp) -> list:
+    """SharedMLP -> list of tc.PackedLayer with eval-mode BatchNorm folded in (pytorch_utils.py:36-102)."""
+    packed = []
+    for blk in mlp:
+        assert not hasattr(blk, "in"), "instance norm is not supported by the fused path"
+        bn = blk.bn.bn if hasattr(blk, "bn") else None
+        w, b = tc.fold_conv_bn(blk.conv, bn)
+        packed.append(tc.PackedLayer(w, b, relu=hasattr(blk, "activation")))
+    return packed
 
 
 class _PointnetSAModuleBase(nn.Module):
@@ -36,6 +54,9 @@ class _PointnetSAModuleBase(nn.Module):
             new_xyz = pointnet2_utils.gather_operation(
                 xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
 
+        if _use_fused(self) and self.pool_method == 'max_pool':
+            return new_xyz, self._forward_fused(xyz, features, new_xyz), idx
+
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
             grouped = mlp(grouper(xyz, new_xyz, features))  # (B, mlp[-1], npoint, nsample)
@@ -47,6 +68,38 @@ class _PointnetSAModuleBase(nn.Module):
                 raise NotImplementedError
             pooled.append(grouped.squeeze(-1))  # (B, mlp[-1], npoint)
         return new_xyz, torch.cat(pooled, dim=1), idx
+
+
+    def train(self, mode: bool = True):
+        self._packed = None          # weights may change: re-pack on the next fused forward
+        return super().train(mode)
+
+    # ---- fused inference path: grouping fused into the first layer, max-pool into the last ----------
+    def pack(self):
+        self._packed = [pack_shared_mlp(m) for m in self.mlps]
+        return self._packed
+
+    def _forward_fused(self, xyz, features, new_xyz):
+        packed = getattr(self, "_packed", None) or self.pack()
+        outs = []
+        if features is not None:
+            features = features.contiguous()
+        for grouper, layers in zip(self.groupers, packed):
+            if isinstance(grouper, pointnet2_utils.QueryAndGroup):
+                assert grouper.use_xyz, "the fused path groups xyz with the features"
+                idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+                pool = grouper.nsample
+                h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
+                                           pool=pool if len(layers) == 1 else 0)
+            else:  # GroupAll
+                pool = xyz.shape[1]
+                assert pool <= 128 and 128 % pool == 0, "GroupAll fused path: point count must divide 128"
+                h = tc.grouped_first_layer(layers[0], xyz, features, None, None, 0,
+                                           pool=pool if len(layers) == 1 else 0)
+            for i, layer in enumerate(layers[1:]):
+                h = tc.mlp_layer(layer, h, pool=pool if i == len(layers) - 2 else 0)
+            outs.append(h)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):
@@ -84,6 +137,10 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn, activation=activation)
 
+    def train(self, mode: bool = True):
+        self._packed = None
+        return super().train(mode)
+
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
                 known_feats: torch.Tensor) -> torch.Tensor:
         """
@@ -98,4 +155,12 @@ class PointnetFPModule(nn.Module):
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
+        if _use_fused(self):
+            packed = getattr(self, "_packed", None)
+            if packed is None:
+                packed = self._packed = pack_shared_mlp(self.mlp)
+            h = new_features.contiguous()
+            for layer in packed:
+                h = tc.mlp_layer(layer, h)
+            return h
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)

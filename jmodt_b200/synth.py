@@ -114,3 +114,26 @@ def nudge_off_box_faces(pts, boxes_enlarged, margin=1e-4):
     out = pts.copy()
     out[bad, 1] += 50.0
     return out
+
+
+def fill_deterministic(module, seed: int = 0):
+    """Fills every parameter / buffer of a torch module with values that depend only on the tensor's NAME and
+    shape (not on construction order), so the reference modules and this package's mirrors can be given
+    identical weights without shipping checkpoints.  Used by tests/golden/make_golden_modules.py and the tests."""
+    import zlib
+
+    import torch
+    with torch.no_grad():
+        for name, t in module.state_dict().items():
+            if name.endswith("num_batches_tracked"):
+                continue
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+            if name.endswith("running_var") or (t.dim() == 1 and name.endswith("weight")):
+                v = torch.rand(t.shape, generator=g) + 0.5
+            elif t.dim() == 1:
+                v = torch.randn(t.shape, generator=g) * 0.1
+            else:
+                fan_in = int(np.prod(t.shape[1:]))
+                v = torch.randn(t.shape, generator=g) / float(np.sqrt(max(fan_in, 1)))
+            t.copy_(v.to(t.dtype))
+    return module

@@ -1,0 +1,149 @@
+"""This package's sm_100a path against outputs of the REAL reference modules (tests/golden/ref_modules.npz,
+generated on CPU by tests/golden/make_golden_modules.py from /root/reference with name-hashed weights), plus
+fused-vs-unfused checks of the set-abstraction / feature-propagation modules.  fp32 tolerance from north_star:
+1e-4 relative (normwise)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+G = np.load(os.path.join(ROOT, "tests", "golden", "ref_modules.npz"))
+
+
+def _rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / (np.abs(want).max() + 1e-12)
+
+
+def test_state_dict_keys_equal_the_reference():
+    """Not a GPU test: the drop-in contract on parameter names."""
+    from jmodt_b200.detector import PointNet2MSG
+    from jmodt_b200.head import RCNN
+    assert list(PointNet2MSG(input_channels=0).state_dict().keys()) == json.loads(str(G["keys_backbone"]))
+    assert list(RCNN().state_dict().keys()) == json.loads(str(G["keys_rcnn"]))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+@pytest.mark.gpu
+def test_attention_fusion_vs_reference(cuda):
+    from jmodt_b200.detector import AttentionFusion
+    from jmodt_b200.synth import fill_deterministic
+    af = fill_deterministic(AttentionFusion(64, 96, 96)).to(cuda).eval()
+    out = af(torch.from_numpy(G["af_point"]).to(cuda), torch.from_numpy(G["af_img"]).to(cuda))
+    assert _rel(out.cpu().numpy(), G["af_out"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_feature_gather_vs_reference(cuda):
+    from jmodt_b200.detector import feature_gather
+    out = feature_gather(torch.from_numpy(G["fg_map"]).to(cuda), torch.from_numpy(G["fg_xy"]).to(cuda))
+    np.testing.assert_allclose(out.cpu().numpy(), G["fg_out"], atol=2e-6, rtol=1e-5)
+    assert (G["fg_out"] == 0).any() and (G["fg_out"] != 0).any()      # covers out-of-image taps
+
+
+@pytest.mark.gpu
+def test_decode_bbox_target_vs_reference(cuda):
+    from jmodt_b200.detector import RpnConfig, decode_bbox_target
+    cfg = RpnConfig()
+    out = decode_bbox_target(torch.from_numpy(G["dec_xyz"]).to(cuda), torch.from_numpy(G["dec_reg"]).to(cuda),
+                             cfg.loc_scope, cfg.loc_bin_size, cfg.num_head_bin,
+                             torch.tensor(cfg.mean_size, dtype=torch.float32, device=cuda))
+    np.testing.assert_allclose(out.cpu().numpy(), G["dec_out"], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_rcnn_dense_layers_and_affinity_vs_reference(cuda):
+    from jmodt_b200.head import RCNN, affinity, run_stack
+    from jmodt_b200.synth import fill_deterministic
+    rcnn = fill_deterministic(RCNN()).to(cuda).eval()
+    P = rcnn.pack()
+    pts = torch.from_numpy(G["rcnn_pts_input"]).to(cuda)
+    xyz_feature = run_stack(P["xyz_up"], pts[..., 0:5].transpose(1, 2).contiguous())
+    merged = run_stack(P["merge_down"], torch.cat((xyz_feature, pts[..., 5:].transpose(1, 2)), 1).contiguous())
+    assert _rel(merged.cpu().numpy(), G["rcnn_merged"]) < 1e-4
+    feat_t = torch.from_numpy(G["rcnn_feat"]).to(cuda).squeeze(-1).t().contiguous().unsqueeze(0)
+    assert _rel(run_stack(P["cls"], feat_t)[0].t().cpu().numpy(), G["rcnn_cls"]) < 1e-4
+    assert _rel(run_stack(P["reg"], feat_t)[0].t().cpu().numpy(), G["rcnn_reg"]) < 1e-4
+    link, start, end, logits = affinity(rcnn, torch.from_numpy(G["aff_pred"]).to(cuda),
+                                        torch.from_numpy(G["aff_det"]).to(cuda))
+    assert _rel(logits.cpu().numpy(), G["aff_logits"]) < 1e-4
+    assert _rel(link.cpu().numpy(), G["aff_link"]) < 1e-4
+    assert _rel(start.cpu().numpy(), G["aff_start"]) < 1e-4 and _rel(end.cpu().numpy(), G["aff_end"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_fp_shared_mlp_with_bn_vs_reference(cuda):
+    from jmodt_b200.detector import PointNet2MSG
+    from jmodt_b200.pointnet2.pointnet2_modules import pack_shared_mlp
+    from jmodt_b200.synth import fill_deterministic
+    from jmodt_b200 import tc
+    fp = fill_deterministic(PointNet2MSG(input_channels=0).FP_modules[0]).to(cuda).eval()
+    h = torch.from_numpy(G["fp_in"]).to(cuda)
+    for layer in pack_shared_mlp(fp.mlp):
+        h = tc.mlp_layer(layer, h)
+    assert _rel(h.cpu().numpy(), G["fp_out"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_sa_msg_and_fp_fused_equal_unfused_composition(cuda):
+    """Fused inference path (grouping in the first layer's operand staging, max-pool in the last epilogue) vs the
+    reference composition ball_query -> group -> SharedMLP(cuDNN fp32) -> max_pool of the same module."""
+    from jmodt_b200.pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+    from jmodt_b200.synth import fill_deterministic, make_batch
+    pts = torch.from_numpy(make_batch(11, 2, with_image=False)["pts"]).to(cuda)
+    feats = torch.randn(2, 96, 16384, device=cuda)
+    sa = fill_deterministic(PointnetSAModuleMSG(npoint=1024, radii=[0.5, 1.0], nsamples=[16, 32],
+                                                mlps=[[96, 64, 64, 128], [96, 64, 96, 128]], bn=True)).to(cuda).eval()
+    with torch.no_grad():
+        new_xyz, fused, idx = sa(pts, feats)
+        sa.fused = False
+        new_xyz2, unfused, idx2 = sa(pts, feats)
+    assert torch.equal(idx, idx2) and torch.equal(new_xyz, new_xyz2) and fused.shape == (2, 256, 1024)
+    assert _rel(fused.cpu().numpy(), unfused.cpu().numpy()) < 1e-4
+    sa0 = fill_deterministic(PointnetSAModuleMSG(npoint=4096, radii=[0.1, 0.5], nsamples=[16, 32],
+                                                 mlps=[[0, 16, 16, 32], [0, 32, 32, 64]], bn=True)).to(cuda).eval()
+    with torch.no_grad():
+        _, f0, _ = sa0(pts, None)
+        sa0.fused = False
+        _, u0, _ = sa0(pts, None)
+    assert _rel(f0.cpu().numpy(), u0.cpu().numpy()) < 1e-4
+    fp = fill_deterministic(PointnetFPModule(mlp=[256 + 96, 128, 128])).to(cuda).eval()
+    with torch.no_grad():
+        a = fp(pts, new_xyz, feats, fused)
+        fp.fused = False
+        b = fp(pts, new_xyz, feats, fused)
+    assert a.shape == (2, 128, 16384) and _rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_point_rcnn_end_to_end_runs_and_is_consistent(cuda):
+    """Whole pipeline on 2 synthetic frames: shapes of the reference output dict (point_rcnn.py:23-72), the proposal
+    layer's zero-padding contract, and RCNN outputs equal to running the head on the same rois again."""
+    from jmodt_b200.detector import PointRCNN, RpnConfig
+    from jmodt_b200.synth import fill_deterministic, make_batch
+    cfg = RpnConfig(post_nms_top_n=128)
+    model = fill_deterministic(PointRCNN(rpn_cfg=cfg)).to(cuda).eval()
+    b = make_batch(40, 2)
+    inp = {"pts_input": torch.from_numpy(b["pts"]).to(cuda), "img": torch.from_numpy(b["img"]).to(cuda),
+           "pts_xy": torch.from_numpy(b["pts_xy"]).to(cuda)}
+    out = model(inp)
+    assert out["rpn_cls"].shape == (2, 16384, 1) and out["rpn_reg"].shape == (2, 16384, 76)
+    assert out["backbone_features"].shape == (2, 128, 16384) and out["rois"].shape == (2, 128, 7)
+    assert out["rcnn_cls"].shape == (256, 1) and out["rcnn_reg"].shape == (256, 46) and out["rcnn_feat"].shape == (256, 512, 1)
+    for k in ("rpn_cls", "rpn_reg", "rcnn_cls", "rcnn_reg", "rcnn_feat"):
+        assert torch.isfinite(out[k]).all(), k
+    out2 = model(inp, rois=out["rois"])
+    assert torch.equal(out2["rcnn_feat"], out["rcnn_feat"])
+    res = model.pair_affinity(out["rcnn_feat"], 128)
+    assert len(res) == 1 and res[0][0].shape == (128, 128) and res[0][1].shape == (128,)
+    assert torch.allclose(res[0][0].sum(), torch.tensor(128.0, device=cuda), atol=1e-2)   # (rowsoftmax+colsoftmax)/2
