@@ -88,12 +88,12 @@ class RCNN(nn.Module):
         super().__init__()
         self.cfg = cfg = cfg or HeadConfig()
         self.mode = mode
+        self.SA_modules = nn.ModuleList()      # registered first, as in rcnn.py:16 (state_dict key order)
         self.rcnn_input_channel = 3 + int(cfg.use_intensity) + int(cfg.use_mask) + int(cfg.use_depth)
         self.xyz_up_layer = pt_utils.SharedMLP([self.rcnn_input_channel] + cfg.xyz_up_layer, bn=cfg.use_bn)
         c_out = cfg.xyz_up_layer[-1]
         self.merge_down_layer = pt_utils.SharedMLP([c_out * 2, c_out], bn=cfg.use_bn)
 
-        self.SA_modules = nn.ModuleList()
         channel_in = input_channels
         for k in range(len(cfg.sa_npoints)):
             mlps = [channel_in] + list(cfg.sa_mlps[k])
