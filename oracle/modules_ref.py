@@ -60,3 +60,80 @@ def affinity(link_layer, se_layer, pred_features, det_features):
     start = torch.sigmoid(se_layer(cor_feat.mean(dim=0).unsqueeze(-1))).flatten()
     end = torch.sigmoid(se_layer(cor_feat.mean(dim=1).unsqueeze(-1))).flatten()
     return link, start, end, logits
+
+
+# --------------------------------------------------------------------------------------------------
+# RPN backbone on the CPU: reference forward (backbone.py:159-198, pointnet2_modules.py:20-63,135-164)
+# composed from the C oracle's index ops (oracle/cref.py) and torch-CPU layers.  `net` is a module tree
+# with the reference's sub-module names (the reference's own PointNet2MSG or this repo's mirror, on CPU).
+# --------------------------------------------------------------------------------------------------
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def sa_msg_forward(sa, xyz, features, cref):
+    """pointnet2_modules.py:20-63 for one PointnetSAModuleMSG; xyz (B,N,3) torch CPU."""
+    import numpy as np
+    idx = torch.from_numpy(cref.fps(_np(xyz), sa.npoint))
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+    outs = []
+    for grouper, mlp in zip(sa.groupers, sa.mlps):
+        bidx = torch.from_numpy(cref.ball_query(grouper.radius, grouper.nsample, _np(xyz), _np(new_xyz)))
+        B, m, ns = bidx.shape
+        flat = bidx.long().view(B, 1, m * ns)
+        gx = torch.gather(xyz.transpose(1, 2), 2, flat.expand(-1, 3, -1)).view(B, 3, m, ns)
+        gx = gx - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is not None:
+            gf = torch.gather(features, 2, flat.expand(-1, features.shape[1], -1)).view(B, -1, m, ns)
+            gx = torch.cat([gx, gf], dim=1)
+        h = mlp(gx)
+        outs.append(F.max_pool2d(h, kernel_size=[1, h.size(3)]).squeeze(-1))
+    return new_xyz, torch.cat(outs, dim=1), idx
+
+
+def fp_forward(fp, unknown, known, unknow_feats, known_feats, cref):
+    """pointnet2_modules.py:135-164"""
+    d2, idx = cref.three_nn(_np(unknown), _np(known))
+    dist = torch.sqrt(torch.from_numpy(d2))
+    dist_recip = 1.0 / (dist + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+    interp = torch.from_numpy(cref.three_interpolate(_np(known_feats), idx, _np(weight)))
+    new_features = interp if unknow_feats is None else torch.cat([interp, unknow_feats], dim=1)
+    return fp.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+
+def ia_fusion_forward(fusion, point_features, img_features):
+    """backbone.py:45-76 with plain torch ops on the module's parameters."""
+    ia = fusion.IA_Layer
+    batch = img_features.size(0)
+    img_f = img_features.transpose(1, 2).contiguous().view(-1, ia.ic)
+    pt_f = point_features.transpose(1, 2).contiguous().view(-1, ia.pc)
+    att = torch.sigmoid(ia.fc3(torch.tanh(ia.fc1(img_f) + ia.fc2(pt_f)))).squeeze(1).view(batch, 1, -1)
+    c, bn = ia.conv1[0], ia.conv1[1]
+    img_new = F.relu(F.batch_norm(F.conv1d(img_features, c.weight, c.bias), bn.running_mean, bn.running_var,
+                                  bn.weight, bn.bias, False, 0.0, bn.eps))
+    fused = torch.cat([point_features, img_new * att], dim=1)
+    b1 = fusion.bn1
+    return F.relu(F.batch_norm(F.conv1d(fused, fusion.conv1.weight, fusion.conv1.bias), b1.running_mean,
+                               b1.running_var, b1.weight, b1.bias, False, 0.0, b1.eps))
+
+
+def grid_gather(feature_map, xy):
+    """backbone.py:79-89"""
+    return F.grid_sample(feature_map.float(), xy.unsqueeze(1), align_corners=True).squeeze(2)
+
+
+def backbone_forward(net, xyz, xy, image_maps, cref):
+    """backbone.py:159-198 given the image stack's outputs (maps per level, fused map)."""
+    l_xyz, l_features, l_xy = [xyz], [None], [xy]
+    for i, sa in enumerate(net.SA_modules):
+        li_xyz, li_features, li_index = sa_msg_forward(sa, l_xyz[i], l_features[i], cref)
+        li_xy = torch.gather(l_xy[i], 1, li_index.long().unsqueeze(-1).repeat(1, 1, 2))
+        li_features = ia_fusion_forward(net.Fusion_Conv[i], li_features, grid_gather(image_maps[0][i], li_xy))
+        l_xy.append(li_xy)
+        l_xyz.append(li_xyz)
+        l_features.append(li_features)
+    for i in range(-1, -(len(net.FP_modules) + 1), -1):
+        l_features[i - 1] = fp_forward(net.FP_modules[i], l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i], cref)
+    l_features[0] = ia_fusion_forward(net.final_fusion_img_point, l_features[0], grid_gather(image_maps[1], xy))
+    return l_xyz[0], l_features[0]

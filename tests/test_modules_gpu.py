@@ -147,3 +147,24 @@ def test_point_rcnn_end_to_end_runs_and_is_consistent(cuda):
     res = model.pair_affinity(out["rcnn_feat"], 128)
     assert len(res) == 1 and res[0][0].shape == (128, 128) and res[0][1].shape == (128,)
     assert torch.allclose(res[0][0].sum(), torch.tensor(128.0, device=cuda), atol=1e-2)   # (rowsoftmax+colsoftmax)/2
+
+
+@pytest.mark.gpu
+def test_rpn_backbone_vs_cpu_oracle(cuda, cref):
+    """Whole RPN point path (4x SA-MSG + LI-Fusion + 4x FP + final fusion) on the sm_100a kernels against the CPU
+    restatement (C-oracle index ops + torch-CPU layers) on a reduced cloud (2048 points, scaled-down sampling)."""
+    from jmodt_b200.detector import PointNet2MSG, RpnConfig
+    from jmodt_b200.synth import fill_deterministic, make_batch
+    from oracle import modules_ref
+    cfg = RpnConfig(sa_npoints=[512, 128, 32, 16])
+    net = fill_deterministic(PointNet2MSG(input_channels=0, cfg=cfg)).eval()
+    b = make_batch(60, 1, n_points=2048, n_rois=16, empty_rois=0)
+    xyz, xy, img = torch.from_numpy(b["pts"]), torch.from_numpy(b["pts_xy"]), torch.from_numpy(b["img"])[:, :, :96, :320].contiguous()
+    with torch.no_grad():
+        maps_cpu = net.image_features(img)
+        want_xyz, want = modules_ref.backbone_forward(net, xyz, xy, maps_cpu, cref)
+    net_gpu = net.to(cuda)
+    maps_gpu = ([m.to(cuda) for m in maps_cpu[0]], maps_cpu[1].to(cuda))     # same image maps on both sides
+    got_xyz, got = net_gpu(xyz.to(cuda), None, xy.to(cuda), image_maps=maps_gpu)
+    assert torch.equal(got_xyz.cpu(), want_xyz) and got.shape == (1, 128, 2048)
+    assert _rel(got.cpu().numpy(), want.numpy()) < 1e-4
