@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step (BASELINE config 3 uses 8)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ops", choices=["ops"])
+    ap.add_argument("--workload", default="e2e", choices=["e2e", "ops"],
+                    help="e2e: RPN point path + proposal layer + RoI pooling + per-proposal RCNN + pair affinity "
+                         "(BASELINE config 3); ops: the bare jmodt/ops suite (BASELINE config 2)")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -85,12 +87,10 @@ class OpsSuite:
         from jmodt_b200.roipool3d import roipool3d_utils as ru
         self.torch, self.pu, self.ru, self.iou, self.iouc = torch, pu, ru, iou3d_utils, iou3d_cuda
         self.dev, self.frames = dev, frames
-        self.launches = 0
         self.kernel_ms = {}
         self.timing = False
 
     def _t(self, name, fn, launches=1):
-        self.launches += launches
         if not self.timing:
             return fn()
         torch = self.torch
@@ -148,6 +148,72 @@ class OpsSuite:
         fin = self._t("nms_rotated", lambda: self.iouc.nms_device(d["final_bev"], 0.1, True), 2)
         return {"empty": empty, "keep_num": torch.stack([k[1] for k in keeps]), "iou": ious,
                 "final_num": fin[1], "pooled": pooled}
+
+
+
+class FusionE2E:
+    """BASELINE config 3: end-to-end region-proposal fusion + link / start-end affinity on `frames` frames.
+    Per step: RPN point path (4x SA-MSG with LI-Fusion on precomputed image feature maps, 4x FP, final fusion,
+    cls/reg heads) -> seg mask / depth -> ProposalLayer (decode + distance-binned NMS) -> RoI pooling + canonical
+    transform -> per-proposal RCNN (xyz_up, merge_down, 3x SA, cls/reg) -> link / start-end affinity of the frame
+    pairs (0,1),(2,3),...  The 3x3 image conv/deconv stack runs ONCE outside the timed region (cuDNN),
+    and the RCNN stage consumes the synthetic cluster RoIs while the proposal layer still runs
+    on the RPN outputs inside the step."""
+
+    def __init__(self, dev, frames, host_np):
+        import torch
+        from jmodt_b200 import tc
+        from jmodt_b200.detector import PointRCNN, RpnConfig
+        from jmodt_b200.synth import fill_deterministic
+        self.torch, self.tc, self.dev, self.frames = torch, tc, dev, frames
+        torch.manual_seed(0)
+        self.model = fill_deterministic(PointRCNN(rpn_cfg=RpnConfig(post_nms_top_n=N_ROI))).to(dev).eval()
+        with torch.no_grad():
+            img = torch.from_numpy(host_np["img"]).to(dev)
+            maps, fused = self.model.rpn.backbone_net.image_features(img)
+            self.image_maps = ([m.contiguous() for m in maps], fused.contiguous())
+        del img
+        self.launches = 0
+        self.kernel_ms = {}
+        self.timing = False
+
+    def _t(self, name, fn):
+        if not self.timing:
+            return fn()
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.kernel_ms.setdefault(name, []).append((e0, e1))
+        return out
+
+    def step(self, d):
+        torch, m = self.torch, self.model
+        inp = {"pts_input": d["pts"], "pts_xy": d["pts_xy"]}
+        rpn = self._t("rpn_point_path", lambda: m.rpn(inp, image_maps=self.image_maps))
+        scores = rpn["rpn_cls"][:, :, 0]
+        seg_mask = (torch.sigmoid(scores) > m.rpn.cfg.score_thresh).float()
+        depth = torch.norm(rpn["backbone_xyz"], p=2, dim=2)
+        prop, prop_scores = self._t("proposal_layer", lambda: m.rpn.proposal_layer(scores, rpn["rpn_reg"], rpn["backbone_xyz"]))
+        rc_in = {"rpn_xyz": rpn["backbone_xyz"], "rpn_features": rpn["backbone_features"].permute(0, 2, 1),
+                 "seg_mask": seg_mask, "roi_boxes3d": d["rois"], "pts_depth": depth}
+        pts_input, empty = self._t("roipool3d", lambda: m.rcnn_net.pool_rois(rc_in))
+        cls, reg, feat = self._t("rcnn_per_proposal", lambda: m.rcnn_net.forward_points(pts_input))
+        aff = self._t("pair_affinity", lambda: m.pair_affinity(feat, N_ROI))
+        return {"rcnn_cls": cls, "rcnn_reg": reg, "proposals": prop, "empty": empty,
+                "link": torch.stack([a[0] for a in aff]), "start": torch.stack([a[1] for a in aff]),
+                "end": torch.stack([a[2] for a in aff])}
+
+
+def make_inputs_e2e(first_frame, frames):
+    from jmodt_b200 import synth
+    batch = synth.make_batch(first_frame, frames, with_image=True)
+    return {"pts": batch["pts"], "pts_xy": batch["pts_xy"], "rois": batch["rois"], "img": batch["img"]}
+
+
+def to_device_e2e(host, dev, torch, non_blocking=True):
+    return {k: host[k].to(dev, non_blocking=non_blocking) for k in ("pts", "pts_xy", "rois")}
 
 
 def to_device(host, dev, torch, non_blocking=True):
@@ -211,22 +277,27 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from jmodt_b200 import _lib
+    from jmodt_b200 import _lib, tc
     _lib.lib()  # fail loudly if the CUDA library is missing: there is no fallback
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.frames
-    # frames shard across ranks: rank r owns frames [r*B, (r+1)*B) of the synthetic sequence (weak scaling)
-    host_np = make_inputs(rank * B, B)
-    host = {k: ([torch.from_numpy(x).pin_memory() for x in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
-            for k, v in host_np.items()}
-    suite = OpsSuite(dev, B)
-    d = to_device(host, dev, torch)
+    e2e_mode = args.workload == "e2e"
+    # frames shard across ranks: rank r owns frames [r*B, (r+1)*B) of the synthetic sequence (weak scaling);
+    # no data-path collective is needed (affinity pairs (2k, 2k+1) never straddle a shard because B is even)
+    host_np = make_inputs_e2e(rank * B, B) if e2e_mode else make_inputs(rank * B, B)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    host = {k: ([pin(x) for x in v] if isinstance(v, list) else pin(v)) for k, v in host_np.items() if k != "img"}
+    suite = FusionE2E(dev, B, host_np) if e2e_mode else OpsSuite(dev, B)
+    upload = to_device_e2e if e2e_mode else to_device
+    d = upload(host, dev, torch)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
@@ -238,8 +309,10 @@ def run_b200(args):
     for _ in range(args.warmup):
         suite.step(d)
     barrier()
-    suite.launches = 0
     suite.timing = True
+    tc.profiler.reset()
+    tc.profiler.enabled = True
+    launches0 = _lib.launch_count
     sampler = ClockSampler(local)
     sampler.start()
     evs = []
@@ -255,19 +328,23 @@ def run_b200(args):
     barrier()
     wall_s = time.perf_counter() - t_wall
     clocks = sampler.stop()
+    launches = _lib.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
-    launches = suite.launches
     kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in suite.kernel_ms.items()}
     kernel_calls = {k: len(v) / args.steps for k, v in suite.kernel_ms.items()}
+    tc_sum = tc.profiler.summary()
+    tc.profiler.enabled = False
     suite.timing = False
 
     # ---- e2e: same work through the public API with HOST (pinned) inputs and a host read of the results
     def e2e_step():
-        dd = to_device(host, dev, torch)
+        dd = upload(host, dev, torch)
         out = suite.step(dd)
-        res = [out["empty"].cpu(), out["keep_num"].cpu(), out["final_num"].cpu()] + [x.cpu() for x in out["iou"]]
-        return res
+        if e2e_mode:
+            keys = ("rcnn_cls", "rcnn_reg", "proposals", "empty", "link", "start", "end")
+            return [out[k].cpu() for k in keys]
+        return [out["empty"].cpu(), out["keep_num"].cpu(), out["final_num"].cpu()] + [x.cpu() for x in out["iou"]]
     for _ in range(2):
         e2e_step()
     barrier()
@@ -279,7 +356,7 @@ def run_b200(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
-    h2d = sum(int(np.prod(x.shape)) * 4 for k, v in host_np.items() for x in (v if isinstance(v, list) else [v]))
+    h2d = sum(int(t.numel() * t.element_size()) for v in host.values() for t in (v if isinstance(v, list) else [v]))
     d2h = sum(int(t.numel() * t.element_size()) for t in res)
 
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -296,33 +373,55 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        rp_ms = kernel_ms.get("roipool3d", float("nan"))
-        achieved = ROIPOOL_BYTES_PER_FRAME * B / (rp_ms * 1e-3) / 1e9
+        if e2e_mode:
+            # dominant kernel: tc_gemm_kernel (every 1x1-conv / Linear layer).  achieved = algorithmic fp32 FLOPs
+            # (2*M*K*columns, unpadded) / CUDA-event time of those launches.  Each fp32 product is issued as three
+            # bf16 MMAs, so 1/3 of the bf16 peak is this kernel's ceiling; `frac` is against the full bf16 peak.
+            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+            achieved = tc_sum["flops"] / (tc_sum["ms"] * 1e-3) / 1e12 if tc_sum["ms"] > 0 else float("nan")
+            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel", "achieved": achieved, "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                        if peaks else "fallback 1590 TFLOP/s",
+                        "algorithmic_flops_per_step": tc_sum["flops"] / args.steps,
+                        "kernel_ms_per_step": tc_sum["ms"] / args.steps, "launches_per_step": tc_sum["launches"] / args.steps,
+                        "share_of_step": tc_sum["ms"] / total_ms if total_ms else None,
+                        "note": "fp32-grade result = 3 bf16 MMAs per product; issued tensor FLOPs = 3x achieved"}
+            workload = ("end-to-end region-proposal fusion + link/start-end affinity (BASELINE config 3): RPN point path "
+                        "with LI-Fusion on precomputed image maps, proposal layer, roipool3d+canonical, per-proposal "
+                        "RCNN, pair affinity; image 3x3 conv stack outside the timed region (SURVEY 8f.1); RCNN on "
+                        "synthetic cluster RoIs")
+        else:
+            hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+            rp_ms = kernel_ms.get("roipool3d", float("nan"))
+            achieved = ROIPOOL_BYTES_PER_FRAME * B / (rp_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "roipool3d_kernel<true>", "achieved": achieved, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                        "algorithmic_bytes_per_launch": ROIPOOL_BYTES_PER_FRAME * B, "kernel_ms": rp_ms}
+            workload = ("jmodt/ops suite (BASELINE config 2 op list at the real network shapes): FPS x6, ball_query x10, "
+                        "three_nn/three_interpolate x4, nms_normal x2/frame, roipool3d+canonical, boxes_iou3d, rotated nms")
         out = {
             "metric": "proposals/sec (16k pts, 128 RoI/frame)", "value": proposals_per_step / (ms_per_step * 1e-3),
             "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "jmodt/ops suite (BASELINE config 2 op list at the real network shapes): FPS x6, "
-                                   "ball_query x10, three_nn/three_interpolate x4, nms_normal x2/frame, "
-                                   "roipool3d+canonical, boxes_iou3d, rotated nms",
+            "config": {"workload": workload,
                        "frames_per_gpu_per_step": B, "points_per_frame": N_PTS, "rois_per_frame": N_ROI,
+                       "weights": "random (name-hashed) init of the reference architecture",
                        "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event pairs on torch's current stream (the launching stream)"},
             "e2e": {"value": proposals_per_step / (e2e_ms * 1e-3), "unit": "proposals/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "roipool3d_kernel<true>", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes_per_launch": ROIPOOL_BYTES_PER_FRAME * B, "kernel_ms": rp_ms},
-            "kernel_ms_per_call": kernel_ms, "kernel_calls_per_step": kernel_calls,
+            "roofline": roofline,
+            "stage_ms_per_call": kernel_ms, "stage_calls_per_step": kernel_calls,
             "wall_s_timed_region": wall_s,
         }
-        if not args.no_cpu_baseline and world >= 1:
-            out["cpu_baseline"] = cpu_reference(min(args.cpu_sample_frames, B), threads=1)
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = (cpu_reference_e2e(threads=os.cpu_count() or 1) if e2e_mode
+                                   else cpu_reference(min(args.cpu_sample_frames, B), threads=1))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -405,30 +504,99 @@ def cpu_reference(frames, threads):
             "seconds": dt}
 
 
+def cpu_reference_e2e(threads, rcnn_sample=32, pair_sample=64):
+    """Host-CPU time of the same end-to-end path on a bounded sample: the reference forward restated in
+    oracle/modules_ref.py (torch-CPU layers with `threads` intra-op threads; FPS / ball-query / three_nn / NMS / RoI
+    pooling through the C oracle).  One full frame of the RPN point path + proposal layer, `rcnn_sample` proposals
+    of the per-proposal network, and a `pair_sample` x `pair_sample` affinity block; costs are scaled to one frame
+    (128 proposals, half a 128x128 pair) and reported as proposals/s."""
+    import torch
+
+    from jmodt_b200 import box_utils, synth
+    from jmodt_b200.detector import PointRCNN, RpnConfig, decode_bbox_target
+    from jmodt_b200.synth import fill_deterministic
+    from oracle import cref, modules_ref
+    cref.build()
+    torch.set_num_threads(max(1, threads))
+    torch.manual_seed(0)
+    model = fill_deterministic(PointRCNN(rpn_cfg=RpnConfig(post_nms_top_n=N_ROI))).eval()   # CPU parameters only
+    f = synth.make_batch(0, 1, with_image=True)
+    xyz, xy = torch.from_numpy(f["pts"]), torch.from_numpy(f["pts_xy"])
+    with torch.no_grad():
+        maps = model.rpn.backbone_net.image_features(torch.from_numpy(f["img"]))        # untimed, as on the GPU
+        t0 = time.perf_counter()
+        bxyz, feats = modules_ref.backbone_forward(model.rpn.backbone_net, xyz, xy, maps, cref)
+        rpn_cls = model.rpn.rpn_cls_layer(feats).transpose(1, 2)
+        rpn_reg = model.rpn.rpn_reg_layer(feats).transpose(1, 2)
+        t_rpn = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cfg = model.rpn.cfg
+        props = decode_bbox_target(bxyz.view(-1, 3), rpn_reg.reshape(-1, rpn_reg.shape[-1]), cfg.loc_scope,
+                                   cfg.loc_bin_size, cfg.num_head_bin, torch.tensor(cfg.mean_size))
+        props[:, 1] += props[:, 3] / 2
+        order = torch.sort(rpn_cls[0, :, 0], descending=True)[1]
+        po = props[order]
+        for lo, hi, n in [(0.0, 40.0, 6300), (40.0, 80.0, 2700)]:
+            sel = po[(po[:, 2] > lo) & (po[:, 2] <= hi)][:n]
+            if len(sel):
+                cref.nms_sorted(box_utils.boxes3d_to_bev_torch(sel).numpy(), cfg.nms_thresh, False)
+        t_prop = time.perf_counter() - t0
+        # per-proposal network on a sample of RoIs
+        t0 = time.perf_counter()
+        rois = f["rois"][0, :rcnn_sample]
+        seg = (torch.sigmoid(rpn_cls[0, :, 0]) > cfg.score_thresh).float()
+        depth = torch.norm(bxyz[0], p=2, dim=1) / 70.0 - 0.5
+        pts_feature = torch.cat([seg[:, None], depth[:, None], feats[0].t()], dim=1).numpy()
+        pooled, _ = cref.roipool3d(f["pts"], pts_feature[None], cref.enlarge_box3d(rois, 0.2)[None], ROI_PTS)
+        pooled = torch.from_numpy(pooled[0])
+        pooled[:, :, 0:3] -= torch.from_numpy(rois[:, None, 0:3])
+        pooled[:, :, 0:3] = box_utils.rotate_pc_along_y_torch(pooled[:, :, 0:3].clone(), torch.from_numpy(rois[:, 6]))
+        fps = lambda x, n: torch.from_numpy(cref.fps(x.numpy(), n))
+        ball = lambda r, ns, x, c: torch.from_numpy(cref.ball_query(r, ns, x.numpy(), c.numpy()))
+        _, _, feat = modules_ref.rcnn_forward_points(model.rcnn_net, pooled, fps, ball)
+        t_rcnn = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        g = torch.Generator().manual_seed(0)
+        pf, df = torch.rand(pair_sample, 512, generator=g), torch.rand(pair_sample, 512, generator=g)
+        modules_ref.affinity(model.rcnn_net.link_layer, model.rcnn_net.se_layer, pf, df)
+        t_aff = time.perf_counter() - t0
+    per_frame = t_rpn + t_prop + t_rcnn * (N_ROI / rcnn_sample) + 0.5 * t_aff * (N_ROI / pair_sample) ** 2
+    return {"value": N_ROI / per_frame, "unit": "proposals/s", "cores": threads, "kind": "port",
+            "sample": f"1 frame of the RPN point path ({t_rpn:.1f} s) and proposal layer ({t_prop:.1f} s), {rcnn_sample} of 128 "
+                      f"proposals through the per-proposal network ({t_rcnn:.1f} s), a {pair_sample}x{pair_sample} block of one "
+                      f"128x128 affinity pair ({t_aff:.1f} s); scaled to one frame = {per_frame:.1f} s",
+            "seconds": t_rpn + t_prop + t_rcnn + t_aff}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    frames_per_step = max(1, min(threads, 8))
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference(1, 1)
-    steps = max(1, min(args.steps, 3))
-    secs = []
-    for _ in range(steps):
-        base = cpu_reference(frames_per_step, threads)   # inputs are generated outside its timed region
-        secs.append(base["seconds"])
-    dt = float(np.mean(secs))
-    value = frames_per_step * N_ROI / dt
-    base.update({"value": value, "cores": threads,
-                 "sample": f"{frames_per_step} frames per step on {threads} host threads (one frame per thread); " + base["sample"]})
+    if args.workload == "e2e":
+        base = cpu_reference_e2e(threads)
+        steps, value, ms = 1, base["value"], base["seconds"] * 1e3
+        workload = "end-to-end region-proposal fusion + affinity on the host CPU (bounded sample, see cpu_baseline.sample)"
+        frames_per_step = 1
+    else:
+        frames_per_step = max(1, min(threads, 8))
+        steps = max(1, min(args.steps, 3))
+        secs = []
+        for _ in range(steps):
+            base = cpu_reference(frames_per_step, threads)   # inputs are generated outside its timed region
+            secs.append(base["seconds"])
+        dt = float(np.mean(secs))
+        value, ms = frames_per_step * N_ROI / dt, dt * 1e3
+        base.update({"value": value, "cores": threads,
+                     "sample": f"{frames_per_step} frames per step on {threads} host threads (one frame per thread); " + base["sample"]})
+        workload = "jmodt/ops suite on the host CPU (same op list and shapes as the B200 arm)"
     print(json.dumps({
         "impl": "reference", "metric": "proposals/sec (16k pts, 128 RoI/frame)", "value": value,
-        "unit": "proposals/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "proposals/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "jmodt/ops suite on the host CPU (same op list and shapes as the B200 arm)",
-                   "frames_per_step": frames_per_step, "points_per_frame": N_PTS, "rois_per_frame": N_ROI},
+        "config": {"workload": workload, "frames_per_step": frames_per_step, "points_per_frame": N_PTS,
+                   "rois_per_frame": N_ROI},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -84,7 +84,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+launch_count = 0  # kernels enqueued through the C ABI (bench.py reports it as gpu_launches)
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 2 if what == "nms" else 1      # nms = mask kernel + sweep kernel
     if rc != 0:
         msg = lib().jmb_last_error().decode(errors="replace")
         raise JmodtB200Error(f"{what} failed (code {rc}): {msg}")

@@ -13,6 +13,37 @@ from . import _lib
 BM, BK = 128, 32
 
 
+class Profiler:
+    """Optional per-launch accounting for bench.py: algorithmic FLOPs (2*M*K*columns, unpadded) and a CUDA-event
+    pair per launch on the launching stream."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (flops, start_event, end_event)
+        self.launches = 0
+
+    def reset(self):
+        self.records, self.launches = [], 0
+
+    def launch(self, flops, fn):
+        self.launches += 1
+        if not self.enabled:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.records.append((flops, e0, e1))
+        return out
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
+        return {"flops": float(sum(f for f, _, _ in self.records)), "ms": float(ms), "launches": len(self.records)}
+
+
+profiler = Profiler()
+
+
 class PackedLayer:
     """bf16 hi/lo chunk images of one layer's weight (+ fp32 bias, zero padded to a multiple of 128)."""
 
@@ -56,10 +87,10 @@ def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None =
     shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
     y = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
     st = _lib.stream_and_device(x)
-    _lib.check(_lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
-                                           x.data_ptr(), K * N, N, None, None, None, 0, 0,
-                                           1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
-               "tc_mlp_layer")
+    profiler.launch(2.0 * layer.M * K * G * N, lambda: _lib.check(
+        _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
+                                    x.data_ptr(), K * N, N, None, None, None, 0, 0,
+                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st), "tc_mlp_layer"))
     return y
 
 
@@ -77,9 +108,10 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
     y = torch.empty(shape, dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)
     fx = feats if feats is not None else xyz  # never dereferenced for rows >= 3 when C == 0
-    _lib.check(_lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, layer.K, G, N, 1,
-                                           fx.data_ptr(), C * n_pts, n_pts, _lib.ptr(idx), xyz.data_ptr(),
-                                           _lib.ptr(centres), nsample if centres is not None else 0, n_pts,
-                                           1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
-               "tc_mlp_layer(grouped)")
+    profiler.launch(2.0 * layer.M * layer.K * G * N, lambda: _lib.check(
+        _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, layer.K, G, N, 1,
+                                    fx.data_ptr(), C * n_pts, n_pts, _lib.ptr(idx), xyz.data_ptr(),
+                                    _lib.ptr(centres), nsample if centres is not None else 0, n_pts,
+                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
+        "tc_mlp_layer(grouped)"))
     return y
