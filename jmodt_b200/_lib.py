@@ -40,6 +40,7 @@ SIGNATURES = {
     "jmb_nms_workspace_bytes": [_i],
     "jmb_nms": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
+    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
 }

@@ -23,20 +23,13 @@
 // cp.async.bulk, X chunks by vector loads + in-register bf16 split) into an mbarrier ring and run the
 // epilogue; warp 4 lane 0 issues tcgen05.mma and signals through tcgen05.commit.  64 KB smem + 128 TMEM
 // columns per CTA -> 3 CTAs per SM, so one CTA's epilogue overlaps another's MMAs.
-#include "common.cuh"
-
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace jmb {
 
-constexpr int TC_BM = 128;      // output channels per tile  (TMEM lanes)
-constexpr int TC_BN = 128;      // columns per tile          (TMEM columns)
-constexpr int TC_BK = 32;       // K per pipeline stage
 constexpr int TC_STAGES = 2;
-constexpr int TC_IMG = TC_BM * TC_BK * 2;          // bytes of one bf16 operand chunk image (8 KB)
 constexpr int TC_STAGE_BYTES = 4 * TC_IMG;         // W_hi, W_lo, X_hi, X_lo
 constexpr int TC_THREADS = 160;
-constexpr uint32_t TC_LBO = 2048, TC_SBO = 128;    // byte strides of the canonical no-swizzle layouts
 
 struct TcGemmParams {
     const __nv_bfloat16 *wpack;   // [Mt][Kc][2][TC_IMG/2] chunk images (see pack_weights in tc.py)
@@ -55,89 +48,6 @@ struct TcGemmParams {
     int pool, relu;
     float *y;
 };
-
-// ---- thin PTX wrappers ----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-    // no-swizzle canonical layout: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version(1) <<46
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
-           ((uint64_t)1 << 46);
-}
-// kind::f16, BF16 x BF16 -> F32, M=128, N=128, A K-major, B MN-major
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// fp32 -> (bf16 hi, bf16 lo) with hi + lo ~= x to 2^-17; packs two values per 32-bit word
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-    const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-}
 
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const TcGemmParams p) {

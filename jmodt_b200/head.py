@@ -108,6 +108,7 @@ class RCNN(nn.Module):
         self.se_layer = _fc_stack(channel_in, cfg.se_fc, 1, cfg.use_bn, cfg.dp_ratio)
         self.init_weights()
         self._packed = None
+        self.fuse_chain = True      # run qualifying SA layers as ONE kernel (csrc/sa_fused.cu)
 
     def init_weights(self):  # rcnn.py:116-134, weight_init='xavier'
         for m in self.modules():
@@ -167,6 +168,9 @@ class RCNN(nn.Module):
                 fidx = pu.farthest_point_sample(l_xyz, sa.npoint)
                 new_xyz = pu.gather_operation(l_xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
                 idx = pu.ball_query(grouper.radius, grouper.nsample, l_xyz, new_xyz)
+                if self.fuse_chain and tc.sa_fused_supported(packed, l_feat.shape[1], sa.npoint, grouper.nsample):
+                    l_xyz, l_feat = new_xyz, tc.sa_fused(packed, l_xyz, l_feat.contiguous(), idx, new_xyz)
+                    continue
                 h = tc.grouped_first_layer(packed[0], l_xyz, l_feat, idx, new_xyz, grouper.nsample)
                 pool = grouper.nsample
             else:                                                                         # GroupAll

@@ -89,6 +89,10 @@ class _PointnetSAModuleBase(nn.Module):
                 assert grouper.use_xyz, "the fused path groups xyz with the features"
                 idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
                 pool = grouper.nsample
+                if getattr(self, "fuse_chain", True) and features is not None and \
+                        tc.sa_fused_supported(layers, features.shape[1], new_xyz.shape[1], grouper.nsample):
+                    outs.append(tc.sa_fused(layers, xyz, features, idx, new_xyz))   # whole layer in one kernel
+                    continue
                 h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
                                            pool=pool if len(layers) == 1 else 0)
             else:  # GroupAll

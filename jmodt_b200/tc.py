@@ -115,3 +115,29 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
                                     1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
         "tc_mlp_layer(grouped)"))
     return y
+
+
+def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) -> bool:
+    """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu)."""
+    return (len(layers) == 3 and layers[0].M == 128 and layers[1].M == 128 and layers[1].K == 128
+            and layers[2].K == 128 and layers[2].M in (128, 256) and all(l.relu for l in layers)
+            and 3 < 3 + n_feat_channels <= 160 and nsample in (8, 16, 32, 64) and (npoint * nsample) % 128 == 0)
+
+
+def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, centres: torch.Tensor) -> torch.Tensor:
+    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts), idx (G, npoint, nsample)
+    int32, centres (G, npoint, 3) -> (G, C3, npoint)."""
+    G, n_pts, _ = xyz.shape
+    C = feats.shape[1]
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    l1, l2, l3 = layers
+    assert l1.K == 3 + C and feats.is_contiguous() and idx.is_contiguous() and xyz.is_contiguous()
+    out = torch.empty((G, l3.M, npoint), dtype=torch.float32, device=xyz.device)
+    st = _lib.stream_and_device(xyz)
+    flops = 2.0 * G * npoint * nsample * (l1.M * l1.K + l2.M * l2.K + l3.M * l3.K)
+    profiler.launch(flops, lambda: _lib.check(
+        _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
+                                l3.wpack.data_ptr(), l3.bias.data_ptr(), l1.K, l3.M, G, npoint, nsample, n_pts,
+                                feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
+                                out.data_ptr(), st), "sa_fused"))
+    return out

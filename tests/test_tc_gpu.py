@@ -63,3 +63,35 @@ def test_maxpool_epilogue_and_grouped_prologue(cuda):
     ga = tc.grouped_first_layer(layer, xyz, feats, None, None, 0, pool=128)
     want_ga = torch.einsum("mk,gkn->gmn", w.double(), torch.cat([xyz.transpose(1, 2), feats], 1).double()) + b.double()[None, :, None]
     _check(ga.double(), want_ga.clamp_min(0).view(G, M, n_pts // 128, 128).max(dim=3)[0])
+
+
+@pytest.mark.parametrize("C,npoint,ns,C3", [(128, 128, 64, 128), (128, 32, 64, 256), (61, 64, 16, 128), (128, 16, 8, 256)])
+def test_sa_fused_single_kernel_matches_layerwise_and_torch(cuda, C, npoint, ns, C3):
+    """The one-kernel set-abstraction layer vs (a) the layer-by-layer tcgen05 path and (b) torch fp32."""
+    from jmodt_b200 import tc
+    from jmodt_b200.pointnet2 import pointnet2_utils as pu
+    g = torch.Generator(device="cpu").manual_seed(C + npoint)
+    G, n_pts = 37, 512
+    xyz = (torch.rand(G, n_pts, 3, generator=g) * 2).to(cuda)
+    feats = torch.randn(G, C, n_pts, generator=g).to(cuda)
+    dims = [3 + C, 128, 128, C3]
+    layers, ws = [], []
+    for i in range(3):
+        w = (torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).to(cuda)
+        b = (torch.randn(dims[i + 1], generator=g) * 0.2).to(cuda)
+        ws.append((w, b))
+        layers.append(tc.PackedLayer(w, b, True))
+    fidx = pu.farthest_point_sample(xyz, npoint)
+    centres = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+    idx = pu.ball_query(0.4, ns, xyz, centres)
+    assert tc.sa_fused_supported(layers, C, npoint, ns)
+    got = tc.sa_fused(layers, xyz, feats, idx, centres)
+    h = tc.grouped_first_layer(layers[0], xyz, feats, idx, centres, ns)
+    h = tc.mlp_layer(layers[1], h)
+    layerwise = tc.mlp_layer(layers[2], h, pool=ns)
+    assert got.shape == layerwise.shape == (G, C3, npoint)
+    _check(got.double(), layerwise.double(), tol=1e-6)        # same arithmetic, same rounding points
+    x = pu.QueryAndGroup(0.4, ns)(xyz, centres, feats).double()
+    for w, b in ws:
+        x = (torch.einsum("mk,gkps->gmps", w.double(), x) + b.double()[None, :, None, None]).clamp_min(0)
+    _check(got.double(), x.max(dim=3)[0], tol=5e-5)
