@@ -19,7 +19,7 @@
 namespace jmb {
 
 constexpr int SF_WORKERS = 256;
-constexpr int SF_THREADS = SF_WORKERS + 32;
+constexpr int SF_THREADS = SF_WORKERS + 64;  // + warp 8: MMA issuer, warp 9: weight loader
 constexpr int SF_WSTAGES = 4;
 constexpr int SF_MAXKC1 = 5;
 constexpr int SF_CHUNK = 2 * TC_IMG;  // hi + lo image of one 32-row chunk: 16 KB
@@ -81,7 +81,7 @@ sa_fused_kernel(const SaFusedParams p) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
         uint32_t acc_phase = 0;
 
-        auto produce_x1 = [&](long long tile) {
+        auto produce_x1 = [&](long long tile, int c_begin, int c_end) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
             const int n0 = nt * TC_BN + ng * 8;  // 8 columns of one centre (nsample % 8 == 0)
@@ -95,7 +95,7 @@ sa_fused_kernel(const SaFusedParams p) {
             const float *cen = p.centres + ((size_t)g * p.npoint + n0 / p.nsample) * 3;
             const float *pts = p.xyz + (size_t)g * p.n_pts * 3;
             const float *fg = p.feats + (size_t)g * (p.K1 - 3) * p.n_pts;
-            for (int c = 0; c < p.Kc1; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint8_t *xhi = s_x1 + (size_t)c * SF_CHUNK, *xlo = xhi + TC_IMG;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -192,7 +192,8 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         const long long first = blockIdx.x;
-        if (first < total_tiles) produce_x1(first);
+        const int csplit = (p.Kc1 + 1) / 2;   // next tile's gather is split over the layer-2 and layer-3 MMA windows
+        if (first < total_tiles) produce_x1(first, 0, p.Kc1);
         for (long long tile = first; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
             tc_fence_after();
@@ -200,7 +201,8 @@ sa_fused_kernel(const SaFusedParams p) {
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&s_epi_done);
-            if (tile + gridDim.x < total_tiles) produce_x1(tile + gridDim.x);  // overlaps the layer-2 MMAs
+            const bool more = tile + gridDim.x < total_tiles;
+            if (more) produce_x1(tile + gridDim.x, 0, csplit);          // overlaps the layer-2 MMAs
 
             mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
             tc_fence_after();
@@ -208,6 +210,7 @@ sa_fused_kernel(const SaFusedParams p) {
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&s_epi_done);
+            if (more) produce_x1(tile + gridDim.x, csplit, p.Kc1);      // overlaps the layer-3 MMAs
 
             for (int mt = 0; mt < p.Mt3; ++mt) {
                 mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
@@ -217,31 +220,33 @@ sa_fused_kernel(const SaFusedParams p) {
                 mbar_arrive(&s_epi_done);
             }
         }
-    } else {
+    } else if (warp == 9) {
         if (lane == 0) {
-            // ====================================== MMA issuer + weight loader ======================================
-            const int CH = p.Kc1 + 4 + 4 * p.Mt3;  // weight chunks consumed per tile
+            // ====================================== weight loader ======================================
+            // The weight stream of a tile is fixed (Kc1 + 4 + 4*Mt3 chunk images); run ahead of the issuer through
+            // the ring so a layer's first chunk is already in shared memory when its MMAs may start.
+            const int CH = p.Kc1 + 4 + 4 * p.Mt3;
             long long my_tiles = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
             const long long total_chunks = my_tiles * CH;
-            long long wreq = 0, wuse = 0;
-            auto chunk_src = [&](int j) -> const __nv_bfloat16 * {  // j-th chunk of a tile's weight stream
-                if (j < p.Kc1) return p.w1 + (size_t)j * (SF_CHUNK / 2);
-                j -= p.Kc1;
-                if (j < 4) return p.w2 + (size_t)j * (SF_CHUNK / 2);
-                return p.w3 + (size_t)(j - 4) * (SF_CHUNK / 2);
-            };
-            auto prefetch = [&]() {
-                while (wreq < total_chunks && wreq < wuse + SF_WSTAGES) {
-                    const int s = (int)(wreq % SF_WSTAGES);
-                    mbar_wait(&s_w_empty[s], (uint32_t)(((wreq / SF_WSTAGES) & 1) ^ 1));
-                    mbar_arrive_expect_tx(&s_w_full[s], SF_CHUNK);
-                    bulk_g2s(s_w + (size_t)s * SF_CHUNK, chunk_src((int)(wreq % CH)), SF_CHUNK, &s_w_full[s]);
-                    ++wreq;
-                }
-            };
+            for (long long wreq = 0; wreq < total_chunks; ++wreq) {
+                const int s = (int)(wreq % SF_WSTAGES);
+                int j = (int)(wreq % CH);
+                const __nv_bfloat16 *src;
+                if (j < p.Kc1) src = p.w1 + (size_t)j * (SF_CHUNK / 2);
+                else if (j < p.Kc1 + 4) src = p.w2 + (size_t)(j - p.Kc1) * (SF_CHUNK / 2);
+                else src = p.w3 + (size_t)(j - p.Kc1 - 4) * (SF_CHUNK / 2);
+                mbar_wait(&s_w_empty[s], (uint32_t)(((wreq / SF_WSTAGES) & 1) ^ 1));
+                mbar_arrive_expect_tx(&s_w_full[s], SF_CHUNK);
+                bulk_g2s(s_w + (size_t)s * SF_CHUNK, src, SF_CHUNK, &s_w_full[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+            // ====================================== MMA issuer ======================================
+            long long wuse = 0;
             auto mma_chunk = [&](uint32_t b_base, int k16_steps, bool first_of_layer) {
-                prefetch();
                 const int s = (int)(wuse % SF_WSTAGES);
                 mbar_wait(&s_w_full[s], (uint32_t)((wuse / SF_WSTAGES) & 1));
                 tc_fence_after();

@@ -87,14 +87,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// fp32 -> (bf16 hi, bf16 lo) with hi + lo ~= x to 2^-17; packs two values per 32-bit word
+// fp32 -> (bf16 hi, bf16 lo) with hi + lo ~= x to 2^-17; packs two values per 32-bit word (a in the low half).
+// cvt.rn.bf16x2.f32 converts both values in one instruction.
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-    const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
 }
-
 
 }  // namespace jmb

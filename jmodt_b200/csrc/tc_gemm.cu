@@ -27,7 +27,7 @@
 
 namespace jmb {
 
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 3;
 constexpr int TC_STAGE_BYTES = 4 * TC_IMG;         // W_hi, W_lo, X_hi, X_lo
 constexpr int TC_THREADS = 160;
 
@@ -85,84 +85,119 @@ tc_gemm_kernel(const TcGemmParams p) {
         const int t = threadIdx.x;
         const int kk = t & 7;               // k row inside a group of 8
         const int ng = warp * 4 + ((t >> 3) & 3);   // n group of 8 columns inside the tile
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            const int mt = (int)(tile % p.Mt);
+        // Operand staging is software-pipelined: the global loads of work item i+1 (the next K chunk, possibly of the
+        // next tile) are issued into registers before item i is converted and stored, so one load round trip is hidden
+        // behind the split / store / MMA of the previous chunk and behind the epilogue.
+        struct TileCoord { int mt, nt, g, n0; };
+        auto coord = [&](long long tile) {
+            TileCoord c;
+            c.mt = (int)(tile % p.Mt);
             const long long gn = tile / p.Mt;
-            const int nt = (int)(gn % Nt);
-            const int g = (int)(gn / Nt);
-            const int n0 = nt * TC_BN + ng * 8;  // first of this thread's 8 columns
-
-            // per-tile gather state
-            int pidx[8];
-            float cen[3] = {0.f, 0.f, 0.f};
-            if (p.mode == 1) {
+            c.nt = (int)(gn % Nt);
+            c.g = (int)(gn / Nt);
+            c.n0 = c.nt * TC_BN + ng * 8;
+            return c;
+        };
+        int pidx[8];              // gather mode: point index of this thread's 8 columns, for the tile being LOADED
+        long long pidx_tile = -1;
+        auto load_chunk = [&](long long tile, int kc, float (&v)[TC_BK / 8][8]) {
+            const TileCoord tc_ = coord(tile);
+            const float *xg = p.x + (size_t)tc_.g * p.x_group_stride;
+            if (p.mode == 1 && pidx_tile != tile) {
+                pidx_tile = tile;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int n = n0 + j;
+                    const int n = tc_.n0 + j;
                     pidx[j] = 0;
-                    if (n < p.N) pidx[j] = p.idx ? __ldg(p.idx + (size_t)g * p.N + n) : (n % p.n_pts);
+                    if (n < p.N) pidx[j] = p.idx ? __ldg(p.idx + (size_t)tc_.g * p.N + n) : (n % p.n_pts);
                 }
             }
-            const float *xg = p.x + (size_t)g * p.x_group_stride;
-
-            for (int kc = 0; kc < p.Kc; ++kc, ++chunk_ctr) {
-                const int s = chunk_ctr % TC_STAGES;
-                const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
-                mbar_wait(&s_empty[s], ph ^ 1);
-                uint8_t *stage = tc_smem + (size_t)s * TC_STAGE_BYTES;
-                if (t == 0) {
-                    mbar_arrive_expect_tx(&s_full[s], 2 * TC_IMG);
-                    bulk_g2s(stage, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG, 2 * TC_IMG, &s_full[s]);
-                }
-                uint8_t *xhi = stage + 2 * TC_IMG, *xlo = stage + 3 * TC_IMG;
 #pragma unroll
-                for (int kb = 0; kb < TC_BK / 8; ++kb) {
-                    const int k = kc * TC_BK + kb * 8 + kk;
-                    float v[8];
+            for (int kb = 0; kb < TC_BK / 8; ++kb) {
+                const int k = kc * TC_BK + kb * 8 + kk;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-                    if (k < p.K) {
-                        if (p.mode == 0) {
-                            const float *row = xg + (size_t)k * p.x_row_stride + n0;
-                            if (n0 + 8 <= p.N && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                                const float4 a = __ldg(reinterpret_cast<const float4 *>(row));
-                                const float4 b = __ldg(reinterpret_cast<const float4 *>(row) + 1);
-                                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    if (n0 + j < p.N) v[j] = __ldg(row + j);
-                            }
-                        } else if (k < 3) {
-                            const float *pts = p.xyz + (size_t)g * p.n_pts * 3;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int n = n0 + j;
-                                if (n < p.N) {
-                                    float c = 0.f;
-                                    if (p.centres) c = __ldg(p.centres + ((size_t)g * (p.N / p.nsample) + n / p.nsample) * 3 + k);
-                                    v[j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), c);
-                                }
-                            }
+                for (int j = 0; j < 8; ++j) v[kb][j] = 0.f;
+                if (k < p.K) {
+                    if (p.mode == 0) {
+                        const float *row = xg + (size_t)k * p.x_row_stride + tc_.n0;
+                        if (tc_.n0 + 8 <= p.N && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4 *>(row));
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(row) + 1);
+                            v[kb][0] = a4.x; v[kb][1] = a4.y; v[kb][2] = a4.z; v[kb][3] = a4.w;
+                            v[kb][4] = b4.x; v[kb][5] = b4.y; v[kb][6] = b4.z; v[kb][7] = b4.w;
                         } else {
-                            const float *row = xg + (size_t)(k - 3) * p.x_row_stride;
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                if (n0 + j < p.N) v[j] = __ldg(row + pidx[j]);
+                                if (tc_.n0 + j < p.N) v[kb][j] = __ldg(row + j);
                         }
+                    } else if (k < 3) {
+                        const float *pts = p.xyz + (size_t)tc_.g * p.n_pts * 3;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int n = tc_.n0 + j;
+                            if (n < p.N) {
+                                float c = 0.f;
+                                if (p.centres) c = __ldg(p.centres + ((size_t)tc_.g * (p.N / p.nsample) + n / p.nsample) * 3 + k);
+                                v[kb][j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), c);
+                            }
+                        }
+                    } else {
+                        const float *row = xg + (size_t)(k - 3) * p.x_row_stride;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (tc_.n0 + j < p.N) v[kb][j] = __ldg(row + pidx[j]);
                     }
-                    uint4 h, l;
-                    split2(v[0], v[1], h.x, l.x);
-                    split2(v[2], v[3], h.y, l.y);
-                    split2(v[4], v[5], h.z, l.z);
-                    split2(v[6], v[7], h.w, l.w);
-                    const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)kb * TC_LBO + (uint32_t)kk * 16;
-                    *reinterpret_cast<uint4 *>(xhi + off) = h;
-                    *reinterpret_cast<uint4 *>(xlo + off) = l;
                 }
-                fence_proxy_async();
-                mbar_arrive(&s_full[s]);
+            }
+        };
+        auto store_chunk = [&](int mt, int kc, const float (&v)[TC_BK / 8][8]) {
+            const int s = chunk_ctr % TC_STAGES;
+            const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
+            mbar_wait(&s_empty[s], ph ^ 1);
+            uint8_t *stage = tc_smem + (size_t)s * TC_STAGE_BYTES;
+            if (t == 0) {
+                mbar_arrive_expect_tx(&s_full[s], 2 * TC_IMG);
+                bulk_g2s(stage, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG, 2 * TC_IMG, &s_full[s]);
+            }
+            uint8_t *xhi = stage + 2 * TC_IMG, *xlo = stage + 3 * TC_IMG;
+#pragma unroll
+            for (int kb = 0; kb < TC_BK / 8; ++kb) {
+                uint4 h, l;
+                split2(v[kb][0], v[kb][1], h.x, l.x);
+                split2(v[kb][2], v[kb][3], h.y, l.y);
+                split2(v[kb][4], v[kb][5], h.z, l.z);
+                split2(v[kb][6], v[kb][7], h.w, l.w);
+                const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)kb * TC_LBO + (uint32_t)kk * 16;
+                *reinterpret_cast<uint4 *>(xhi + off) = h;
+                *reinterpret_cast<uint4 *>(xlo + off) = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&s_full[s]);
+            ++chunk_ctr;
+        };
+
+        float va[TC_BK / 8][8], vb[TC_BK / 8][8];
+        if ((long long)blockIdx.x < total_tiles) load_chunk(blockIdx.x, 0, va);
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
+            const TileCoord tcur = coord(tile);
+            const int mt = tcur.mt, nt = tcur.nt, g = tcur.g;
+            const long long next_tile = tile + gridDim.x;
+            for (int kc = 0; kc < p.Kc; kc += 2) {
+                // item (tile, kc) is in va; prefetch (tile, kc+1) or the next tile's first chunk into vb
+                if (kc + 1 < p.Kc) load_chunk(tile, kc + 1, vb);
+                else if (next_tile < total_tiles) load_chunk(next_tile, 0, vb);
+                store_chunk(mt, kc, va);
+                if (kc + 1 < p.Kc) {
+                    if (kc + 2 < p.Kc) load_chunk(tile, kc + 2, va);
+                    else if (next_tile < total_tiles) load_chunk(next_tile, 0, va);
+                    store_chunk(mt, kc + 1, vb);
+                } else {
+                    // odd chunk count: the prefetched first chunk of the next tile sits in vb; move it to va
+#pragma unroll
+                    for (int kb = 0; kb < TC_BK / 8; ++kb)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) va[kb][j] = vb[kb][j];
+                }
             }
 
             // ---- epilogue: one output channel per thread ----
