@@ -179,6 +179,21 @@ JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const 
                          const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                          void *stream);
 
+/* ---- proposal layer ---------------------------------------------------------------------- */
+
+/* Scratch bytes for jmb_proposal_layer. */
+JMB_API size_t jmb_proposal_workspace_bytes(int B, int N, int pre_top_n, int post_top_n);
+
+/* replaces the per-frame loop of ProposalLayer.forward + distance_based_proposal (reference
+ * jmodt/detection/layers/proposal_layer.py:36-121) for a whole batch, on the device: proposals (B,N,7) decoded
+ * boxes [x, y_bottom, z, h, w, l, ry], scores (B,N), order (B,N) int64 = argsort(scores, descending) per frame.
+ * Two distance bins (0,40] / (40,80] with 70 % / 30 % of the pre- and post-NMS quotas; NMS is axis-aligned
+ * (rotated = 0, cfg.RPN.NMS_TYPE = 'normal') or rotated.  ret_boxes (B, post_top_n, 7) and ret_scores
+ * (B, post_top_n) are zero padded like the reference's. */
+JMB_API int jmb_proposal_layer(int B, int N, const float *proposals, const float *scores, const long long *order,
+                               int pre_top_n, int post_top_n, float nms_thresh, int rotated, float *ret_boxes,
+                               float *ret_scores, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

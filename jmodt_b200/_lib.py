@@ -41,10 +41,12 @@ SIGNATURES = {
     "jmb_nms": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
+    "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
 }
-_RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz}
+_RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz, "jmb_proposal_workspace_bytes": _sz}
 
 
 class JmodtB200Error(RuntimeError):
@@ -90,7 +92,7 @@ launch_count = 0  # kernels enqueued through the C ABI (bench.py reports it as g
 
 def check(rc: int, what: str) -> None:
     global launch_count
-    launch_count += 2 if what == "nms" else 1      # nms = mask kernel + sweep kernel
+    launch_count += {"nms": 2, "proposal_layer": 4}.get(what, 1)   # nms = mask + sweep kernels, proposal = 4
     if rc != 0:
         msg = lib().jmb_last_error().decode(errors="replace")
         raise JmodtB200Error(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,266 @@
+// Distance-binned proposal selection + NMS for a whole batch, on the device, without host round trips.
+//
+// Replaces the per-frame / per-bin Python loop of ProposalLayer.forward + distance_based_proposal (reference
+// jmodt/detection/layers/proposal_layer.py:36-121): boolean-mask indexing, `dist_mask.sum() != 0` host syncs,
+// one NMS call (cudaMalloc + D2H mask copy + host sweep, iou3d.cpp:121-166) per frame and bin, torch.cat.
+// Here: one selection kernel (ordered compaction of the score-sorted proposals per frame and distance bin), one
+// batched mask kernel, one batched greedy sweep that stops after the post-NMS quota, one finalisation kernel.
+#include "iou3d_device.cuh"
+
+namespace jmb {
+
+struct ProposalParams {
+    int B, N;
+    int pre[2], post[2];
+    float lo[2], hi[2];
+    int max_pre, col_blocks, max_post;
+};
+
+// per-set workspace views
+struct ProposalWs {
+    int *sel_idx;                 // [sets][max_pre]  original point index
+    float *sel_bev;               // [sets][max_pre][5]
+    int *count;                   // [sets]
+    unsigned long long *mask;     // [sets][max_pre][col_blocks]
+    int *keep;                    // [sets][max_post]
+    int *nkeep;                   // [sets]
+};
+
+__global__ void __launch_bounds__(256)
+proposal_select_kernel(ProposalParams p, const float *__restrict__ proposals, const long long *__restrict__ order,
+                       ProposalWs ws) {
+    const int bin = blockIdx.x, b = blockIdx.y, set = b * 2 + bin;
+    const float *prop = proposals + (size_t)b * p.N * 7;
+    const long long *ord = order + (size_t)b * p.N;
+    int *sel_idx = ws.sel_idx + (size_t)set * p.max_pre;
+    float *sel_bev = ws.sel_bev + (size_t)set * p.max_pre * 5;
+    __shared__ int s_warp[8];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // pass 0: entries of this bin, first pre[bin].  pass 1 (bin 1 only, if pass 0 found nothing): entries of the
+    // FIRST bin after skipping its first pre[0] matches (proposal_layer.py:92-99).
+    for (int pass = 0; pass < 2; ++pass) {
+        const float lo = pass == 0 ? p.lo[bin] : p.lo[0], hi = pass == 0 ? p.hi[bin] : p.hi[0];
+        const int skip = pass == 0 ? 0 : p.pre[0];
+        const int want = p.pre[bin];
+        int seen = 0;  // matches so far (block-uniform)
+        for (int i0 = 0; i0 < p.N && seen < skip + want; i0 += 256) {
+            const int i = i0 + threadIdx.x;
+            bool hit = false;
+            int e = 0;
+            if (i < p.N) {
+                e = (int)ord[i];
+                const float z = __ldg(prop + (size_t)e * 7 + 2);
+                hit = (z > lo) && (z <= hi);
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_warp[warp] = __popc(mk);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                if (w < warp) before += s_warp[w];
+                total += s_warp[w];
+            }
+            const int pos = seen + before + __popc(mk & ((1u << lane) - 1u)) - skip;
+            if (hit && pos >= 0 && pos < want) {
+                sel_idx[pos] = e;
+                const float *q = prop + (size_t)e * 7;
+                const float x = __ldg(q), z = __ldg(q + 2), w_ = __ldg(q + 4), l = __ldg(q + 5);
+                const float hl = __fmul_rn(l, 0.5f), hw = __fmul_rn(w_, 0.5f);   // boxes3d_to_bev_torch
+                float *o = sel_bev + (size_t)pos * 5;
+                o[0] = __fsub_rn(x, hl); o[1] = __fsub_rn(z, hw); o[2] = __fadd_rn(x, hl); o[3] = __fadd_rn(z, hw);
+                o[4] = __ldg(q + 6);
+            }
+            seen += total;
+            __syncthreads();
+        }
+        const int got = max(0, min(seen - skip, want));
+        if (threadIdx.x == 0) s_total = got;
+        __syncthreads();
+        if (pass == 0 && (s_total > 0 || bin == 0)) break;   // bin 0 with no points is simply skipped (:93-94)
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ws.count[set] = s_total;
+}
+
+template <bool ROTATED>
+__global__ void __launch_bounds__(64)
+nms_mask_batched_kernel(ProposalParams p, float thresh, ProposalWs ws) {
+    const int set = blockIdx.z;
+    const int n = ws.count[set];
+    const int row_start = blockIdx.y, col_start = blockIdx.x;
+    if (col_start < row_start || row_start * 64 >= n || col_start * 64 >= n) return;
+    const float *boxes = ws.sel_bev + (size_t)set * p.max_pre * 5;
+    unsigned long long *mask = ws.mask + (size_t)set * p.max_pre * p.col_blocks;
+    const int row_size = min(n - row_start * 64, 64);
+    const int col_size = min(n - col_start * 64, 64);
+    __shared__ float block_boxes[64 * 5];
+    if ((int)threadIdx.x < col_size) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) block_boxes[threadIdx.x * 5 + k] = boxes[(size_t)(64 * col_start + threadIdx.x) * 5 + k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < row_size) {
+        const int cur = 64 * row_start + threadIdx.x;
+        float a[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a[k] = boxes[(size_t)cur * 5 + k];
+        unsigned long long t = 0;
+        const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+        for (int i = start; i < col_size; ++i) {
+            const float v = ROTATED ? iou_bev(a, block_boxes + i * 5) : iou_normal(a, block_boxes + i * 5);
+            if (v > thresh) t |= 1ULL << i;
+        }
+        mask[(size_t)cur * p.col_blocks + col_start] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nms_sweep_batched_kernel(ProposalParams p, ProposalWs ws) {
+    extern __shared__ unsigned long long s_remv[];
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_nkeep, s_stop;
+    const int set = blockIdx.x, bin = set & 1;
+    const int n = ws.count[set];
+    const int col_blocks = (n + 63) / 64;
+    const int max_keep = p.post[bin];
+    const unsigned long long *mask = ws.mask + (size_t)set * p.max_pre * p.col_blocks;
+    int *keep = ws.keep + (size_t)set * p.max_post;
+    for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) s_remv[j] = 0ULL;
+    if (threadIdx.x == 0) { s_nkeep = 0; s_stop = 0; }
+    __syncthreads();
+    for (int blk = 0; blk < col_blocks; ++blk) {
+        if (threadIdx.x < 64) {
+            const int row = blk * 64 + threadIdx.x;
+            s_diag[threadIdx.x] = row < n ? mask[(size_t)row * p.col_blocks + blk] : 0ULL;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long cur = s_remv[blk], kept = 0ULL;
+            int nk = s_nkeep;
+            const int rows = min(64, n - blk * 64);
+            for (int i = 0; i < rows; ++i) {
+                if (!((cur >> i) & 1ULL)) {
+                    if (nk >= max_keep) { s_stop = 1; break; }
+                    keep[nk++] = blk * 64 + i;
+                    kept |= 1ULL << i;
+                    cur |= s_diag[i];
+                }
+            }
+            s_kept = kept;
+            s_nkeep = nk;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const unsigned long long kept = s_kept;
+        for (int j = blk + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
+            unsigned long long acc = s_remv[j], kk = kept;
+            while (kk) {
+                const int i = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                acc |= mask[(size_t)(blk * 64 + i) * p.col_blocks + j];
+            }
+            s_remv[j] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ws.nkeep[set] = s_nkeep;
+}
+
+__global__ void __launch_bounds__(128)
+proposal_finalize_kernel(ProposalParams p, const float *__restrict__ proposals, const float *__restrict__ scores,
+                         ProposalWs ws, float *__restrict__ ret_boxes, float *__restrict__ ret_scores) {
+    const int b = blockIdx.x;
+    const int total_post = p.post[0] + p.post[1];
+    const int k0 = ws.nkeep[b * 2], k1 = ws.nkeep[b * 2 + 1];
+    for (int j = threadIdx.x; j < total_post; j += blockDim.x) {
+        float box[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float sc = 0.f;
+        int bin = -1, r = 0;
+        if (j < k0) { bin = 0; r = j; }
+        else if (j < k0 + k1) { bin = 1; r = j - k0; }
+        if (bin >= 0) {
+            const int set = b * 2 + bin;
+            const int e = ws.sel_idx[(size_t)set * p.max_pre + ws.keep[(size_t)set * p.max_post + r]];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) box[k] = __ldg(proposals + ((size_t)b * p.N + e) * 7 + k);
+            sc = __ldg(scores + (size_t)b * p.N + e);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) ret_boxes[((size_t)b * total_post + j) * 7 + k] = box[k];
+        ret_scores[(size_t)b * total_post + j] = sc;
+    }
+}
+
+static void fill_params(ProposalParams &p, int B, int N, int pre_top_n, int post_top_n) {
+    p.B = B; p.N = N;
+    p.pre[0] = (int)(pre_top_n * 0.7); p.pre[1] = pre_top_n - p.pre[0];      // proposal_layer.py:67-68
+    p.post[0] = (int)(post_top_n * 0.7); p.post[1] = post_top_n - p.post[0]; // :69-70
+    p.lo[0] = 0.f; p.hi[0] = 40.f; p.lo[1] = 40.f; p.hi[1] = 80.f;           // nms_range_list (:66)
+    p.max_pre = p.pre[0] > p.pre[1] ? p.pre[0] : p.pre[1];
+    if (p.max_pre > N) p.max_pre = N;
+    if (p.max_pre < 1) p.max_pre = 1;
+    p.col_blocks = (p.max_pre + 63) / 64;
+    p.max_post = p.post[0] > p.post[1] ? p.post[0] : p.post[1];
+    if (p.max_post < 1) p.max_post = 1;
+}
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t carve(const ProposalParams &p, uint8_t *base, ProposalWs *ws) {
+    const size_t sets = (size_t)p.B * 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base ? base + o : nullptr; };
+    uint8_t *a = take(sets * p.max_pre * sizeof(int));
+    uint8_t *b = take(sets * p.max_pre * 5 * sizeof(float));
+    uint8_t *c = take(sets * sizeof(int));
+    uint8_t *d = take(sets * (size_t)p.max_pre * p.col_blocks * sizeof(unsigned long long));
+    uint8_t *e = take(sets * p.max_post * sizeof(int));
+    uint8_t *f = take(sets * sizeof(int));
+    if (ws) {
+        ws->sel_idx = (int *)a; ws->sel_bev = (float *)b; ws->count = (int *)c;
+        ws->mask = (unsigned long long *)d; ws->keep = (int *)e; ws->nkeep = (int *)f;
+    }
+    return off;
+}
+
+}  // namespace jmb
+
+extern "C" size_t jmb_proposal_workspace_bytes(int B, int N, int pre_top_n, int post_top_n) {
+    using namespace jmb;
+    if (B <= 0 || N <= 0) return 0;
+    ProposalParams p;
+    fill_params(p, B, N, pre_top_n, post_top_n);
+    return carve(p, nullptr, nullptr);
+}
+
+extern "C" int jmb_proposal_layer(int B, int N, const float *proposals, const float *scores, const long long *order,
+                                  int pre_top_n, int post_top_n, float nms_thresh, int rotated, float *ret_boxes,
+                                  float *ret_scores, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(B >= 0 && N >= 0 && pre_top_n > 0 && post_top_n > 0, "proposal_layer: bad sizes");
+    if (B == 0) return JMB_OK;
+    JMB_REQUIRE(proposals && scores && order && ret_boxes && ret_scores, "proposal_layer: null pointer");
+    JMB_REQUIRE(B <= 32767, "proposal_layer: batch too large");
+    ProposalParams p;
+    fill_params(p, B, N, pre_top_n, post_top_n);
+    ProposalWs ws;
+    const size_t need = carve(p, (uint8_t *)workspace, &ws);
+    if (!workspace || workspace_bytes < need) {
+        set_error("proposal_layer: workspace of %zu bytes required", need);
+        return JMB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    proposal_select_kernel<<<dim3(2, B), 256, 0, st>>>(p, proposals, order, ws);
+    dim3 mgrid(p.col_blocks, p.col_blocks, B * 2);
+    if (rotated) nms_mask_batched_kernel<true><<<mgrid, 64, 0, st>>>(p, nms_thresh, ws);
+    else nms_mask_batched_kernel<false><<<mgrid, 64, 0, st>>>(p, nms_thresh, ws);
+    const size_t smem = (size_t)p.col_blocks * sizeof(unsigned long long);
+    JMB_REQUIRE(smem <= 48 * 1024, "proposal_layer: pre_nms_top_n too large");
+    nms_sweep_batched_kernel<<<B * 2, 256, smem, st>>>(p, ws);
+    proposal_finalize_kernel<<<B, 128, 0, st>>>(p, proposals, scores, ws, ret_boxes, ret_scores);
+    return check_launch("proposal_layer");
+}

@@ -311,6 +311,7 @@ class ProposalLayer(nn.Module):
     def __init__(self, mode="TEST", cfg: RpnConfig | None = None):
         super().__init__()
         self.mode, self.cfg = mode, cfg or RpnConfig()
+        self.batched = True       # False: the reference's per-frame / per-bin loop (same results, host syncs)
 
     @torch.no_grad()
     def forward(self, rpn_scores, rpn_reg, xyz):
@@ -322,12 +323,30 @@ class ProposalLayer(nn.Module):
         proposals[:, 1] += proposals[:, 3] / 2
         proposals = proposals.view(B, -1, 7)
         _, sorted_idxs = torch.sort(rpn_scores, dim=1, descending=True)
+        if self.batched:
+            return self._forward_batched(rpn_scores.contiguous(), proposals.contiguous(), sorted_idxs.contiguous())
         ret_bbox3d = rpn_scores.new_zeros(B, cfg.post_nms_top_n, 7)
         ret_scores = rpn_scores.new_zeros(B, cfg.post_nms_top_n)
         for k in range(B):
             s, p = self.distance_based_proposal(rpn_scores[k], proposals[k], sorted_idxs[k])
             ret_bbox3d[k, :p.size(0)] = p
             ret_scores[k, :p.size(0)] = s
+        return ret_bbox3d, ret_scores
+
+    def _forward_batched(self, scores, proposals, order):
+        """Whole batch in four kernels, no host synchronisation (csrc/proposal.cu)."""
+        cfg = self.cfg
+        B, N = scores.shape
+        L = _lib.lib()
+        st = _lib.stream_and_device(scores)
+        ws_bytes = L.jmb_proposal_workspace_bytes(B, N, cfg.pre_nms_top_n, cfg.post_nms_top_n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
+        ret_bbox3d = torch.empty(B, cfg.post_nms_top_n, 7, dtype=torch.float32, device=scores.device)
+        ret_scores = torch.empty(B, cfg.post_nms_top_n, dtype=torch.float32, device=scores.device)
+        _lib.check(L.jmb_proposal_layer(B, N, proposals.data_ptr(), scores.data_ptr(), order.data_ptr(),
+                                        cfg.pre_nms_top_n, cfg.post_nms_top_n, float(cfg.nms_thresh),
+                                        int(cfg.nms_type == "rotate"), ret_bbox3d.data_ptr(), ret_scores.data_ptr(),
+                                        ws.data_ptr(), ws_bytes, st), "proposal_layer")
         return ret_bbox3d, ret_scores
 
     def distance_based_proposal(self, scores, proposals, order):

@@ -168,3 +168,30 @@ def test_rpn_backbone_vs_cpu_oracle(cuda, cref):
     got_xyz, got = net_gpu(xyz.to(cuda), None, xy.to(cuda), image_maps=maps_gpu)
     assert torch.equal(got_xyz.cpu(), want_xyz) and got.shape == (1, 128, 2048)
     assert _rel(got.cpu().numpy(), want.numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_batched_proposal_layer_equals_reference_loop(cuda):
+    """csrc/proposal.cu (4 kernels, no host sync) vs the reference's per-frame / per-bin procedure
+    (proposal_layer.py:36-121) executed with this package's single-set NMS: identical boxes and scores."""
+    from jmodt_b200.detector import ProposalLayer, RpnConfig
+    from jmodt_b200.synth import make_batch
+    g = torch.Generator().manual_seed(9)
+    for case, post in [("both bins", 128), ("far bin empty", 100), ("near bin empty", 64)]:
+        cfg = RpnConfig(post_nms_top_n=post)
+        B, N = 3, 16384
+        xyz = torch.from_numpy(make_batch(70, B, with_image=False)["pts"]).to(cuda)
+        if case == "far bin empty":
+            xyz[..., 2] = xyz[..., 2].clamp(max=35.0)
+        if case == "near bin empty":
+            xyz[..., 2] = xyz[..., 2] * 0.3 + 45.0
+        reg = (torch.randn(B, N, 76, generator=g) * 0.5).to(cuda)
+        scores = torch.randn(B, N, generator=g).to(cuda)
+        layer = ProposalLayer(cfg=cfg)
+        boxes_b, scores_b = layer(scores, reg, xyz)
+        layer.batched = False
+        boxes_l, scores_l = layer(scores, reg, xyz)
+        assert boxes_b.shape == (B, post, 7)
+        assert torch.equal(scores_b, scores_l), case
+        assert torch.equal(boxes_b, boxes_l), case
+        assert (scores_b != 0).any()
