@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace jmb {
 
@@ -156,6 +157,182 @@ fps_kernel_large(int n, int m, int bs, int log2bs, int S, const float *__restric
     }
 }
 
+// ---- cluster FPS: one frame spread over CL thread blocks (distributed shared memory) --------------------
+// For small batches one SM per frame leaves the chip idle while a 4095-step dependency chain runs.  Here the
+// points of a frame live in the REGISTERS of CL*T threads (PPT each); every iteration each CTA reduces to its own
+// best (distance, rank) and the owning thread pushes a 5-word record (distance, rank, x, y, z) into the shared
+// memory of ALL CTAs of the cluster with st.shared::cluster, then arrives on their mbarriers; each CTA waits for CL
+// arrivals and picks the global winner locally — one __syncthreads and one DSMEM exchange per iteration, no global
+// memory traffic.  Same rank layout as fps_kernel, so the choice among ties is the reference's.
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int CL, int T, int PPT>
+__global__ void __launch_bounds__(T)
+fps_cluster_kernel(int n, int m, int bs, int log2bs, int S, const float *__restrict__ dataset,
+                   float *__restrict__ temp_out, int *__restrict__ idxs) {
+    constexpr int STRIDE = CL * T;  // slots per j
+    __shared__ int s_d[2][32];
+    __shared__ unsigned s_r[2][32];
+    __shared__ __align__(16) unsigned s_rec[2][CL][8];   // (dist bits, rank, x, y, z)
+    __shared__ __align__(8) unsigned long long s_bar[2];
+
+    unsigned cta;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
+    const int frame = blockIdx.x / CL;
+    const int t = threadIdx.x;
+    const unsigned lane = lane_id();
+    const int warp = t >> 5;
+    const float *pts = dataset + (size_t)frame * n * 3;
+    int *out = idxs + (size_t)frame * m;
+
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&s_bar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&s_bar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int r = j * STRIDE + (int)cta * T + t;
+        const int k = fps_slot_to_point(r, bs, log2bs, S, n);
+        const bool valid = k < n;
+        px[j] = valid ? __ldg(pts + (size_t)k * 3) : 0.f;
+        py[j] = valid ? __ldg(pts + (size_t)k * 3 + 1) : 0.f;
+        pz[j] = valid ? __ldg(pts + (size_t)k * 3 + 2) : 0.f;
+        tmp[j] = valid ? 1e10f : -1.0f;
+    }
+    // every CTA's barriers must be initialised before anyone arrives on them remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    float x1 = __ldg(pts), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);  // point 0 (rank 0)
+    if (cta == 0 && t == 0) out[0] = 0;
+
+    for (int it = 1; it < m; ++it) {
+        if (t == 0)  // arm this iteration's barrier: CL records of 20 bytes will land in s_rec[it & 1]
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(&s_bar[it & 1])), "r"(CL * 20) : "memory");
+        float best = -1.0f;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = dist2_ref(px[j] - x1, py[j] - y1, pz[j] - z1);
+            const float d2 = fminf(d, tmp[j]);
+            tmp[j] = d2;
+            if (d2 > best) { best = d2; bj = j; }
+        }
+        const int db = __float_as_int(best);
+        const unsigned rr = (unsigned)(bj * STRIDE + (int)cta * T + t);
+        int wm = __reduce_max_sync(0xffffffffu, db);
+        unsigned wr = __reduce_min_sync(0xffffffffu, db == wm ? rr : 0xffffffffu);
+        const int buf = it & 1;
+        if (T > 32) {
+            if (lane == 0) { s_d[buf][warp] = wm; s_r[buf][warp] = wr; }
+            __syncthreads();
+            const int vd = (int)lane < T / 32 ? s_d[buf][lane] : (int)0x80000000;
+            const unsigned vr = (int)lane < T / 32 ? s_r[buf][lane] : 0xffffffffu;
+            wm = __reduce_max_sync(0xffffffffu, vd);
+            wr = __reduce_min_sync(0xffffffffu, vd == wm ? vr : 0xffffffffu);
+        }
+        // The warp that owns this CTA's best point publishes it: lanes 0..CL-1 each push the 20-byte record into one
+        // CTA of the cluster with st.async, which completes transaction bytes on that CTA's mbarrier — no release
+        // fence, no serialised remote arrives.
+        {
+            const bool iswin = (rr == wr) && (db == wm);
+            const unsigned wmask = __ballot_sync(0xffffffffu, iswin);
+            if (wmask) {
+                const int src = __ffs(wmask) - 1;
+                float wx = px[0], wy = py[0], wz = pz[0];
+#pragma unroll
+                for (int j = 1; j < PPT; ++j)
+                    if (j == bj) { wx = px[j]; wy = py[j]; wz = pz[j]; }
+                wx = __shfl_sync(0xffffffffu, wx, src);
+                wy = __shfl_sync(0xffffffffu, wy, src);
+                wz = __shfl_sync(0xffffffffu, wz, src);
+                if (lane < (unsigned)CL) {
+                    uint32_t rec_remote, bar_remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rec_remote) : "r"(fps_smem_u32(&s_rec[buf][cta][0])), "r"(lane));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_remote) : "r"(fps_smem_u32(&s_bar[buf])), "r"(lane));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rec_remote),
+                                 "r"((unsigned)wm), "r"(wr), "r"(__float_as_uint(wx)), "r"(__float_as_uint(wy)), "r"(bar_remote)
+                                 : "memory");
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(rec_remote + 16),
+                                 "r"(__float_as_uint(wz)), "r"(bar_remote)
+                                 : "memory");
+                }
+            }
+        }
+        // wait for the CL records of this iteration (the k-th use of a buffer completes its phase k)
+        {
+            const uint32_t bar = fps_smem_u32(&s_bar[buf]);
+            const uint32_t parity = (uint32_t)(((it - 1) >> 1) & 1);
+            uint32_t done;
+            do {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}\n"
+                    : "=r"(done)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
+            } while (!done);
+        }
+        int gd = (int)0x80000000;
+        unsigned gr = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+            const uint4 rec = *reinterpret_cast<const uint4 *>(&s_rec[buf][c][0]);
+            const int d = (int)rec.x;
+            if (d > gd || (d == gd && rec.y < gr)) {
+                gd = d; gr = rec.y;
+                x1 = __uint_as_float(rec.z); y1 = __uint_as_float(rec.w); z1 = __uint_as_float(s_rec[buf][c][4]);
+            }
+        }
+        if (cta == 0 && t == 0) out[it] = fps_slot_to_point((int)gr, bs, log2bs, S, n);
+    }
+
+    if (temp_out != nullptr) {
+        float *tp = temp_out + (size_t)frame * n;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int k = fps_slot_to_point(j * STRIDE + (int)cta * T + t, bs, log2bs, S, n);
+            if (k < n) tp[k] = tmp[j];
+        }
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CL, int T, int PPT>
+static int launch_fps_cluster(int b, int n, int m, int bs, int log2bs, int S, const float *dataset, float *temp,
+                              int *idxs, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * CL);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CL > 8) {
+        static bool allowed = false;
+        if (!allowed) {
+            cudaFuncSetAttribute(fps_cluster_kernel<CL, T, PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            allowed = true;
+        }
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL, T, PPT>, n, m, bs, log2bs, S, dataset, temp, idxs);
+    if (e != cudaSuccess) {
+        set_error("fps(cluster): %s", cudaGetErrorString(e));
+        return JMB_ERR_CUDA;
+    }
+    return check_launch("furthest_point_sampling(cluster)");
+}
+
 template <int T, int PPT>
 static int launch_fps(int b, int n, int m, int bs, int log2bs, int S, const float *dataset,
                       float *temp, int *idxs, cudaStream_t st) {
@@ -241,6 +418,48 @@ extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dat
         JMB_REQUIRE(temp != nullptr, "fps: n=%d needs the temp buffer", n);
         fps_kernel_large<<<b, 1024, 0, st>>>(n, m, bs, log2bs, S, dataset, temp, idxs);
         return check_launch("furthest_point_sampling(large)");
+    }
+    // small batches: spread each frame over a thread-block cluster (latency); large batches: one CTA per frame
+    // (throughput).  sms*2 is the point where single-CTA kernels already fill the machine.
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    if (m > 1) {
+        static int cfg_override = -1;   // JMB_FPS_CFG: tuning aid for profiles/fps_tune.py
+        if (cfg_override < 0) { const char *e = getenv("JMB_FPS_CFG"); cfg_override = e ? atoi(e) : 0; }
+        if (cfg_override > 0 && slots == 16384) {
+            switch (cfg_override) {
+                case 1: return launch_fps_cluster<8, 512, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 2: return launch_fps_cluster<8, 256, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 3: return launch_fps_cluster<8, 128, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 4: return launch_fps_cluster<16, 256, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 5: return launch_fps_cluster<16, 128, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 6: return launch_fps_cluster<4, 512, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 7: return launch_fps_cluster<16, 64, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                default: break;
+            }
+        }
+        if (cfg_override > 0 && slots == 4096) {
+            switch (cfg_override) {
+                case 1: return launch_fps_cluster<4, 256, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 2: return launch_fps_cluster<8, 128, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 3: return launch_fps_cluster<4, 128, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 4: return launch_fps_cluster<8, 64, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 5: return launch_fps_cluster<2, 256, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 6: return launch_fps_cluster<16, 64, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 7: return launch_fps_cluster<2, 128, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                default: break;
+            }
+        }
+        // measured on B200 (profiles/fps_tune.py): 16384 points: 8 CTAs x 256 threads x 8 points = 2.93 ms vs 6.0 ms
+        // for one CTA; at 4096 points the per-iteration exchange latency cancels the gain, so one CTA is kept.
+        if (slots > 8192 && slots <= 16384 && (long long)b * 8 <= 2LL * sms)
+            return launch_fps_cluster<8, 256, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+        if (slots > 4096 && slots <= 8192 && (long long)b * 8 <= 2LL * sms)
+            return launch_fps_cluster<8, 256, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
     }
     int T = pow2_ceil((slots + 3) / 4);
     if (T < 32) T = 32;
