@@ -156,11 +156,13 @@ JMB_API int jmb_nms_normal(int n, const float *boxes, float thresh, int64_t *kee
  *           point idx[g][n] (or n % n_pts if idx is NULL); rows 0-2 are xyz[g][point] - centres[g][n / nsample]
  *           (no centring if centres is NULL), rows 3.. are x[g][k-3][point] with x = feats (G, K-3, n_pts).
  *   out_mode 0: y (G, M, N);  out_mode 1: max over each `pool` consecutive columns -> y (G, M, N / pool)
- *           (the set-abstraction max-pool, pointnet2_modules.py:50-52). */
+ *           (the set-abstraction max-pool, pointnet2_modules.py:50-52).
+ *   y_group_stride: elements between groups of y (0 = dense); lets a layer write into a channel slice of a wider
+ *           (G, C_total, N) tensor, replacing torch.cat. */
 JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
                              const float *x, long long x_group_stride, int x_row_stride, const int *idx,
                              const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
-                             int pool, int relu, float *y, void *stream);
+                             int pool, int relu, float *y, long long y_group_stride, void *stream);
 
 /* ---- LI-Fusion image feature sampling ---------------------------------------------------- */
 

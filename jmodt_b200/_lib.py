@@ -44,7 +44,7 @@ SIGNATURES = {
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _vp],
 }
 _RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz, "jmb_proposal_workspace_bytes": _sz}
 

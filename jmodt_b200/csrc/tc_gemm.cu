@@ -47,6 +47,7 @@ struct TcGemmParams {
     int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool)
     int pool, relu;
     float *y;
+    long long y_group_stride;     // elements between consecutive groups of y (>= M*N, lets a layer write into a slice of a wider tensor)
 };
 
 __global__ void __launch_bounds__(TC_THREADS)
@@ -207,7 +208,7 @@ tc_gemm_kernel(const TcGemmParams p) {
             const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
             if (p.out_mode == 0) {
-                float *yrow = p.y + ((size_t)g * p.M + m) * p.N + (size_t)nt * TC_BN;
+                float *yrow = p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + (size_t)nt * TC_BN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < TC_BN; c0 += 32) {
                     float v[32];
@@ -235,7 +236,7 @@ tc_gemm_kernel(const TcGemmParams p) {
                 // max-pool over windows of `pool` columns (pool divides 128; windows never straddle a tile).
                 // N % pool == 0, so a window is either fully inside [0, N) or fully outside.
                 const int groups_per_row = p.N / p.pool;
-                float *yrow = p.y + ((size_t)g * p.M + m) * groups_per_row + (size_t)(nt * TC_BN) / p.pool;
+                float *yrow = p.y + (size_t)g * p.y_group_stride + (size_t)m * groups_per_row + (size_t)(nt * TC_BN) / p.pool;
                 const int sub = p.pool < 32 ? p.pool : 32;      // window length inside one 32-column chunk
                 float run = -INFINITY;
 #pragma unroll 1
@@ -312,7 +313,7 @@ tc_gemm_kernel(const TcGemmParams p) {
 extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
                                         const float *x, long long x_group_stride, int x_row_stride, const int *idx,
                                         const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
-                                        int pool, int relu, float *y, void *stream) {
+                                        int pool, int relu, float *y, long long y_group_stride, void *stream) {
     using namespace jmb;
     JMB_REQUIRE(M > 0 && K > 0 && G >= 0 && N >= 0, "tc_mlp_layer: bad sizes");
     if (G == 0 || N == 0) return JMB_OK;
@@ -328,6 +329,7 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.G = G; p.N = N; p.mode = mode; p.x = x; p.x_group_stride = x_group_stride; p.x_row_stride = x_row_stride;
     p.idx = idx; p.xyz = xyz; p.centres = centres; p.nsample = nsample; p.n_pts = n_pts;
     p.out_mode = out_mode; p.pool = pool; p.relu = relu; p.y = y;
+    p.y_group_stride = y_group_stride > 0 ? y_group_stride : (long long)M * (out_mode ? N / pool : N);
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;

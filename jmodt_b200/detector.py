@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, box_utils, tc
-from .head import RCNN, HeadConfig, affinity
+from .head import RCNN, HeadConfig, affinity, affinity_batched
 from .iou3d import iou3d_cuda
 from .pointnet2 import pytorch_utils as pt_utils
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
@@ -415,4 +415,6 @@ class PointRCNN(nn.Module):
     def pair_affinity(self, rcnn_feat, rois_per_frame):
         """Link / start-end scores between consecutive frames (t, t+1) of a batch: rcnn_feat (B*M, 512, 1)."""
         f = rcnn_feat.view(-1, rois_per_frame, rcnn_feat.shape[1])
-        return [affinity(self.rcnn_net, f[i], f[i + 1]) for i in range(0, f.shape[0] - 1, 2)]
+        npairs = f.shape[0] // 2
+        link, start, end, logits = affinity_batched(self.rcnn_net, f[0:2 * npairs:2], f[1:2 * npairs:2])
+        return [(link[i], start[i], end[i], logits[i]) for i in range(npairs)]

@@ -159,8 +159,14 @@ class RCNN(nn.Module):
         xyz = pts_input[..., 0:3].contiguous()
         xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()                   # (G, 5, 512)
         rpn_feature = pts_input[..., cin:].transpose(1, 2)                                # (G, 128, 512)
-        xyz_feature = run_stack(P["xyz_up"], xyz_input)
-        merged = run_stack(P["merge_down"], torch.cat((xyz_feature, rpn_feature), dim=1).contiguous())
+        c_up = P["xyz_up"][-1].M
+        both = torch.empty((xyz.shape[0], c_up + rpn_feature.shape[1], xyz.shape[1]), dtype=torch.float32,
+                           device=xyz.device)                                          # cat((xyz_feature, rpn_feature))
+        both[:, c_up:].copy_(rpn_feature)
+        h = xyz_input
+        for i, layer in enumerate(P["xyz_up"]):
+            h = tc.mlp_layer(layer, h, out=both[:, :c_up] if i == len(P["xyz_up"]) - 1 else None)
+        merged = run_stack(P["merge_down"], both)
         l_xyz, l_feat = xyz, merged
         for sa, packed in zip(self.SA_modules, P["sa"]):
             grouper = sa.groupers[0]
@@ -193,6 +199,24 @@ class RCNN(nn.Module):
         pts_input, empty = self.pool_rois(input_data)
         rcnn_cls, rcnn_reg, feat = self.forward_points(pts_input)
         return {"rcnn_cls": rcnn_cls, "rcnn_reg": rcnn_reg, "rcnn_feat": feat, "pooled_empty_flag": empty}
+
+
+@torch.no_grad()
+def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
+    """`affinity` for G frame pairs at once: pred_features (G, P, 512), det_features (G, D, 512) ->
+    link (G, P, D), start (G, D), end (G, P), logits (G, P, D).  One launch per layer for all pairs."""
+    G, P, _ = pred_features.shape
+    D = det_features.shape[1]
+    packed = rcnn.packed
+    pt = pred_features.transpose(1, 2).contiguous()                                       # (G, 512, P)
+    dt = det_features.transpose(1, 2).contiguous()                                        # (G, 512, D)
+    cor = (pt.unsqueeze(3) - dt.unsqueeze(2)).abs().contiguous()                          # (G, 512, P, D)
+    logits = run_stack(packed["link"], cor.view(G, -1, P * D)).view(G, P, D)
+    col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)       # softmax over predecessors
+    link = (torch.softmax(logits, dim=2) + col) / 2
+    start = torch.sigmoid(run_stack(packed["se"], cor.mean(dim=2).contiguous())).view(G, D)
+    end = torch.sigmoid(run_stack(packed["se"], cor.mean(dim=3).contiguous())).view(G, P)
+    return link, start, end, logits
 
 
 @torch.no_grad()

@@ -80,17 +80,20 @@ def fold_conv_bn(conv, bn=None):
 
 def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None = None,
               pool: int = 0) -> torch.Tensor:
-    """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0."""
+    """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0.
+    `out` may be a channel slice `buf[:, c0:c0+M]` of a wider contiguous (G, C, N) tensor (replaces torch.cat)."""
     assert x.dim() == 3 and x.is_contiguous() and x.dtype == torch.float32
     G, K, N = x.shape
     assert K == layer.K
     shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
     y = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
+    assert tuple(y.shape) == shape and y.stride(2) == 1 and y.stride(1) == shape[2]
+    y_gs = y.stride(0) if G > 1 else 0
     st = _lib.stream_and_device(x)
     profiler.launch(2.0 * layer.M * K * G * N, lambda: _lib.check(
         _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
                                     x.data_ptr(), K * N, N, None, None, None, 0, 0,
-                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st), "tc_mlp_layer"))
+                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), y_gs, st), "tc_mlp_layer"))
     return y
 
 
@@ -112,7 +115,7 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
         _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, layer.K, G, N, 1,
                                     fx.data_ptr(), C * n_pts, n_pts, _lib.ptr(idx), xyz.data_ptr(),
                                     _lib.ptr(centres), nsample if centres is not None else 0, n_pts,
-                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), st),
+                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), 0, st),
         "tc_mlp_layer(grouped)"))
     return y
 
