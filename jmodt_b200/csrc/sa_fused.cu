@@ -4,26 +4,33 @@
 // QueryAndGroup's two group_points launches + subtract + cat (pointnet2_utils.py:241-264), three cuDNN 1x1 convs
 // over (B, C, npoint, nsample) (pytorch_utils.py:6-33) and F.max_pool2d.  At the RCNN SA0 shape the reference
 // round-trips a 549 MB/frame grouped tensor and two 537 MB/frame activations through HBM; here a tile of 128
-// (centre, sample) columns never leaves the SM:
+// (centre, sample) columns never leaves the SM, and NO weight is re-read after the prologue:
 //
-//   workers (8 warps)   gather the layer-1 operand X1 (K1 x 128) straight into its UMMA shared-memory image
-//                       (bf16 hi/lo split in registers), later turn each layer's TMEM accumulator into the next
-//                       layer's operand image (bias, ReLU, split, 16-byte stores), and max-pool the last layer;
-//   issuer (1 thread)   streams the weight chunk images with cp.async.bulk through a 4-stage ring and issues
-//                       tcgen05.mma (three bf16 MMAs per fp32 product: W_hi.X_hi + W_lo.X_hi + W_hi.X_lo);
-//   the next tile's gather overlaps the current tile's layer-2 MMAs.
+//   * layer-1 weights (K1 <= 160) stay in shared memory for the lifetime of the persistent CTA (A operand, SS MMA);
+//   * layer-2 / layer-3 weights (bf16 hi and lo parts) stay in TENSOR MEMORY and are the A operand of TS-mode MMAs
+//     (TMEM map: 128 accumulator columns, 128 for W2, 128 per 128-row block of W3 -> at most 512);
+//   * a tile is processed as two 64-column halves with separate accumulators, operand images and worker groups
+//     (4 warps each), so one half's epilogue (TMEM -> bias/ReLU -> bf16 split -> next operand image, or max-pool)
+//     and its gather of the NEXT tile run while the tensor core works on the other half;
+//   * every fp32 product is three bf16 MMAs accumulated in fp32: W_hi.X_hi + W_lo.X_hi + W_hi.X_lo.
 //
 // Shapes: layer widths C1 = C2 = 128, C3 in {128, 256}; 3 + C_in = K1 <= 160; nsample in {8,...,64} dividing 64.
 #include "tc_common.cuh"
 
 namespace jmb {
 
-constexpr int SF_WORKERS = 256;
-constexpr int SF_THREADS = SF_WORKERS + 64;  // + warp 8: MMA issuer, warp 9: weight loader
-constexpr int SF_WSTAGES = 4;
+constexpr int SF_GROUP = 128;                 // threads per worker group (one 64-column half each)
+constexpr int SF_WORKERS = 2 * SF_GROUP;
+constexpr int SF_THREADS = SF_WORKERS + 32;   // + warp 8: MMA issuer
 constexpr int SF_MAXKC1 = 5;
-constexpr int SF_CHUNK = 2 * TC_IMG;  // hi + lo image of one 32-row chunk: 16 KB
-constexpr int SF_SMEM = (SF_WSTAGES + SF_MAXKC1 + 4) * SF_CHUNK;  // W ring + X1 + activations = 208 KB
+constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chunk: 16 KB
+constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
+constexpr int SF_HALF = 64;
+constexpr uint32_t SF_HALF_OFF = (SF_HALF / 8) * TC_SBO;           // byte offset of the second half inside an image
+// kind::f16, BF16 x BF16 -> F32, M=128, N=64, A K-major, B MN-major
+constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                              ((uint32_t)(SF_HALF >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bases (hi at +0, lo at +64 of each block)
 
 struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
@@ -37,28 +44,75 @@ struct SaFusedParams {
     float *out;            // (G, 128*Mt3, npoint)
 };
 
+__device__ __forceinline__ void umma_ss64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(SF_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts64(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(SF_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// Row m of a packed 128 x 128 weight block (4 chunk images of 128 x 32) -> 64 TMEM columns (bf16 pairs) of lane m.
+__device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_block, int part /*0 hi, 1 lo*/, int m,
+                                                    uint32_t taddr) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {        // 32 columns (two K chunks) per tcgen05.st
+        uint32_t r[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int kc = half * 2 + cc;
+            const uint8_t *img = reinterpret_cast<const uint8_t *>(wpack_block) + (size_t)kc * SF_CHUNK + (size_t)part * TC_IMG;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + k8 * TC_LBO + (m >> 3) * TC_SBO + (m & 7) * 16));
+                r[cc * 16 + k8 * 4 + 0] = v.x; r[cc * 16 + k8 * 4 + 1] = v.y;
+                r[cc * 16 + k8 * 4 + 2] = v.z; r[cc * 16 + k8 * 4 + 3] = v.w;
+            }
+        }
+        tmem_st32(taddr + half * 32, r);
+    }
+}
+
 __global__ void __launch_bounds__(SF_THREADS, 1)
 sa_fused_kernel(const SaFusedParams p) {
     extern __shared__ __align__(1024) uint8_t sf_smem[];
-    uint8_t *s_w = sf_smem;
-    uint8_t *s_x1 = sf_smem + SF_WSTAGES * SF_CHUNK;
+    uint8_t *s_w1 = sf_smem;
+    uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[SF_MAXKC1], s_w_full[SF_WSTAGES], s_w_empty[SF_WSTAGES], s_acc_full,
-        s_epi_done;
+    __shared__ __align__(8) uint64_t s_x1_full[2][SF_MAXKC1], s_acc_full[2], s_epi_done[2], s_w1_full;
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int c = 0; c < SF_MAXKC1; ++c) mbar_init(&s_x1_full[c], SF_WORKERS);
-        for (int s = 0; s < SF_WSTAGES; ++s) { mbar_init(&s_w_full[s], 1); mbar_init(&s_w_empty[s], 1); }
-        mbar_init(&s_acc_full, 1);
-        mbar_init(&s_epi_done, SF_WORKERS);
+        for (int h = 0; h < 2; ++h) {
+            for (int c = 0; c < SF_MAXKC1; ++c) mbar_init(&s_x1_full[h][c], SF_GROUP);
+            mbar_init(&s_acc_full[h], 1);
+            mbar_init(&s_epi_done[h], SF_GROUP);
+        }
+        mbar_init(&s_w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                     "r"((uint32_t)TC_BN)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -67,24 +121,46 @@ sa_fused_kernel(const SaFusedParams p) {
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
+    // ---- prologue: all weights become resident (W1 in shared memory, W2 / W3 in tensor memory) ----
+    if (threadIdx.x == SF_WORKERS) {
+        mbar_arrive_expect_tx(&s_w1_full, (uint32_t)p.Kc1 * SF_CHUNK);
+        for (int c = 0; c < p.Kc1; ++c)
+            bulk_g2s(s_w1 + (size_t)c * SF_CHUNK, p.w1 + (size_t)c * (SF_CHUNK / 2), SF_CHUNK, &s_w1_full);
+    }
+    if (warp < 4) {
+        const int m = warp * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        weight_rows_to_tmem(p.w2, 0, m, lane_base + SF_TMEM_W2);
+        weight_rows_to_tmem(p.w2, 1, m, lane_base + SF_TMEM_W2 + 64);
+        for (int mt = 0; mt < p.Mt3; ++mt) {
+            const __nv_bfloat16 *blk = p.w3 + (size_t)mt * 4 * (SF_CHUNK / 2);
+            weight_rows_to_tmem(blk, 0, m, lane_base + SF_TMEM_W3 + mt * 128);
+            weight_rows_to_tmem(blk, 1, m, lane_base + SF_TMEM_W3 + mt * 128 + 64);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
     const int N = p.npoint * p.nsample;
     const int Nt = N / TC_BN;
     const long long total_tiles = (long long)p.G * Nt;
     const int kmax16 = ((p.K1 + 15) / 16) * 16;  // rows the layer-1 MMAs actually read
 
     if (warp < 8) {
-        // ====================================== workers ======================================
-        const int t = threadIdx.x;
-        const int kk = t & 7, ng = (t >> 3) & 15, kbsel = t >> 7;
-        const int quad = warp & 3, half = warp >> 2;
+        // ====================================== workers: group h owns columns [64h, 64h+64) ======================================
+        const int h = warp >> 2, quad = warp & 3;
+        const int tg = threadIdx.x & (SF_GROUP - 1);
+        const int kk = tg & 7, ng = (tg >> 3) & 7, kbsel = tg >> 6;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread in the epilogues
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * SF_HALF;
         uint32_t acc_phase = 0;
 
         auto produce_x1 = [&](long long tile, int c_begin, int c_end) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
-            const int n0 = nt * TC_BN + ng * 8;  // 8 columns of one centre (nsample % 8 == 0)
+            const int n0 = nt * TC_BN + h * SF_HALF + ng * 8;  // 8 columns of one centre (nsample % 8 == 0)
             int pidx[8];
             {
                 const int4 a = __ldg(reinterpret_cast<const int4 *>(p.idx + (size_t)g * N + n0));
@@ -116,42 +192,42 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __ldg(row + pidx[j]);
                     }
-                    uint4 h, l;
-                    split2(v[0], v[1], h.x, l.x);
-                    split2(v[2], v[3], h.y, l.y);
-                    split2(v[4], v[5], h.z, l.z);
-                    split2(v[6], v[7], h.w, l.w);
-                    const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)kbl * TC_LBO + (uint32_t)kk * 16;
-                    *reinterpret_cast<uint4 *>(xhi + off) = h;
-                    *reinterpret_cast<uint4 *>(xlo + off) = l;
+                    uint4 hh, ll;
+                    split2(v[0], v[1], hh.x, ll.x);
+                    split2(v[2], v[3], hh.y, ll.y);
+                    split2(v[4], v[5], hh.z, ll.z);
+                    split2(v[6], v[7], hh.w, ll.w);
+                    const uint32_t off = (uint32_t)(h * 8 + ng) * TC_SBO + (uint32_t)kbl * TC_LBO + (uint32_t)kk * 16;
+                    *reinterpret_cast<uint4 *>(xhi + off) = hh;
+                    *reinterpret_cast<uint4 *>(xlo + off) = ll;
                 }
                 fence_proxy_async();
-                mbar_arrive(&s_x1_full[c]);
+                mbar_arrive(&s_x1_full[h][c]);
             }
         };
 
-        // accumulator -> next layer's operand image (row m of the accumulator is row k = m of the operand)
+        // accumulator half -> next layer's operand image (row m of the accumulator is row k = m of the operand)
         auto epilogue_act = [&](const float *bias_ptr) {
             const float bias = __ldg(bias_ptr + m);
             uint8_t *ahi = s_act + (size_t)quad * SF_CHUNK, *alo = ahi + TC_IMG;
             const uint32_t rowoff = (uint32_t)(lane >> 3) * TC_LBO + (uint32_t)(lane & 7) * 16;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+            for (int c0 = 0; c0 < SF_HALF; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint4 h, l;
+                    uint4 hh, ll;
                     float *w = v + q * 8;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) w[j] = fmaxf(w[j] + bias, 0.f);
-                    split2(w[0], w[1], h.x, l.x);
-                    split2(w[2], w[3], h.y, l.y);
-                    split2(w[4], w[5], h.z, l.z);
-                    split2(w[6], w[7], h.w, l.w);
-                    const uint32_t off = (uint32_t)(half * 8 + (c0 >> 3) + q) * TC_SBO + rowoff;
-                    *reinterpret_cast<uint4 *>(ahi + off) = h;
-                    *reinterpret_cast<uint4 *>(alo + off) = l;
+                    split2(w[0], w[1], hh.x, ll.x);
+                    split2(w[2], w[3], hh.y, ll.y);
+                    split2(w[4], w[5], hh.z, ll.z);
+                    split2(w[6], w[7], hh.w, ll.w);
+                    const uint32_t off = (uint32_t)(h * 8 + (c0 >> 3) + q) * TC_SBO + rowoff;
+                    *reinterpret_cast<uint4 *>(ahi + off) = hh;
+                    *reinterpret_cast<uint4 *>(alo + off) = ll;
                 }
             }
         };
@@ -161,11 +237,11 @@ sa_fused_kernel(const SaFusedParams p) {
             const int g = (int)(tile / Nt);
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
             float *orow = p.out + ((size_t)g * (TC_BM * p.Mt3) + mt * TC_BM + m) * p.npoint +
-                          (nt * TC_BN + half * 64) / p.nsample;
+                          (nt * TC_BN + h * SF_HALF) / p.nsample;
             const int sub = p.nsample < 32 ? p.nsample : 32;
             float run = -INFINITY;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+            for (int c0 = 0; c0 < SF_HALF; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -192,97 +268,85 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         const long long first = blockIdx.x;
-        const int csplit = (p.Kc1 + 1) / 2;   // next tile's gather is split over the layer-2 and layer-3 MMA windows
+        const int csplit = (p.Kc1 + 1) / 2;   // the next tile's gather is split over the layer-2 and layer-3 windows
         if (first < total_tiles) produce_x1(first, 0, p.Kc1);
         for (long long tile = first; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
+            const bool more = tile + gridDim.x < total_tiles;
+            mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;        // layer 1 of this half done: its X1 half is free
             tc_fence_after();
             epilogue_act(p.b1);
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(&s_epi_done);
-            const bool more = tile + gridDim.x < total_tiles;
-            if (more) produce_x1(tile + gridDim.x, 0, csplit);          // overlaps the layer-2 MMAs
+            mbar_arrive(&s_epi_done[h]);
+            if (more) produce_x1(tile + gridDim.x, 0, csplit);
 
-            mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
+            mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
             tc_fence_after();
             epilogue_act(p.b2);
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(&s_epi_done);
-            if (more) produce_x1(tile + gridDim.x, csplit, p.Kc1);      // overlaps the layer-3 MMAs
+            mbar_arrive(&s_epi_done[h]);
+            if (more) produce_x1(tile + gridDim.x, csplit, p.Kc1);
 
             for (int mt = 0; mt < p.Mt3; ++mt) {
-                mbar_wait(&s_acc_full, acc_phase); acc_phase ^= 1;
+                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
                 epilogue_pool(tile, mt);
                 tc_fence_before();
-                mbar_arrive(&s_epi_done);
+                mbar_arrive(&s_epi_done[h]);
             }
         }
-    } else if (warp == 9) {
-        if (lane == 0) {
-            // ====================================== weight loader ======================================
-            // The weight stream of a tile is fixed (Kc1 + 4 + 4*Mt3 chunk images); run ahead of the issuer through
-            // the ring so a layer's first chunk is already in shared memory when its MMAs may start.
-            const int CH = p.Kc1 + 4 + 4 * p.Mt3;
-            long long my_tiles = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
-            const long long total_chunks = my_tiles * CH;
-            for (long long wreq = 0; wreq < total_chunks; ++wreq) {
-                const int s = (int)(wreq % SF_WSTAGES);
-                int j = (int)(wreq % CH);
-                const __nv_bfloat16 *src;
-                if (j < p.Kc1) src = p.w1 + (size_t)j * (SF_CHUNK / 2);
-                else if (j < p.Kc1 + 4) src = p.w2 + (size_t)(j - p.Kc1) * (SF_CHUNK / 2);
-                else src = p.w3 + (size_t)(j - p.Kc1 - 4) * (SF_CHUNK / 2);
-                mbar_wait(&s_w_empty[s], (uint32_t)(((wreq / SF_WSTAGES) & 1) ^ 1));
-                mbar_arrive_expect_tx(&s_w_full[s], SF_CHUNK);
-                bulk_g2s(s_w + (size_t)s * SF_CHUNK, src, SF_CHUNK, &s_w_full[s]);
-            }
-        }
-        __syncwarp();
     } else {
         if (lane == 0) {
             // ====================================== MMA issuer ======================================
-            long long wuse = 0;
-            auto mma_chunk = [&](uint32_t b_base, int k16_steps, bool first_of_layer) {
-                const int s = (int)(wuse % SF_WSTAGES);
-                mbar_wait(&s_w_full[s], (uint32_t)((wuse / SF_WSTAGES) & 1));
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(s_w + (size_t)s * SF_CHUNK);
-                for (int k16 = 0; k16 < k16_steps; ++k16) {
-                    const uint32_t koff = (uint32_t)k16 * 2 * TC_LBO;
-                    const uint64_t whi = make_smem_desc(a_base + koff), wlo = make_smem_desc(a_base + TC_IMG + koff);
-                    const uint64_t xhi = make_smem_desc(b_base + koff), xlo = make_smem_desc(b_base + TC_IMG + koff);
-                    umma_ss(tmem_base, whi, xhi, !(first_of_layer && k16 == 0));
-                    umma_ss(tmem_base, wlo, xhi, 1);
-                    umma_ss(tmem_base, whi, xlo, 1);
-                }
-                umma_commit(&s_w_empty[s]);
-                ++wuse;
-            };
-            uint32_t epi_phase = 0, tile_ctr = 0;
-            bool first_layer_ever = true;
-            auto wait_epilogue = [&]() {
-                if (first_layer_ever) { first_layer_ever = false; return; }
-                mbar_wait(&s_epi_done, epi_phase); epi_phase ^= 1;
+            mbar_wait(&s_w1_full, 0);
+            uint32_t epi_phase[2] = {0, 0};
+            bool first_use[2] = {true, true};
+            uint32_t tile_ctr = 0;
+            auto wait_epilogue = [&](int h) {     // accumulator half h is free / its activation image is ready
+                if (first_use[h]) { first_use[h] = false; return; }
+                mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
                 tc_fence_after();
             };
+            const uint32_t w1_base = smem_u32(s_w1), x1_base = smem_u32(s_x1), act_base = smem_u32(s_act);
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-                // layer 1: operand = gathered X1
-                wait_epilogue();
-                for (int c = 0; c < p.Kc1; ++c) {
-                    mbar_wait(&s_x1_full[c], tile_ctr & 1);
-                    const int rows = kmax16 - c * TC_BK;
-                    mma_chunk(smem_u32(s_x1 + (size_t)c * SF_CHUNK), rows >= 32 ? 2 : 1, c == 0);
+                // layer 1 (SS): A = W1 chunk images in shared memory, B = gathered X1 half
+                for (int h = 0; h < 2; ++h) {
+                    wait_epilogue(h);
+                    const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+                    for (int c = 0; c < p.Kc1; ++c) {
+                        mbar_wait(&s_x1_full[h][c], tile_ctr & 1);
+                        tc_fence_after();
+                        const int steps = (kmax16 - c * TC_BK) >= 32 ? 2 : 1;
+                        for (int k16 = 0; k16 < steps; ++k16) {
+                            const uint32_t koff = (uint32_t)c * SF_CHUNK + (uint32_t)k16 * 2 * TC_LBO;
+                            const uint64_t whi = make_smem_desc(w1_base + koff), wlo = make_smem_desc(w1_base + koff + TC_IMG);
+                            const uint64_t xhi = make_smem_desc(x1_base + koff + h * SF_HALF_OFF);
+                            const uint64_t xlo = make_smem_desc(x1_base + koff + TC_IMG + h * SF_HALF_OFF);
+                            umma_ss64(acc, whi, xhi, (c | k16) != 0);
+                            umma_ss64(acc, wlo, xhi, 1);
+                            umma_ss64(acc, whi, xlo, 1);
+                        }
+                    }
+                    umma_commit(&s_acc_full[h]);
                 }
-                umma_commit(&s_acc_full);
-                // layer 2 and the Mt3 row blocks of layer 3: operand = activation image
+                // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
                 for (int l = 0; l < 1 + p.Mt3; ++l) {
-                    wait_epilogue();
-                    for (int c = 0; c < 4; ++c) mma_chunk(smem_u32(s_act + (size_t)c * SF_CHUNK), 2, c == 0);
-                    umma_commit(&s_acc_full);
+                    const uint32_t wcol = l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128;
+                    for (int h = 0; h < 2; ++h) {
+                        wait_epilogue(h);
+                        const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+#pragma unroll
+                        for (int k16 = 0; k16 < 8; ++k16) {
+                            const uint32_t boff = (uint32_t)(k16 >> 1) * SF_CHUNK + (uint32_t)(k16 & 1) * 2 * TC_LBO + h * SF_HALF_OFF;
+                            const uint64_t xhi = make_smem_desc(act_base + boff), xlo = make_smem_desc(act_base + boff + TC_IMG);
+                            const uint32_t ahi = tmem_base + wcol + (uint32_t)k16 * 8, alo = ahi + 64;
+                            umma_ts64(acc, ahi, xhi, k16 != 0);
+                            umma_ts64(acc, alo, xhi, 1);
+                            umma_ts64(acc, ahi, xlo, 1);
+                        }
+                        umma_commit(&s_acc_full[h]);
+                    }
                 }
             }
         }
@@ -292,7 +356,7 @@ sa_fused_kernel(const SaFusedParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
