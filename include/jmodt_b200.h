@@ -173,11 +173,12 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
 
 /* One whole single-scale set-abstraction layer (reference pointnet2_modules.py:20-63 with QueryAndGroup and a
  * 3-layer SharedMLP of widths 128, 128, C3 in {128,256}) in ONE kernel: grouped gather -> MLP -> max over nsample.
- * w1/w2/w3 are packed layers (jmodt_b200/tc.py), K1 = 3 + C_in <= 160, nsample in {8,16,32,64},
- * npoint*nsample a multiple of 128.  feats (G, K1-3, n_pts), idx (G, npoint, nsample), xyz (G, n_pts, 3),
+ * w2/w3 are packed layers (jmodt_b200/tc.py); w1 is packed with its input columns reordered to [channels, xyz]
+ * (tc.PackedLayer(..., xyz_last=True)).  C_in % 8 == 0, C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample a
+ * multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
  * centres (G, npoint, 3) -> out (G, C3, npoint). */
 JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                         const float *b3, int K1, int C3, int G, int npoint, int nsample, int n_pts,
+                         const float *b3, int C_in, int C3, int G, int npoint, int nsample, int n_pts,
                          const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                          void *stream);
 

@@ -14,7 +14,12 @@
 //     and its gather of the NEXT tile run while the tensor core works on the other half;
 //   * every fp32 product is three bf16 MMAs accumulated in fp32: W_hi.X_hi + W_lo.X_hi + W_hi.X_lo.
 //
-// Shapes: layer widths C1 = C2 = 128, C3 in {128, 256}; 3 + C_in = K1 <= 160; nsample in {8,...,64} dividing 64.
+//   * the gather reads POINT-MAJOR features (G, n_pts, C): one neighbour = one contiguous row, fetched with 16-byte
+//     loads (a channel-first source costs a 32-byte sector per 4-byte element: 8x the L2 traffic, which bounded the
+//     first version of this kernel).  The layer-1 operand is therefore staged K-major (B operand, b_major = K) with
+//     the channels first and the three relative coordinates last; W1's columns are permuted to match at pack time.
+//
+// Shapes: layer widths C1 = C2 = 128, C3 in {128, 256}; C_in % 8 == 0, C_in + 3 <= 160; nsample in {8,...,64} | 64.
 #include "tc_common.cuh"
 
 namespace jmb {
@@ -30,14 +35,18 @@ constexpr uint32_t SF_HALF_OFF = (SF_HALF / 8) * TC_SBO;           // byte offse
 // kind::f16, BF16 x BF16 -> F32, M=128, N=64, A K-major, B MN-major
 constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
                               ((uint32_t)(SF_HALF >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// layer 1: same but B K-major (bit 16 = 0)
+constexpr uint32_t SF_IDESC_L1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
+                                 ((uint32_t)(SF_HALF >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bases (hi at +0, lo at +64 of each block)
 
 struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
     const float *b1, *b2, *b3;
-    int K1, Kc1, Mt3;
+    int K1, Kc1, Mt3;      // K1 = Cp + 3 with Cp = C_in rounded up to 8 (channels first, xyz last)
+    int C;                 // feature channels
     int G, npoint, nsample, n_pts;
-    const float *feats;    // (G, K1-3, n_pts)
+    const float *feats;    // (G, n_pts, C) POINT-MAJOR
     const int *idx;        // (G, npoint, nsample)
     const float *xyz;      // (G, n_pts, 3)
     const float *centres;  // (G, npoint, 3)
@@ -48,7 +57,7 @@ __device__ __forceinline__ void umma_ss64(uint32_t d_tmem, uint64_t a_desc, uint
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(SF_IDESC), "r"(accumulate)
+        "l"(a_desc), "l"(b_desc), "r"(SF_IDESC_L1), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_ts64(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
@@ -96,14 +105,14 @@ sa_fused_kernel(const SaFusedParams p) {
     uint8_t *s_w1 = sf_smem;
     uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[2][SF_MAXKC1], s_acc_full[2], s_epi_done[2], s_w1_full;
+    __shared__ __align__(8) uint64_t s_x1_full[2], s_acc_full[2], s_epi_done[2], s_w1_full;
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int h = 0; h < 2; ++h) {
-            for (int c = 0; c < SF_MAXKC1; ++c) mbar_init(&s_x1_full[h][c], SF_GROUP);
+            mbar_init(&s_x1_full[h], SF_GROUP);
             mbar_init(&s_acc_full[h], 1);
             mbar_init(&s_epi_done[h], SF_GROUP);
         }
@@ -120,6 +129,12 @@ sa_fused_kernel(const SaFusedParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+
+    // The X1 image rows between K1 and the next multiple of 16 are read by the last layer-1 MMA but never written by
+    // the gather: clear the whole image once (their weights are zero, but 0 * garbage-NaN would poison the sum).
+    for (int i = threadIdx.x; i < SF_MAXKC1 * SF_CHUNK / 16; i += SF_THREADS)
+        reinterpret_cast<uint4 *>(s_x1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
 
     // ---- prologue: all weights become resident (W1 in shared memory, W2 / W3 in tensor memory) ----
     if (threadIdx.x == SF_WORKERS) {
@@ -152,57 +167,52 @@ sa_fused_kernel(const SaFusedParams p) {
         // ====================================== workers: group h owns columns [64h, 64h+64) ======================================
         const int h = warp >> 2, quad = warp & 3;
         const int tg = threadIdx.x & (SF_GROUP - 1);
-        const int kk = tg & 7, ng = (tg >> 3) & 7, kbsel = tg >> 6;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread in the epilogues
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * SF_HALF;
         uint32_t acc_phase = 0;
 
-        auto produce_x1 = [&](long long tile, int c_begin, int c_end) {
+        // One thread = one neighbour (column) x every second 8-channel group: 16-byte loads from its contiguous
+        // point-major row, bf16 split, one 16-byte store per part into the K-major operand image
+        // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive 16-byte slots: conflict-free).
+        const int nl = tg & 63, kgsel = tg >> 6;
+        const int n_groups = p.C / 8;                 // feature k-groups; group n_groups holds (dx, dy, dz, 0...)
+        auto produce_x1 = [&](long long tile, int part) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
-            const int n0 = nt * TC_BN + h * SF_HALF + ng * 8;  // 8 columns of one centre (nsample % 8 == 0)
-            int pidx[8];
-            {
-                const int4 a = __ldg(reinterpret_cast<const int4 *>(p.idx + (size_t)g * N + n0));
-                const int4 b = __ldg(reinterpret_cast<const int4 *>(p.idx + (size_t)g * N + n0) + 1);
-                pidx[0] = a.x; pidx[1] = a.y; pidx[2] = a.z; pidx[3] = a.w;
-                pidx[4] = b.x; pidx[5] = b.y; pidx[6] = b.z; pidx[7] = b.w;
-            }
-            const float *cen = p.centres + ((size_t)g * p.npoint + n0 / p.nsample) * 3;
-            const float *pts = p.xyz + (size_t)g * p.n_pts * 3;
-            const float *fg = p.feats + (size_t)g * (p.K1 - 3) * p.n_pts;
-            for (int c = c_begin; c < c_end; ++c) {
-                uint8_t *xhi = s_x1 + (size_t)c * SF_CHUNK, *xlo = xhi + TC_IMG;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int kbl = 2 * i + kbsel;
-                    const int kbase = c * TC_BK + kbl * 8;
-                    if (kbase >= kmax16) continue;
-                    const int k = kbase + kk;
-                    float v[8];
-                    if (k >= p.K1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-                    } else if (k < 3) {
-                        const float cv = __ldg(cen + k);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), cv);
-                    } else {
-                        const float *row = fg + (size_t)(k - 3) * p.n_pts;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __ldg(row + pidx[j]);
-                    }
-                    uint4 hh, ll;
-                    split2(v[0], v[1], hh.x, ll.x);
-                    split2(v[2], v[3], hh.y, ll.y);
-                    split2(v[4], v[5], hh.z, ll.z);
-                    split2(v[6], v[7], hh.w, ll.w);
-                    const uint32_t off = (uint32_t)(h * 8 + ng) * TC_SBO + (uint32_t)kbl * TC_LBO + (uint32_t)kk * 16;
-                    *reinterpret_cast<uint4 *>(xhi + off) = hh;
-                    *reinterpret_cast<uint4 *>(xlo + off) = ll;
+            const int n = nt * TC_BN + h * SF_HALF + nl;
+            const int pi = __ldg(p.idx + (size_t)g * N + n);
+            const float *frow = p.feats + ((size_t)g * p.n_pts + pi) * p.C;
+            const uint32_t noff = (uint32_t)(h * 8 + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
+            // part 0: the first half of this thread's k-groups, part 1: the rest (two overlap windows per tile)
+            const int per_thread = (n_groups + 1 - kgsel + 1) / 2;      // groups kgsel, kgsel+2, ... <= n_groups
+            const int i_begin = part == 0 ? 0 : per_thread / 2, i_end = part == 0 ? per_thread / 2 : per_thread;
+            for (int i = i_begin; i < i_end; ++i) {
+                const int kg = kgsel + 2 * i;
+                float v[8];
+                if (kg < n_groups) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(frow + kg * 8));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(frow + kg * 8) + 1);
+                    v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+                } else {
+                    const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
+                    const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
+                    v[0] = __fsub_rn(__ldg(pt), __ldg(cen));
+                    v[1] = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
+                    v[2] = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
+                    v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
                 }
+                uint4 hh, ll;
+                split2(v[0], v[1], hh.x, ll.x);
+                split2(v[2], v[3], hh.y, ll.y);
+                split2(v[4], v[5], hh.z, ll.z);
+                split2(v[6], v[7], hh.w, ll.w);
+                uint8_t *img = s_x1 + (size_t)(kg >> 2) * SF_CHUNK + (uint32_t)(kg & 3) * TC_LBO + noff;
+                *reinterpret_cast<uint4 *>(img) = hh;
+                *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
+            }
+            if (part == 1) {
                 fence_proxy_async();
-                mbar_arrive(&s_x1_full[h][c]);
+                mbar_arrive(&s_x1_full[h]);
             }
         };
 
@@ -268,8 +278,7 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         const long long first = blockIdx.x;
-        const int csplit = (p.Kc1 + 1) / 2;   // the next tile's gather is split over the layer-2 and layer-3 windows
-        if (first < total_tiles) produce_x1(first, 0, p.Kc1);
+        if (first < total_tiles) { produce_x1(first, 0); produce_x1(first, 1); }
         for (long long tile = first; tile < total_tiles; tile += gridDim.x) {
             const bool more = tile + gridDim.x < total_tiles;
             mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;        // layer 1 of this half done: its X1 half is free
@@ -278,7 +287,7 @@ sa_fused_kernel(const SaFusedParams p) {
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&s_epi_done[h]);
-            if (more) produce_x1(tile + gridDim.x, 0, csplit);
+            if (more) produce_x1(tile + gridDim.x, 0);     // overlaps the other half's / next layer's MMAs
 
             mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
             tc_fence_after();
@@ -286,7 +295,7 @@ sa_fused_kernel(const SaFusedParams p) {
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&s_epi_done[h]);
-            if (more) produce_x1(tile + gridDim.x, csplit, p.Kc1);
+            if (more) produce_x1(tile + gridDim.x, 1);
 
             for (int mt = 0; mt < p.Mt3; ++mt) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
@@ -314,9 +323,9 @@ sa_fused_kernel(const SaFusedParams p) {
                 for (int h = 0; h < 2; ++h) {
                     wait_epilogue(h);
                     const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+                    mbar_wait(&s_x1_full[h], tile_ctr & 1);
+                    tc_fence_after();
                     for (int c = 0; c < p.Kc1; ++c) {
-                        mbar_wait(&s_x1_full[h][c], tile_ctr & 1);
-                        tc_fence_after();
                         const int steps = (kmax16 - c * TC_BK) >= 32 ? 2 : 1;
                         for (int k16 = 0; k16 < steps; ++k16) {
                             const uint32_t koff = (uint32_t)c * SF_CHUNK + (uint32_t)k16 * 2 * TC_LBO;
@@ -363,22 +372,23 @@ sa_fused_kernel(const SaFusedParams p) {
 }  // namespace jmb
 
 extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                            const float *b3, int K1, int C3, int G, int npoint, int nsample, int n_pts,
+                            const float *b3, int C, int C3, int G, int npoint, int nsample, int n_pts,
                             const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                             void *stream) {
     using namespace jmb;
     JMB_REQUIRE(G >= 0 && npoint > 0 && nsample > 0 && n_pts > 0, "sa_fused: bad sizes");
     if (G == 0) return JMB_OK;
     JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && feats && idx && xyz && centres && out, "sa_fused: null pointer");
-    JMB_REQUIRE(K1 > 3 && K1 <= SF_MAXKC1 * TC_BK, "sa_fused: 3 + C_in = %d must be in (3, 160]", K1);
+    JMB_REQUIRE(C > 0 && C % 8 == 0 && C + 3 <= SF_MAXKC1 * TC_BK, "sa_fused: C_in = %d must be a multiple of 8 and <= 152", C);
+    const int K1 = C + 3;   // C is a multiple of 8, so the xyz group starts right after the channels
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15u) == 0, "sa_fused: feats must be 16-byte aligned");
     JMB_REQUIRE(C3 == 128 || C3 == 256, "sa_fused: last layer width must be 128 or 256");
     JMB_REQUIRE(nsample % 8 == 0 && 64 % nsample == 0, "sa_fused: nsample must be 8, 16, 32 or 64");
     JMB_REQUIRE(((long long)npoint * nsample) % TC_BN == 0, "sa_fused: npoint*nsample must be a multiple of 128");
-    JMB_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0, "sa_fused: idx must be 16-byte aligned");
     SaFusedParams p;
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM;
+    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM; p.C = C;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
     p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out;
     static int sms = 0;

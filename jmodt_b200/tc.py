@@ -47,8 +47,10 @@ profiler = Profiler()
 class PackedLayer:
     """bf16 hi/lo chunk images of one layer's weight (+ fp32 bias, zero padded to a multiple of 128)."""
 
-    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool):
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, relu: bool, xyz_last: bool = False):
         w = weight.detach().reshape(weight.shape[0], -1).float()
+        if xyz_last:   # input columns [dx, dy, dz, channels...] -> [channels..., dx, dy, dz] (csrc/sa_fused.cu)
+            w = torch.cat((w[:, 3:], w[:, :3]), dim=1)
         self.M, self.K = w.shape
         Mt, Kc = -(-self.M // BM), -(-self.K // BK)
         wp = torch.zeros(Mt * BM, Kc * BK, dtype=torch.float32, device=w.device)
@@ -60,11 +62,18 @@ class PackedLayer:
             return t.view(Mt, 16, 8, Kc, 4, 8).permute(0, 3, 4, 1, 2, 5)
 
         self.wpack = torch.stack((image(hi), image(lo)), dim=2).contiguous()  # [Mt][Kc][2][4][16][8][8]
+        self._w32, self._xyz_last_pack = (None if xyz_last else weight.detach().reshape(weight.shape[0], -1).float()), None
         b = torch.zeros(Mt * BM, dtype=torch.float32, device=w.device)
         if bias is not None:
             b[: self.M] = bias.detach().float()
         self.bias = b
         self.relu = bool(relu)
+
+    def repacked_xyz_last(self) -> "PackedLayer":
+        """This layer with its input columns reordered to [channels, xyz] (cached)."""
+        if self._xyz_last_pack is None:
+            self._xyz_last_pack = PackedLayer(self._w32, self.bias[: self.M], self.relu, xyz_last=True)
+        return self._xyz_last_pack
 
 
 def fold_conv_bn(conv, bn=None):
@@ -124,23 +133,28 @@ def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) 
     """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu)."""
     return (len(layers) == 3 and layers[0].M == 128 and layers[1].M == 128 and layers[1].K == 128
             and layers[2].K == 128 and layers[2].M in (128, 256) and all(l.relu for l in layers)
-            and 3 < 3 + n_feat_channels <= 160 and nsample in (8, 16, 32, 64) and (npoint * nsample) % 128 == 0)
+            and n_feat_channels % 8 == 0 and 0 < n_feat_channels <= 152
+            and nsample in (8, 16, 32, 64) and (npoint * nsample) % 128 == 0)
 
 
-def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, centres: torch.Tensor) -> torch.Tensor:
-    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts), idx (G, npoint, nsample)
-    int32, centres (G, npoint, 3) -> (G, C3, npoint)."""
+def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, centres: torch.Tensor,
+             w1_xyz_last: PackedLayer | None = None) -> torch.Tensor:
+    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first (transposed
+    here to the point-major layout the gather wants), idx (G, npoint, nsample) int32, centres (G, npoint, 3)
+    -> (G, C3, npoint).  `w1_xyz_last` is layers[0] packed with xyz_last=True (built on the fly if omitted)."""
     G, n_pts, _ = xyz.shape
     C = feats.shape[1]
     npoint, nsample = idx.shape[1], idx.shape[2]
     l1, l2, l3 = layers
-    assert l1.K == 3 + C and feats.is_contiguous() and idx.is_contiguous() and xyz.is_contiguous()
+    assert l1.K == 3 + C and idx.is_contiguous() and xyz.is_contiguous()
+    l1 = w1_xyz_last if w1_xyz_last is not None else l1.repacked_xyz_last()
+    feats = feats.transpose(1, 2).contiguous()          # (G, n_pts, C): one neighbour = one contiguous row
     out = torch.empty((G, l3.M, npoint), dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)
     flops = 2.0 * G * npoint * nsample * (l1.M * l1.K + l2.M * l2.K + l3.M * l3.K)
     profiler.launch(flops, lambda: _lib.check(
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
-                                l3.wpack.data_ptr(), l3.bias.data_ptr(), l1.K, l3.M, G, npoint, nsample, n_pts,
+                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, l3.M, G, npoint, nsample, n_pts,
                                 feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
                                 out.data_ptr(), st), "sa_fused"))
     return out
