@@ -24,9 +24,14 @@
 
 namespace jmb {
 
-constexpr int SF_GROUP = 128;                 // threads per worker group (one 64-column half each)
-constexpr int SF_WORKERS = 2 * SF_GROUP;
-constexpr int SF_THREADS = SF_WORKERS + 32;   // + warp 8: MMA issuer
+// warp roles: 0-15 epilogue (half h = (w>>2)&1, TMEM lane quadrant w&3, 32-column sub-block w>>3),
+//             16-19 gather (64 threads per half: one neighbour each), 20 MMA issuer
+constexpr int SF_EPI_WARPS = 16;
+constexpr int SF_EPI_PER_HALF = 256;          // epilogue threads per half
+constexpr int SF_GATHER_WARP0 = 16;
+constexpr int SF_GATHER_PER_HALF = 64;
+constexpr int SF_ISSUER_WARP = 20;
+constexpr int SF_THREADS = 21 * 32;
 constexpr int SF_MAXKC1 = 5;
 constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chunk: 16 KB
 constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
@@ -105,21 +110,22 @@ sa_fused_kernel(const SaFusedParams p) {
     uint8_t *s_w1 = sf_smem;
     uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[2], s_acc_full[2], s_epi_done[2], s_w1_full;
+    __shared__ __align__(8) uint64_t s_x1_full[2], s_x1_free[2], s_acc_full[2], s_epi_done[2], s_w1_full;
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int h = 0; h < 2; ++h) {
-            mbar_init(&s_x1_full[h], SF_GROUP);
+            mbar_init(&s_x1_full[h], SF_GATHER_PER_HALF);
+            mbar_init(&s_x1_free[h], 1);
             mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], SF_GROUP);
+            mbar_init(&s_epi_done[h], SF_EPI_PER_HALF);
         }
         mbar_init(&s_w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == SF_ISSUER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                      "r"(512u)
                      : "memory");
@@ -137,7 +143,7 @@ sa_fused_kernel(const SaFusedParams p) {
     fence_proxy_async();
 
     // ---- prologue: all weights become resident (W1 in shared memory, W2 / W3 in tensor memory) ----
-    if (threadIdx.x == SF_WORKERS) {
+    if (threadIdx.x == SF_ISSUER_WARP * 32) {
         mbar_arrive_expect_tx(&s_w1_full, (uint32_t)p.Kc1 * SF_CHUNK);
         for (int c = 0; c < p.Kc1; ++c)
             bulk_g2s(s_w1 + (size_t)c * SF_CHUNK, p.w1 + (size_t)c * (SF_CHUNK / 2), SF_CHUNK, &s_w1_full);
@@ -163,66 +169,21 @@ sa_fused_kernel(const SaFusedParams p) {
     const long long total_tiles = (long long)p.G * Nt;
     const int kmax16 = ((p.K1 + 15) / 16) * 16;  // rows the layer-1 MMAs actually read
 
-    if (warp < 8) {
-        // ====================================== workers: group h owns columns [64h, 64h+64) ======================================
-        const int h = warp >> 2, quad = warp & 3;
-        const int tg = threadIdx.x & (SF_GROUP - 1);
-        const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread in the epilogues
+    if (warp < SF_EPI_WARPS) {
+        // ====================================== epilogue warps ======================================
+        // warp w: columns [64h + 32s, +32) of accumulator rows [32*quad, +32)
+        const int quad = warp & 3, h = (warp >> 2) & 1, sblk = warp >> 3;
+        const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * SF_HALF;
         uint32_t acc_phase = 0;
-
-        // One thread = one neighbour (column) x every second 8-channel group: 16-byte loads from its contiguous
-        // point-major row, bf16 split, one 16-byte store per part into the K-major operand image
-        // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive 16-byte slots: conflict-free).
-        const int nl = tg & 63, kgsel = tg >> 6;
-        const int n_groups = p.C / 8;                 // feature k-groups; group n_groups holds (dx, dy, dz, 0...)
-        auto produce_x1 = [&](long long tile, int part) {
-            const int nt = (int)(tile % Nt);
-            const int g = (int)(tile / Nt);
-            const int n = nt * TC_BN + h * SF_HALF + nl;
-            const int pi = __ldg(p.idx + (size_t)g * N + n);
-            const float *frow = p.feats + ((size_t)g * p.n_pts + pi) * p.C;
-            const uint32_t noff = (uint32_t)(h * 8 + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
-            // part 0: the first half of this thread's k-groups, part 1: the rest (two overlap windows per tile)
-            const int per_thread = (n_groups + 1 - kgsel + 1) / 2;      // groups kgsel, kgsel+2, ... <= n_groups
-            const int i_begin = part == 0 ? 0 : per_thread / 2, i_end = part == 0 ? per_thread / 2 : per_thread;
-            for (int i = i_begin; i < i_end; ++i) {
-                const int kg = kgsel + 2 * i;
-                float v[8];
-                if (kg < n_groups) {
-                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(frow + kg * 8));
-                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(frow + kg * 8) + 1);
-                    v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
-                } else {
-                    const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
-                    const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
-                    v[0] = __fsub_rn(__ldg(pt), __ldg(cen));
-                    v[1] = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
-                    v[2] = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
-                    v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
-                }
-                uint4 hh, ll;
-                split2(v[0], v[1], hh.x, ll.x);
-                split2(v[2], v[3], hh.y, ll.y);
-                split2(v[4], v[5], hh.z, ll.z);
-                split2(v[6], v[7], hh.w, ll.w);
-                uint8_t *img = s_x1 + (size_t)(kg >> 2) * SF_CHUNK + (uint32_t)(kg & 3) * TC_LBO + noff;
-                *reinterpret_cast<uint4 *>(img) = hh;
-                *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
-            }
-            if (part == 1) {
-                fence_proxy_async();
-                mbar_arrive(&s_x1_full[h]);
-            }
-        };
 
         // accumulator half -> next layer's operand image (row m of the accumulator is row k = m of the operand)
         auto epilogue_act = [&](const float *bias_ptr) {
             const float bias = __ldg(bias_ptr + m);
             uint8_t *ahi = s_act + (size_t)quad * SF_CHUNK, *alo = ahi + TC_IMG;
             const uint32_t rowoff = (uint32_t)(lane >> 3) * TC_LBO + (uint32_t)(lane & 7) * 16;
-#pragma unroll 1
-            for (int c0 = 0; c0 < SF_HALF; c0 += 32) {
+            {
+                const int c0 = sblk * 32;
                 float v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -277,33 +238,78 @@ sa_fused_kernel(const SaFusedParams p) {
             }
         };
 
-        const long long first = blockIdx.x;
-        if (first < total_tiles) { produce_x1(first, 0); produce_x1(first, 1); }
-        for (long long tile = first; tile < total_tiles; tile += gridDim.x) {
-            const bool more = tile + gridDim.x < total_tiles;
-            mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;        // layer 1 of this half done: its X1 half is free
-            tc_fence_after();
-            epilogue_act(p.b1);
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(&s_epi_done[h]);
-            if (more) produce_x1(tile + gridDim.x, 0);     // overlaps the other half's / next layer's MMAs
-
-            mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
-            tc_fence_after();
-            epilogue_act(p.b2);
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(&s_epi_done[h]);
-            if (more) produce_x1(tile + gridDim.x, 1);
-
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int layer = 0; layer < 2; ++layer) {
+                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
+                tc_fence_after();
+                epilogue_act(layer == 0 ? p.b1 : p.b2);
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&s_epi_done[h]);
+            }
             for (int mt = 0; mt < p.Mt3; ++mt) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
-                epilogue_pool(tile, mt);
+                if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools the whole 64-column half
                 tc_fence_before();
                 mbar_arrive(&s_epi_done[h]);
             }
+        }
+    } else if (warp < SF_ISSUER_WARP) {
+        // ====================================== gather warps ======================================
+        const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
+        const int h = tg >> 6, nl = tg & 63;
+        const int n_groups = p.C / 8;                 // feature k-groups; group n_groups holds (dx, dy, dz, 0...)
+        // One thread = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
+        // channels in flight), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
+        // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots: conflict-free).
+        auto produce_x1 = [&](long long tile) {
+            const int nt = (int)(tile % Nt);
+            const int g = (int)(tile / Nt);
+            const int n = nt * TC_BN + h * SF_HALF + nl;
+            const int pi = __ldg(p.idx + (size_t)g * N + n);
+            const float *frow = p.feats + ((size_t)g * p.n_pts + pi) * p.C;
+            const uint32_t noff = (uint32_t)(h * 8 + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
+            auto put = [&](int kg, const float (&v)[8]) {
+                uint4 hh, ll;
+                split2(v[0], v[1], hh.x, ll.x);
+                split2(v[2], v[3], hh.y, ll.y);
+                split2(v[4], v[5], hh.z, ll.z);
+                split2(v[6], v[7], hh.w, ll.w);
+                uint8_t *img = s_x1 + (size_t)(kg >> 2) * SF_CHUNK + (uint32_t)(kg & 3) * TC_LBO + noff;
+                *reinterpret_cast<uint4 *>(img) = hh;
+                *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
+            };
+            {   // relative coordinates: k-group n_groups
+                const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
+                const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
+                float v[8] = {__fsub_rn(__ldg(pt), __ldg(cen)), __fsub_rn(__ldg(pt + 1), __ldg(cen + 1)),
+                              __fsub_rn(__ldg(pt + 2), __ldg(cen + 2)), 0.f, 0.f, 0.f, 0.f, 0.f};
+                put(n_groups, v);
+            }
+            for (int kg0 = 0; kg0 < n_groups; kg0 += 4) {
+                float4 a4[4], b4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kg0 + u < n_groups) {
+                        a4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8));
+                        b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (kg0 + u < n_groups) {
+                        const float v[8] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w, b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+                        put(kg0 + u, v);
+                    }
+            }
+            fence_proxy_async();
+            mbar_arrive(&s_x1_full[h]);
+        };
+
+        uint32_t tile_ctr = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
+            if (tile_ctr > 0) mbar_wait(&s_x1_free[h], (tile_ctr - 1) & 1);   // layer-1 MMAs of the previous tile have read this half
+            produce_x1(tile);
         }
     } else {
         if (lane == 0) {
@@ -337,6 +343,7 @@ sa_fused_kernel(const SaFusedParams p) {
                             umma_ss64(acc, whi, xlo, 1);
                         }
                     }
+                    umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
                     umma_commit(&s_acc_full[h]);
                 }
                 // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
@@ -364,7 +371,7 @@ sa_fused_kernel(const SaFusedParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == SF_ISSUER_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
