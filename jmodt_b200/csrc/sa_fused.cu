@@ -22,16 +22,18 @@
 // Shapes: layer widths C1 = C2 = 128, C3 in {128, 256}; C_in % 8 == 0, C_in + 3 <= 160; nsample in {8,...,64} | 64.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace jmb {
 
 // warp roles: 0-15 epilogue (half h = (w>>2)&1, TMEM lane quadrant w&3, 32-column sub-block w>>3),
-//             16-19 gather (64 threads per half: one neighbour each), 20 MMA issuer
+//             16-19 gather (64 threads per half: one neighbour each), 20-21 MMA issuers (one per half)
 constexpr int SF_EPI_WARPS = 16;
 constexpr int SF_EPI_PER_HALF = 256;          // epilogue threads per half
 constexpr int SF_GATHER_WARP0 = 16;
 constexpr int SF_GATHER_PER_HALF = 64;
 constexpr int SF_ISSUER_WARP = 20;
-constexpr int SF_THREADS = 21 * 32;
+constexpr int SF_THREADS = 22 * 32;          // warps 20, 21: one MMA issuer per half
 constexpr int SF_MAXKC1 = 5;
 constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chunk: 16 KB
 constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
@@ -56,6 +58,7 @@ struct SaFusedParams {
     const float *xyz;      // (G, n_pts, 3)
     const float *centres;  // (G, npoint, 3)
     float *out;            // (G, 128*Mt3, npoint)
+    long long *dbg;        // optional timeline buffer (profiling aid): CTA 0 writes clock64() stamps
 };
 
 __device__ __forceinline__ void umma_ss64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
@@ -238,14 +241,21 @@ sa_fused_kernel(const SaFusedParams p) {
             }
         };
 
+        long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
+        int di = 0;
+#define SF_ESTAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int layer = 0; layer < 2; ++layer) {
+                SF_ESTAMP(20 + layer);
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
+                SF_ESTAMP(30 + layer);
                 epilogue_act(layer == 0 ? p.b1 : p.b2);
+                SF_ESTAMP(40 + layer);
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(&s_epi_done[h]);
+                SF_ESTAMP(50 + layer);
             }
             for (int mt = 0; mt < p.Mt3; ++mt) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
@@ -313,56 +323,67 @@ sa_fused_kernel(const SaFusedParams p) {
         }
     } else {
         if (lane == 0) {
-            // ====================================== MMA issuer ======================================
+            // ====================================== MMA issuers: one thread per half ======================================
+            // A single thread's instruction stream (descriptor arithmetic + 3 MMAs per K step) was the bottleneck of the
+            // tensor pipe, so each half has its own issuer, and descriptors are formed by adding constants to a base
+            // descriptor (the start-address field is the low 14 bits; images never cross it).
+            const int h = warp - SF_ISSUER_WARP;
             mbar_wait(&s_w1_full, 0);
-            uint32_t epi_phase[2] = {0, 0};
-            bool first_use[2] = {true, true};
+            uint32_t epi_phase = 0;
+            bool first_use = true;
             uint32_t tile_ctr = 0;
-            auto wait_epilogue = [&](int h) {     // accumulator half h is free / its activation image is ready
-                if (first_use[h]) { first_use[h] = false; return; }
-                mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
+            auto wait_epilogue = [&]() {     // accumulator half h is free / its activation image is ready
+                if (first_use) { first_use = false; return; }
+                mbar_wait(&s_epi_done[h], epi_phase); epi_phase ^= 1;
                 tc_fence_after();
             };
-            const uint32_t w1_base = smem_u32(s_w1), x1_base = smem_u32(s_x1), act_base = smem_u32(s_act);
+            const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+            const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
+            const uint64_t x1_desc = make_smem_desc(smem_u32(s_x1) + h * SF_HALF_OFF);
+            const uint64_t act_desc = make_smem_desc(smem_u32(s_act) + h * SF_HALF_OFF);
+            constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4;
+            const int last_steps = (kmax16 - (p.Kc1 - 1) * TC_BK) >= 32 ? 2 : 1;
+            long long *dbg = (p.dbg && blockIdx.x == 0 && h == 0) ? p.dbg : nullptr;
+            int di = 0;
+#define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-                // layer 1 (SS): A = W1 chunk images in shared memory, B = gathered X1 half
-                for (int h = 0; h < 2; ++h) {
-                    wait_epilogue(h);
-                    const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
-                    mbar_wait(&s_x1_full[h], tile_ctr & 1);
-                    tc_fence_after();
-                    for (int c = 0; c < p.Kc1; ++c) {
-                        const int steps = (kmax16 - c * TC_BK) >= 32 ? 2 : 1;
-                        for (int k16 = 0; k16 < steps; ++k16) {
-                            const uint32_t koff = (uint32_t)c * SF_CHUNK + (uint32_t)k16 * 2 * TC_LBO;
-                            const uint64_t whi = make_smem_desc(w1_base + koff), wlo = make_smem_desc(w1_base + koff + TC_IMG);
-                            const uint64_t xhi = make_smem_desc(x1_base + koff + h * SF_HALF_OFF);
-                            const uint64_t xlo = make_smem_desc(x1_base + koff + TC_IMG + h * SF_HALF_OFF);
-                            umma_ss64(acc, whi, xhi, (c | k16) != 0);
-                            umma_ss64(acc, wlo, xhi, 1);
-                            umma_ss64(acc, whi, xlo, 1);
-                        }
+                // layer 1 (SS): A = W1 chunk images in shared memory, B = gathered X1 half (K-major)
+                SF_STAMP(1);
+                wait_epilogue();
+                SF_STAMP(2);
+                mbar_wait(&s_x1_full[h], tile_ctr & 1);
+                tc_fence_after();
+                SF_STAMP(3);
+                for (int c = 0; c < p.Kc1; ++c) {
+                    const int steps = c == p.Kc1 - 1 ? last_steps : 2;
+                    const uint64_t wd = w1_desc + (uint64_t)c * D_CHUNK, xd = x1_desc + (uint64_t)c * D_CHUNK;
+                    umma_ss64(acc, wd, xd, c != 0);
+                    umma_ss64(acc, wd + D_IMG, xd, 1);
+                    umma_ss64(acc, wd, xd + D_IMG, 1);
+                    if (steps == 2) {
+                        umma_ss64(acc, wd + D_K16, xd + D_K16, 1);
+                        umma_ss64(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
+                        umma_ss64(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
                     }
-                    umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
-                    umma_commit(&s_acc_full[h]);
                 }
+                umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
+                umma_commit(&s_acc_full[h]);
+                SF_STAMP(4);
                 // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
                 for (int l = 0; l < 1 + p.Mt3; ++l) {
-                    const uint32_t wcol = l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128;
-                    for (int h = 0; h < 2; ++h) {
-                        wait_epilogue(h);
-                        const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+                    const uint32_t wcol = tmem_base + (l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128);
+                    wait_epilogue();
+                    SF_STAMP(5 + l);
 #pragma unroll
-                        for (int k16 = 0; k16 < 8; ++k16) {
-                            const uint32_t boff = (uint32_t)(k16 >> 1) * SF_CHUNK + (uint32_t)(k16 & 1) * 2 * TC_LBO + h * SF_HALF_OFF;
-                            const uint64_t xhi = make_smem_desc(act_base + boff), xlo = make_smem_desc(act_base + boff + TC_IMG);
-                            const uint32_t ahi = tmem_base + wcol + (uint32_t)k16 * 8, alo = ahi + 64;
-                            umma_ts64(acc, ahi, xhi, k16 != 0);
-                            umma_ts64(acc, alo, xhi, 1);
-                            umma_ts64(acc, ahi, xlo, 1);
-                        }
-                        umma_commit(&s_acc_full[h]);
+                    for (int k16 = 0; k16 < 8; ++k16) {
+                        const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                        const uint32_t ahi = wcol + (uint32_t)k16 * 8;
+                        umma_ts64(acc, ahi, xd, k16 != 0);
+                        umma_ts64(acc, ahi + 64, xd, 1);
+                        umma_ts64(acc, ahi, xd + D_IMG, 1);
                     }
+                    umma_commit(&s_acc_full[h]);
+                    SF_STAMP(8 + l);
                 }
             }
         }
@@ -383,6 +404,13 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
                             const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                             void *stream) {
     using namespace jmb;
+    static long long *dbg_buf = nullptr;          // JMB_SA_DEBUG=1: CTA 0 records a clock64() timeline (profiling aid)
+    static int dbg_on = -1;
+    if (dbg_on < 0) {
+        const char *e = getenv("JMB_SA_DEBUG");
+        dbg_on = (e && e[0] == '1') ? 1 : 0;
+        if (dbg_on) { cudaMalloc(&dbg_buf, 1024 * sizeof(long long)); cudaMemset(dbg_buf, 0, 1024 * sizeof(long long)); }
+    }
     JMB_REQUIRE(G >= 0 && npoint > 0 && nsample > 0 && n_pts > 0, "sa_fused: bad sizes");
     if (G == 0) return JMB_OK;
     JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && feats && idx && xyz && centres && out, "sa_fused: null pointer");
@@ -397,7 +425,7 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
     p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM; p.C = C;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
-    p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out;
+    p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.dbg = dbg_buf;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
@@ -408,5 +436,17 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
     sa_fused_kernel<<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    if (dbg_on) {
+        long long hbuf[1024];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        for (int part = 0; part < 2; ++part) {
+            const long long *b = hbuf + part * 512;
+            fprintf(stderr, "[sa_fused timeline %s] ", part ? "epilogue warp 0" : "issuer h0");
+            for (int i = 0; i + 1 < 96 && b[i]; i += 2) fprintf(stderr, "%lld:%lld ", b[i], b[i + 1] - b[1]);
+            fprintf(stderr, "\n");
+        }
+        cudaMemset(dbg_buf, 0, 1024 * sizeof(long long));
+    }
     return check_launch("sa_fused");
 }
