@@ -27,9 +27,13 @@
 
 namespace jmb {
 
-constexpr int TC_STAGES = 3;
-constexpr int TC_STAGE_BYTES = 4 * TC_IMG;         // W_hi, W_lo, X_hi, X_lo
-constexpr int TC_THREADS = 160;
+// warp roles: 0-3 operand producers (X), 4-7 epilogue (TMEM lane quadrant = warp & 3), 8 MMA issuer, 9 weight loader
+constexpr int TC_XSTAGES = 3;                      // X ring: 16 KB per stage (hi + lo image)
+constexpr int TC_WSTAGES = 4;                      // W ring: 16 KB per stage, filled by cp.async.bulk, runs ahead of X
+constexpr int TC_CHUNK = 2 * TC_IMG;               // hi + lo image of one 32-row chunk
+constexpr int TC_SMEM = (TC_XSTAGES + TC_WSTAGES) * TC_CHUNK;   // 112 KB -> 2 CTAs per SM
+constexpr int TC_THREADS = 320;
+constexpr int TC_ACC_BUFS = 2;                     // double-buffered accumulator: epilogue overlaps the next tile's MMAs
 
 struct TcGemmParams {
     const __nv_bfloat16 *wpack;   // [Mt][Kc][2][TC_IMG/2] chunk images (see pack_weights in tc.py)
@@ -50,24 +54,25 @@ struct TcGemmParams {
     long long y_group_stride;     // elements between consecutive groups of y (>= M*N, lets a layer write into a slice of a wider tensor)
 };
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_kernel(const TcGemmParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t s_full[TC_STAGES], s_empty[TC_STAGES], s_acc_full, s_acc_empty;
+    __shared__ __align__(8) uint64_t s_xfull[TC_XSTAGES], s_xempty[TC_XSTAGES], s_wfull[TC_WSTAGES], s_wempty[TC_WSTAGES],
+        s_acc_full[TC_ACC_BUFS], s_acc_empty[TC_ACC_BUFS];
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&s_full[s], 129); mbar_init(&s_empty[s], 1); }  // 128 producers + thread 0's expect_tx arrive
-        mbar_init(&s_acc_full, 1);
-        mbar_init(&s_acc_empty, 128);
+        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+        for (int s = 0; s < TC_WSTAGES; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_wempty[s], 1); }
+        for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                     "r"((uint32_t)TC_BN)
+                     "r"((uint32_t)(TC_ACC_BUFS * TC_BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -82,7 +87,7 @@ tc_gemm_kernel(const TcGemmParams p) {
     uint32_t tile_ctr = 0;
 
     if (warp < 4) {
-        // =============================== producers + epilogue ===============================
+        // =============================== operand producers ===============================
         const int t = threadIdx.x;
         const int kk = t & 7;               // k row inside a group of 8
         const int ng = warp * 4 + ((t >> 3) & 3);   // n group of 8 columns inside the tile
@@ -151,16 +156,11 @@ tc_gemm_kernel(const TcGemmParams p) {
                 }
             }
         };
-        auto store_chunk = [&](int mt, int kc, const float (&v)[TC_BK / 8][8]) {
-            const int s = chunk_ctr % TC_STAGES;
-            const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
-            mbar_wait(&s_empty[s], ph ^ 1);
-            uint8_t *stage = tc_smem + (size_t)s * TC_STAGE_BYTES;
-            if (t == 0) {
-                mbar_arrive_expect_tx(&s_full[s], 2 * TC_IMG);
-                bulk_g2s(stage, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG, 2 * TC_IMG, &s_full[s]);
-            }
-            uint8_t *xhi = stage + 2 * TC_IMG, *xlo = stage + 3 * TC_IMG;
+        auto store_chunk = [&](const float (&v)[TC_BK / 8][8]) {
+            const int s = chunk_ctr % TC_XSTAGES;
+            const uint32_t ph = (chunk_ctr / TC_XSTAGES) & 1;
+            mbar_wait(&s_xempty[s], ph ^ 1);
+            uint8_t *xhi = tc_smem + (size_t)s * TC_CHUNK, *xlo = xhi + TC_IMG;
 #pragma unroll
             for (int kb = 0; kb < TC_BK / 8; ++kb) {
                 uint4 h, l;
@@ -173,7 +173,7 @@ tc_gemm_kernel(const TcGemmParams p) {
                 *reinterpret_cast<uint4 *>(xlo + off) = l;
             }
             fence_proxy_async();
-            mbar_arrive(&s_full[s]);
+            mbar_arrive(&s_xfull[s]);
             ++chunk_ctr;
         };
 
@@ -187,11 +187,11 @@ tc_gemm_kernel(const TcGemmParams p) {
                 // item (tile, kc) is in va; prefetch (tile, kc+1) or the next tile's first chunk into vb
                 if (kc + 1 < p.Kc) load_chunk(tile, kc + 1, vb);
                 else if (next_tile < total_tiles) load_chunk(next_tile, 0, vb);
-                store_chunk(mt, kc, va);
+                store_chunk(va);
                 if (kc + 1 < p.Kc) {
                     if (kc + 2 < p.Kc) load_chunk(tile, kc + 2, va);
                     else if (next_tile < total_tiles) load_chunk(next_tile, 0, va);
-                    store_chunk(mt, kc + 1, vb);
+                    store_chunk(vb);
                 } else {
                     // odd chunk count: the prefetched first chunk of the next tile sits in vb; move it to va
 #pragma unroll
@@ -201,12 +201,22 @@ tc_gemm_kernel(const TcGemmParams p) {
                 }
             }
 
+        }
+    } else if (warp < 8) {
+        // =============================== epilogue: one output channel per thread ===============================
+        const int quad = warp & 3;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
+            const int mt = (int)(tile % p.Mt);
+            const long long gn = tile / p.Mt;
+            const int nt = (int)(gn % Nt);
+            const int g = (int)(gn / Nt);
             // ---- epilogue: one output channel per thread ----
-            mbar_wait(&s_acc_full, tile_ctr & 1);
+            const int buf = tile_ctr % TC_ACC_BUFS;
+            mbar_wait(&s_acc_full[buf], (tile_ctr / TC_ACC_BUFS) & 1);
             tc_fence_after();
-            const int m = mt * TC_BM + warp * 32 + lane;
+            const int m = mt * TC_BM + quad * 32 + lane;
             const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_BN;
             if (p.out_mode == 0) {
                 float *yrow = p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + (size_t)nt * TC_BN;
 #pragma unroll 1
@@ -270,32 +280,50 @@ tc_gemm_kernel(const TcGemmParams p) {
                 }
             }
             tc_fence_before();
-            mbar_arrive(&s_acc_empty);
+            mbar_arrive(&s_acc_empty[buf]);
         }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // =============================== weight loader: one 16 KB cp.async.bulk per K chunk ===============================
+            uint32_t wctr = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = (int)(tile % p.Mt);
+                for (int kc = 0; kc < p.Kc; ++kc, ++wctr) {
+                    const int s = wctr % TC_WSTAGES;
+                    mbar_wait(&s_wempty[s], ((wctr / TC_WSTAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&s_wfull[s], TC_CHUNK);
+                    bulk_g2s(tc_smem + (size_t)(TC_XSTAGES + s) * TC_CHUNK, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG,
+                             TC_CHUNK, &s_wfull[s]);
+                }
+            }
+        }
+        __syncwarp();
     } else {
       if (lane == 0) {
         // =============================== MMA issuer ===============================
+        constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            mbar_wait(&s_acc_empty, (tile_ctr & 1) ^ 1);
+            const int buf = tile_ctr % TC_ACC_BUFS;
+            mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
             tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
             for (int kc = 0; kc < p.Kc; ++kc, ++chunk_ctr) {
-                const int s = chunk_ctr % TC_STAGES;
-                const uint32_t ph = (chunk_ctr / TC_STAGES) & 1;
-                mbar_wait(&s_full[s], ph);
+                const int sx = chunk_ctr % TC_XSTAGES, sw = chunk_ctr % TC_WSTAGES;
+                mbar_wait(&s_wfull[sw], (chunk_ctr / TC_WSTAGES) & 1);
+                mbar_wait(&s_xfull[sx], (chunk_ctr / TC_XSTAGES) & 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(tc_smem + (size_t)s * TC_STAGE_BYTES);
-#pragma unroll
-                for (int k16 = 0; k16 < TC_BK / 16; ++k16) {
-                    const uint32_t koff = (uint32_t)k16 * 2 * TC_LBO;
-                    const uint64_t whi = make_smem_desc(base + koff), wlo = make_smem_desc(base + TC_IMG + koff);
-                    const uint64_t xhi = make_smem_desc(base + 2 * TC_IMG + koff), xlo = make_smem_desc(base + 3 * TC_IMG + koff);
-                    umma_ss(tmem_base, whi, xhi, (kc | k16) != 0);
-                    umma_ss(tmem_base, wlo, xhi, 1);
-                    umma_ss(tmem_base, whi, xlo, 1);
-                }
-                umma_commit(&s_empty[s]);
+                const uint64_t xd = make_smem_desc(smem_u32(tc_smem + (size_t)sx * TC_CHUNK));
+                const uint64_t wd = make_smem_desc(smem_u32(tc_smem + (size_t)(TC_XSTAGES + sw) * TC_CHUNK));
+                umma_ss(acc, wd, xd, kc != 0);
+                umma_ss(acc, wd + D_IMG, xd, 1);
+                umma_ss(acc, wd, xd + D_IMG, 1);
+                umma_ss(acc, wd + D_K16, xd + D_K16, 1);
+                umma_ss(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
+                umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
+                umma_commit(&s_xempty[sx]);
+                umma_commit(&s_wempty[sw]);
             }
-            umma_commit(&s_acc_full);
+            umma_commit(&s_acc_full[buf]);
         }
       }
       __syncwarp();
@@ -303,8 +331,8 @@ tc_gemm_kernel(const TcGemmParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_ACC_BUFS * TC_BN)) : "memory");
     }
 }
 
@@ -336,14 +364,14 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
         JMB_CUDA(cudaGetDevice(&dev));
         JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES;
+    const size_t smem = (size_t)TC_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
         JMB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long tiles = (long long)G * div_up(N, TC_BN) * p.Mt;
-    const int grid = (int)(tiles < (long long)sms * 3 ? tiles : (long long)sms * 3);
+    const int grid = (int)(tiles < (long long)sms * 2 ? tiles : (long long)sms * 2);
     tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("tc_mlp_layer");
 }
