@@ -55,6 +55,11 @@ JMB_API int jmb_sm_count(void);
 JMB_API int jmb_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, void *stream);
 
+/* Two ball queries over the same centres in one scan (multi-scale grouping, pointnet2_modules.py:41-42 calls
+ * ball_query once per radius): same results as two jmb_ball_query calls. */
+JMB_API int jmb_ball_query_msg2(int b, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                                const float *new_xyz, const float *xyz, int *idx_a, int *idx_b, void *stream);
+
 /* replaces group_points_wrapper_fast (group_points.cpp:24-35) -> group_points_gpu.cu:47-86.
  * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
 JMB_API int jmb_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
@@ -157,6 +162,7 @@ JMB_API int jmb_nms_normal(int n, const float *boxes, float thresh, int64_t *kee
  *           (no centring if centres is NULL), rows 3.. are x[g][k-3][point] with x = feats (G, K-3, n_pts).
  *   out_mode 0: y (G, M, N);  out_mode 1: max over each `pool` consecutive columns -> y (G, M, N / pool)
  *           (the set-abstraction max-pool, pointnet2_modules.py:50-52).
+ *   out_mode 2: point-major y (G, N, M) (what the fused set-abstraction kernel gathers from).
  *   y_group_stride: elements between groups of y (0 = dense); lets a layer write into a channel slice of a wider
  *           (G, C_total, N) tensor, replacing torch.cat. */
 JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
@@ -176,11 +182,11 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
  * w2/w3 are packed layers (jmodt_b200/tc.py); w1 is packed with its input columns reordered to [channels, xyz]
  * (tc.PackedLayer(..., xyz_last=True)).  C_in % 8 == 0, C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample a
  * multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
- * centres (G, npoint, 3) -> out (G, C3, npoint). */
+ * centres (G, npoint, 3) -> out (G, C3, npoint), or point-major (G, npoint, C3) if out_point_major != 0. */
 JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
                          const float *b3, int C_in, int C3, int G, int npoint, int nsample, int n_pts,
                          const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
-                         void *stream);
+                         int out_point_major, void *stream);
 
 /* ---- proposal layer ---------------------------------------------------------------------- */
 

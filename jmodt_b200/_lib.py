@@ -24,6 +24,7 @@ SIGNATURES = {
     "jmb_set_device": [_i],
     "jmb_sm_count": [],
     "jmb_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "jmb_ball_query_msg2": [_i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -40,7 +41,7 @@ SIGNATURES = {
     "jmb_nms_workspace_bytes": [_i],
     "jmb_nms": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
-    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

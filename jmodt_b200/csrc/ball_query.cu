@@ -16,10 +16,18 @@ constexpr int BQ_WARPS = 8;
 constexpr int BQ_THREADS = BQ_WARPS * 32;
 constexpr int BQ_TILE = 2048;  // points per shared-memory tile (24 KB)
 
-template <int CPW>
+// NR radii (multi-scale grouping queries the same centres with several radii, pointnet2_modules.py:41-42) share
+// one scan of the cloud: the distance is computed once per (centre, point) and compared against each radius.
+struct BallQueryScales {
+    float radius2[2];
+    int nsample[2];
+    int *idx[2];
+};
+
+template <int CPW, int NR>
 __global__ void __launch_bounds__(BQ_THREADS)
-ball_query_kernel(int n, int m, float radius2, int nsample, const float *__restrict__ new_xyz,
-                  const float *__restrict__ xyz, int *__restrict__ idx) {
+ball_query_kernel(int n, int m, BallQueryScales sc, const float *__restrict__ new_xyz,
+                  const float *__restrict__ xyz) {
     __shared__ __align__(16) float s_pts[BQ_TILE * 3];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5;
@@ -29,23 +37,24 @@ ball_query_kernel(int n, int m, float radius2, int nsample, const float *__restr
 
     const float *pts = xyz + (size_t)b * n * 3;
     float cx[CPW], cy[CPW], cz[CPW];
-    int cnt[CPW], first[CPW];
-    int open = 0;  // centres of this warp still collecting
+    int cnt[CPW][NR], first[CPW][NR];
+    int open = 0;  // (centre, radius) rows of this warp still collecting
 #pragma unroll
     for (int i = 0; i < CPW; ++i) {
         const int c = c0 + i;
-        first[i] = 0;
         if (c < m) {
             const float *p = new_xyz + ((size_t)b * m + c) * 3;
             cx[i] = __ldg(p); cy[i] = __ldg(p + 1); cz[i] = __ldg(p + 2);
-            cnt[i] = 0;
-            ++open;
         } else {
             cx[i] = cy[i] = cz[i] = 0.f;
-            cnt[i] = nsample;  // nothing to do
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            first[i][r] = 0;
+            cnt[i][r] = (c < m && sc.nsample[r] > 0) ? 0 : sc.nsample[r];
+            if (cnt[i][r] < sc.nsample[r]) ++open;
         }
     }
-    if (nsample <= 0) open = 0;
 
     for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
         const int tn = min(BQ_TILE, n - t0);
@@ -69,17 +78,25 @@ ball_query_kernel(int n, int m, float radius2, int nsample, const float *__restr
                 const float x = s_pts[pp * 3], y = s_pts[pp * 3 + 1], z = s_pts[pp * 3 + 2];
 #pragma unroll
                 for (int i = 0; i < CPW; ++i) {
-                    if (cnt[i] < nsample) {  // warp-uniform
+                    bool any_open = false;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) any_open |= cnt[i][r] < sc.nsample[r];
+                    if (any_open) {  // warp-uniform
                         const float d2 = dist2_ref(cx[i] - x, cy[i] - y, cz[i] - z);
-                        const bool hit = valid && (d2 < radius2);
-                        const unsigned mk = __ballot_sync(0xffffffffu, hit);
-                        if (mk) {
-                            if (cnt[i] == 0) first[i] = t0 + p0 + __ffs(mk) - 1;
-                            const int pos = cnt[i] + __popc(mk & lt_mask);
-                            if (hit && pos < nsample)
-                                idx[((size_t)b * m + c0 + i) * nsample + pos] = t0 + p;
-                            cnt[i] += __popc(mk);
-                            if (cnt[i] >= nsample) { cnt[i] = nsample; --open; }
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            if (cnt[i][r] < sc.nsample[r]) {
+                                const bool hit = valid && (d2 < sc.radius2[r]);
+                                const unsigned mk = __ballot_sync(0xffffffffu, hit);
+                                if (mk) {
+                                    if (cnt[i][r] == 0) first[i][r] = t0 + p0 + __ffs(mk) - 1;
+                                    const int pos = cnt[i][r] + __popc(mk & lt_mask);
+                                    if (hit && pos < sc.nsample[r])
+                                        sc.idx[r][((size_t)b * m + c0 + i) * sc.nsample[r] + pos] = t0 + p;
+                                    cnt[i][r] += __popc(mk);
+                                    if (cnt[i][r] >= sc.nsample[r]) { cnt[i][r] = sc.nsample[r]; --open; }
+                                }
+                            }
                         }
                     }
                 }
@@ -95,11 +112,32 @@ ball_query_kernel(int n, int m, float radius2, int nsample, const float *__restr
     for (int i = 0; i < CPW; ++i) {
         const int c = c0 + i;
         if (c < m) {
-            const int have = min(cnt[i], nsample);
-            int *row = idx + ((size_t)b * m + c) * nsample;
-            for (int l = have + (int)lane; l < nsample; l += 32) row[l] = first[i];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int have = min(cnt[i][r], sc.nsample[r]);
+                int *row = sc.idx[r] + ((size_t)b * m + c) * sc.nsample[r];
+                for (int l = have + (int)lane; l < sc.nsample[r]; l += 32) row[l] = first[i][r];
+            }
         }
     }
+}
+
+template <int NR>
+static int launch_ball_query(int b, int n, int m, const BallQueryScales &sc, const float *new_xyz, const float *xyz,
+                             cudaStream_t st) {
+    const long long centres = (long long)b * m;
+    // more centres per warp amortise the shared-memory reads; fewer keep small problems parallel
+    if (centres >= 4 * 4096) {
+        dim3 grid(div_up(m, BQ_WARPS * 4), b);
+        ball_query_kernel<4, NR><<<grid, BQ_THREADS, 0, st>>>(n, m, sc, new_xyz, xyz);
+    } else if (centres >= 2 * 2048) {
+        dim3 grid(div_up(m, BQ_WARPS * 2), b);
+        ball_query_kernel<2, NR><<<grid, BQ_THREADS, 0, st>>>(n, m, sc, new_xyz, xyz);
+    } else {
+        dim3 grid(div_up(m, BQ_WARPS), b);
+        ball_query_kernel<1, NR><<<grid, BQ_THREADS, 0, st>>>(n, m, sc, new_xyz, xyz);
+    }
+    return check_launch("ball_query");
 }
 
 }  // namespace jmb
@@ -111,19 +149,22 @@ extern "C" int jmb_ball_query(int b, int n, int m, float radius, int nsample,
     if (b == 0 || m == 0 || nsample == 0) return JMB_OK;
     JMB_REQUIRE(new_xyz && xyz && idx, "ball_query: null pointer");
     JMB_REQUIRE(b <= 65535, "ball_query: batch %d exceeds grid.y limit", b);
-    const float radius2 = radius * radius;  // fp32, as ball_query_gpu.cu:23
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long centres = (long long)b * m;
-    // more centres per warp amortise the shared-memory reads; fewer keep small problems parallel
-    if (centres >= 4 * 4096) {
-        dim3 grid(div_up(m, BQ_WARPS * 4), b);
-        ball_query_kernel<4><<<grid, BQ_THREADS, 0, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
-    } else if (centres >= 2 * 2048) {
-        dim3 grid(div_up(m, BQ_WARPS * 2), b);
-        ball_query_kernel<2><<<grid, BQ_THREADS, 0, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
-    } else {
-        dim3 grid(div_up(m, BQ_WARPS), b);
-        ball_query_kernel<1><<<grid, BQ_THREADS, 0, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
-    }
-    return check_launch("ball_query");
+    BallQueryScales sc;
+    sc.radius2[0] = radius * radius;  // fp32, as ball_query_gpu.cu:23
+    sc.nsample[0] = nsample; sc.idx[0] = idx;
+    sc.radius2[1] = 0.f; sc.nsample[1] = 0; sc.idx[1] = nullptr;
+    return launch_ball_query<1>(b, n, m, sc, new_xyz, xyz, (cudaStream_t)stream);
+}
+
+extern "C" int jmb_ball_query_msg2(int b, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                                   const float *new_xyz, const float *xyz, int *idx_a, int *idx_b, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && n >= 0 && m >= 0 && nsample_a > 0 && nsample_b > 0, "ball_query_msg2: bad sizes");
+    if (b == 0 || m == 0) return JMB_OK;
+    JMB_REQUIRE(new_xyz && xyz && idx_a && idx_b, "ball_query_msg2: null pointer");
+    JMB_REQUIRE(b <= 65535, "ball_query_msg2: batch %d exceeds grid.y limit", b);
+    BallQueryScales sc;
+    sc.radius2[0] = radius_a * radius_a; sc.nsample[0] = nsample_a; sc.idx[0] = idx_a;
+    sc.radius2[1] = radius_b * radius_b; sc.nsample[1] = nsample_b; sc.idx[1] = idx_b;
+    return launch_ball_query<2>(b, n, m, sc, new_xyz, xyz, (cudaStream_t)stream);
 }

@@ -57,7 +57,8 @@ struct SaFusedParams {
     const int *idx;        // (G, npoint, nsample)
     const float *xyz;      // (G, n_pts, 3)
     const float *centres;  // (G, npoint, 3)
-    float *out;            // (G, 128*Mt3, npoint)
+    float *out;            // (G, 128*Mt3, npoint), or (G, npoint, 128*Mt3) if out_point_major
+    int out_point_major;
     long long *dbg;        // optional timeline buffer (profiling aid): CTA 0 writes clock64() stamps
 };
 
@@ -210,8 +211,11 @@ sa_fused_kernel(const SaFusedParams p) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
-            float *orow = p.out + ((size_t)g * (TC_BM * p.Mt3) + mt * TC_BM + m) * p.npoint +
-                          (nt * TC_BN + h * SF_HALF) / p.nsample;
+            const int c3 = TC_BM * p.Mt3, ch = mt * TC_BM + m, ctr0 = (nt * TC_BN + h * SF_HALF) / p.nsample;
+            // element (centre w) of this channel: channel-first out[g][ch][ctr0 + w]  or  point-major out[g][ctr0 + w][ch]
+            float *orow = p.out_point_major ? p.out + ((size_t)g * p.npoint + ctr0) * c3 + ch
+                                            : p.out + ((size_t)g * c3 + ch) * p.npoint + ctr0;
+            const size_t ostride = p.out_point_major ? (size_t)c3 : 1;
             const int sub = p.nsample < 32 ? p.nsample : 32;
             float run = -INFINITY;
 #pragma unroll 1
@@ -226,7 +230,7 @@ sa_fused_kernel(const SaFusedParams p) {
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
                     run = fmaxf(run, mx);
                     if ((c0 + 32) % p.nsample == 0) {
-                        orow[(c0 + 32) / p.nsample - 1] = run;
+                        orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = run;
                         run = -INFINITY;
                     }
                 } else {
@@ -235,7 +239,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j >= w0 && j < w0 + sub) mx = fmaxf(mx, v[j]);
-                        orow[(c0 + w0) / p.nsample] = mx;
+                        orow[(size_t)((c0 + w0) / p.nsample) * ostride] = mx;
                     }
                 }
             }
@@ -402,7 +406,7 @@ sa_fused_kernel(const SaFusedParams p) {
 extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
                             const float *b3, int C, int C3, int G, int npoint, int nsample, int n_pts,
                             const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
-                            void *stream) {
+                            int out_point_major, void *stream) {
     using namespace jmb;
     static long long *dbg_buf = nullptr;          // JMB_SA_DEBUG=1: CTA 0 records a clock64() timeline (profiling aid)
     static int dbg_on = -1;
@@ -425,7 +429,7 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
     p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM; p.C = C;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
-    p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.dbg = dbg_buf;
+    p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;

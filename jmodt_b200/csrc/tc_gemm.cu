@@ -48,7 +48,8 @@ struct TcGemmParams {
     const float *xyz;             // gather: (G, n_pts, 3)
     const float *centres;         // gather: (G, N / nsample, 3) or null (GroupAll: no centring)
     int nsample, n_pts;
-    int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool)
+    int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool),
+                                  // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store
     int pool, relu;
     float *y;
     long long y_group_stride;     // elements between consecutive groups of y (>= M*N, lets a layer write into a slice of a wider tensor)
@@ -242,6 +243,21 @@ tc_gemm_kernel(const TcGemmParams p) {
                         }
                     }
                 }
+            } else if (p.out_mode == 2) {
+                float *ycol = p.y + (size_t)g * p.y_group_stride + (size_t)nt * TC_BN * p.M + m;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (m < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float o = v[j] + bias;
+                            if (p.relu) o = fmaxf(o, 0.f);
+                            if (nt * TC_BN + c0 + j < p.N) ycol[(size_t)(c0 + j) * p.M] = o;
+                        }
+                    }
+                }
             } else {
                 // max-pool over windows of `pool` columns (pool divides 128; windows never straddle a tile).
                 // N % pool == 0, so a window is either fully inside [0, N) or fully outside.
@@ -349,7 +365,8 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     JMB_REQUIRE(mode == 0 || mode == 1, "tc_mlp_layer: bad mode");
     JMB_REQUIRE(mode == 0 || (xyz && n_pts > 0 && K >= 3 && (centres == nullptr || (nsample > 0 && N % nsample == 0))),
                 "tc_mlp_layer: gather mode needs xyz / nsample");
-    JMB_REQUIRE(out_mode == 0 || (pool > 0 && pool <= TC_BN && TC_BN % pool == 0 && N % pool == 0),
+    JMB_REQUIRE(out_mode >= 0 && out_mode <= 2, "tc_mlp_layer: bad out_mode");
+    JMB_REQUIRE(out_mode != 1 || (pool > 0 && pool <= TC_BN && TC_BN % pool == 0 && N % pool == 0),
                 "tc_mlp_layer: pool must divide 128 and N");
     TcGemmParams p;
     p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
@@ -357,7 +374,7 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.G = G; p.N = N; p.mode = mode; p.x = x; p.x_group_stride = x_group_stride; p.x_row_stride = x_row_stride;
     p.idx = idx; p.xyz = xyz; p.centres = centres; p.nsample = nsample; p.n_pts = n_pts;
     p.out_mode = out_mode; p.pool = pool; p.relu = relu; p.y = y;
-    p.y_group_stride = y_group_stride > 0 ? y_group_stride : (long long)M * (out_mode ? N / pool : N);
+    p.y_group_stride = y_group_stride > 0 ? y_group_stride : (long long)M * (out_mode == 1 ? N / pool : N);
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;

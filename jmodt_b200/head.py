@@ -166,20 +166,35 @@ class RCNN(nn.Module):
         h = xyz_input
         for i, layer in enumerate(P["xyz_up"]):
             h = tc.mlp_layer(layer, h, out=both[:, :c_up] if i == len(P["xyz_up"]) - 1 else None)
-        merged = run_stack(P["merge_down"], both)
-        l_xyz, l_feat = xyz, merged
-        for sa, packed in zip(self.SA_modules, P["sa"]):
+        # The fused set-abstraction kernel gathers from POINT-MAJOR features, so the producers write that layout
+        # directly: merge_down -> (G, 512, 128), SA0 -> (G, 128, 128); no transposes in between.
+        sa_list = list(zip(self.SA_modules, P["sa"]))
+        chain_ok = [self.fuse_chain and sa.npoint is not None and
+                    tc.sa_fused_supported(pk, pk[0].K - 3, sa.npoint, sa.groupers[0].nsample) for sa, pk in sa_list]
+        md = P["merge_down"]
+        h = both
+        for i, layer in enumerate(md):
+            h = tc.mlp_layer(layer, h, point_major_out=(chain_ok[0] and i == len(md) - 1))
+        l_xyz, l_feat, pm = xyz, h, chain_ok[0]                                           # pm: l_feat is point-major
+        for k, (sa, packed) in enumerate(sa_list):
             grouper = sa.groupers[0]
             if sa.npoint is not None:
                 fidx = pu.farthest_point_sample(l_xyz, sa.npoint)
                 new_xyz = pu.gather_operation(l_xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
                 idx = pu.ball_query(grouper.radius, grouper.nsample, l_xyz, new_xyz)
-                if self.fuse_chain and tc.sa_fused_supported(packed, l_feat.shape[1], sa.npoint, grouper.nsample):
-                    l_xyz, l_feat = new_xyz, tc.sa_fused(packed, l_xyz, l_feat.contiguous(), idx, new_xyz)
+                if chain_ok[k]:
+                    next_pm = k + 1 < len(sa_list) and chain_ok[k + 1]
+                    l_feat = tc.sa_fused(packed, l_xyz, l_feat, idx, new_xyz, feats_point_major=pm,
+                                         out_point_major=next_pm)
+                    l_xyz, pm = new_xyz, next_pm
                     continue
+                if pm:
+                    l_feat, pm = l_feat.transpose(1, 2).contiguous(), False
                 h = tc.grouped_first_layer(packed[0], l_xyz, l_feat, idx, new_xyz, grouper.nsample)
                 pool = grouper.nsample
             else:                                                                         # GroupAll
+                if pm:
+                    l_feat, pm = l_feat.transpose(1, 2).contiguous(), False
                 new_xyz = None
                 h = tc.grouped_first_layer(packed[0], l_xyz, l_feat, None, None, 0)
                 pool = l_xyz.shape[1]

@@ -84,10 +84,16 @@ class _PointnetSAModuleBase(nn.Module):
         outs = []
         if features is not None:
             features = features.contiguous()
-        for grouper, layers in zip(self.groupers, packed):
+        pre_idx = {}
+        if len(self.groupers) == 2 and all(isinstance(g, pointnet2_utils.QueryAndGroup) for g in self.groupers):
+            ga, gb = self.groupers      # both scales of an MSG level query the same centres: one scan of the cloud
+            pre_idx[0], pre_idx[1] = pointnet2_utils.ball_query_msg2(ga.radius, ga.nsample, gb.radius, gb.nsample,
+                                                                     xyz, new_xyz)
+        for gi, (grouper, layers) in enumerate(zip(self.groupers, packed)):
             if isinstance(grouper, pointnet2_utils.QueryAndGroup):
                 assert grouper.use_xyz, "the fused path groups xyz with the features"
-                idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+                idx = pre_idx[gi] if gi in pre_idx else \
+                    pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
                 pool = grouper.nsample
                 if getattr(self, "fuse_chain", True) and features is not None and \
                         tc.sa_fused_supported(layers, features.shape[1], new_xyz.shape[1], grouper.nsample):

@@ -168,6 +168,23 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+def ball_query_msg2(radius_a: float, nsample_a: int, radius_b: float, nsample_b: int, xyz: torch.Tensor,
+                    new_xyz: torch.Tensor):
+    """Two ball queries over the same centres in ONE scan of the cloud (what PointnetSAModuleMSG needs per level,
+    reference pointnet2_modules.py:41-42); returns the same two index tensors as two `ball_query` calls."""
+    from .. import _lib
+    assert new_xyz.is_contiguous() and xyz.is_contiguous()
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    idx_a = _new(xyz, (B, npoint, nsample_a), torch.int32)
+    idx_b = _new(xyz, (B, npoint, nsample_b), torch.int32)
+    st = _lib.stream_and_device(xyz)
+    _lib.check(_lib.lib().jmb_ball_query_msg2(B, N, npoint, radius_a, nsample_a, radius_b, nsample_b,
+                                              new_xyz.data_ptr(), xyz.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr(),
+                                              st), "ball_query_msg2")
+    return idx_a, idx_b
+
+
 class QueryAndGroup(nn.Module):
     """reference pointnet2_utils.py:231-264"""
 

@@ -88,12 +88,22 @@ def fold_conv_bn(conv, bn=None):
 
 
 def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None = None,
-              pool: int = 0) -> torch.Tensor:
-    """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0.
+              pool: int = 0, point_major_out: bool = False) -> torch.Tensor:
+    """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0, or the
+    point-major (G, N, M) with point_major_out (the layout the fused set-abstraction kernel gathers from).
     `out` may be a channel slice `buf[:, c0:c0+M]` of a wider contiguous (G, C, N) tensor (replaces torch.cat)."""
     assert x.dim() == 3 and x.is_contiguous() and x.dtype == torch.float32
     G, K, N = x.shape
     assert K == layer.K
+    if point_major_out:
+        assert not pool and out is None
+        y = torch.empty((G, N, layer.M), dtype=torch.float32, device=x.device)
+        st = _lib.stream_and_device(x)
+        profiler.launch(2.0 * layer.M * K * G * N, lambda: _lib.check(
+            _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
+                                        x.data_ptr(), K * N, N, None, None, None, 0, 0, 2, 0, int(layer.relu),
+                                        y.data_ptr(), 0, st), "tc_mlp_layer"))
+        return y
     shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
     y = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
     assert tuple(y.shape) == shape and y.stride(2) == 1 and y.stride(1) == shape[2]
@@ -138,23 +148,27 @@ def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) 
 
 
 def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, centres: torch.Tensor,
-             w1_xyz_last: PackedLayer | None = None) -> torch.Tensor:
+             w1_xyz_last: PackedLayer | None = None, feats_point_major: bool = False,
+             out_point_major: bool = False) -> torch.Tensor:
     """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first (transposed
     here to the point-major layout the gather wants), idx (G, npoint, nsample) int32, centres (G, npoint, 3)
     -> (G, C3, npoint).  `w1_xyz_last` is layers[0] packed with xyz_last=True (built on the fly if omitted)."""
     G, n_pts, _ = xyz.shape
-    C = feats.shape[1]
+    C = feats.shape[2] if feats_point_major else feats.shape[1]
     npoint, nsample = idx.shape[1], idx.shape[2]
     l1, l2, l3 = layers
     assert l1.K == 3 + C and idx.is_contiguous() and xyz.is_contiguous()
     l1 = w1_xyz_last if w1_xyz_last is not None else l1.repacked_xyz_last()
-    feats = feats.transpose(1, 2).contiguous()          # (G, n_pts, C): one neighbour = one contiguous row
-    out = torch.empty((G, l3.M, npoint), dtype=torch.float32, device=xyz.device)
+    if not feats_point_major:
+        feats = feats.transpose(1, 2)                   # (G, n_pts, C): one neighbour = one contiguous row
+    feats = feats.contiguous()
+    oshape = (G, npoint, l3.M) if out_point_major else (G, l3.M, npoint)
+    out = torch.empty(oshape, dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)
     flops = 2.0 * G * npoint * nsample * (l1.M * l1.K + l2.M * l2.K + l3.M * l3.K)
     profiler.launch(flops, lambda: _lib.check(
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
                                 l3.wpack.data_ptr(), l3.bias.data_ptr(), C, l3.M, G, npoint, nsample, n_pts,
                                 feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
-                                out.data_ptr(), st), "sa_fused"))
+                                out.data_ptr(), int(out_point_major), st), "sa_fused"))
     return out

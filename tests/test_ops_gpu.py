@@ -376,3 +376,15 @@ def test_errors_are_raised_not_fatal(cuda):
     assert _lib.lib().jmb_ball_query(-1, 8, 8, 0.5, 4, None, None, None, None) == -1
     assert b"negative" in _lib.lib().jmb_last_error()
     assert _lib.lib().jmb_nms(10, x.data_ptr(), 0.5, x.data_ptr(), x.data_ptr(), 0, None, 0, None) == -3
+
+
+def test_ball_query_msg2_equals_two_queries(cuda, cref):
+    from jmodt_b200.pointnet2 import pointnet2_utils as pu
+    rng = np.random.default_rng(77)
+    for (b, n, m, ra, na, rb, nb) in [(2, 16384, 4096, 0.1, 16, 0.5, 32), (3, 1000, 37, 1.0, 5, 2.0, 9), (8, 256, 64, 2.0, 16, 4.0, 32)]:
+        xyz = clustered_cloud(rng, b, n)
+        new_xyz = xyz[:, :m].copy()
+        new_xyz[:, -1] += 1000.0
+        ia, ib = pu.ball_query_msg2(ra, na, rb, nb, T(xyz, cuda), T(new_xyz, cuda))
+        np.testing.assert_array_equal(ia.cpu().numpy(), cref.ball_query(ra, na, xyz, new_xyz))
+        np.testing.assert_array_equal(ib.cpu().numpy(), cref.ball_query(rb, nb, xyz, new_xyz))
