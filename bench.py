@@ -15,6 +15,10 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+if "LOCAL_RANK" in os.environ:   # torchrun pins OMP_NUM_THREADS=1, which makes the host-side setup (synthetic frames,
+    # weight init) crawl; give every rank its share of the host cores instead
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
 import subprocess
 import sys
 import threading
@@ -290,6 +294,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.frames
     e2e_mode = args.workload == "e2e"
+    t_setup = time.perf_counter()
     # frames shard across ranks: rank r owns frames [r*B, (r+1)*B) of the synthetic sequence (weak scaling);
     # no data-path collective is needed (affinity pairs (2k, 2k+1) never straddle a shard because B is even)
     host_np = make_inputs_e2e(rank * B, B) if e2e_mode else make_inputs(rank * B, B)
@@ -300,6 +305,7 @@ def run_b200(args):
     d = upload(host, dev, torch)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
+    print(f"[bench rank {rank}] setup {time.perf_counter() - t_setup:.1f} s", file=sys.stderr)
 
     def barrier():
         if world > 1:
