@@ -25,7 +25,7 @@ class Profiler:
     def reset(self):
         self.records, self.launches = [], 0
 
-    def launch(self, flops, fn):
+    def launch(self, flops, fn, kind="tc_gemm_kernel"):
         self.launches += 1
         if not self.enabled:
             return fn()
@@ -33,12 +33,13 @@ class Profiler:
         e0.record()
         out = fn()
         e1.record()
-        self.records.append((flops, e0, e1))
+        self.records.append((flops, e0, e1, kind))
         return out
 
-    def summary(self):
-        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
-        return {"flops": float(sum(f for f, _, _ in self.records)), "ms": float(ms), "launches": len(self.records)}
+    def summary(self, kind=None):
+        recs = [r for r in self.records if kind is None or r[3] == kind]
+        ms = sum(a.elapsed_time(b) for _, a, b, _ in recs)
+        return {"flops": float(sum(r[0] for r in recs)), "ms": float(ms), "launches": len(recs)}
 
 
 profiler = Profiler()
@@ -170,5 +171,5 @@ def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, 
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
                                 l3.wpack.data_ptr(), l3.bias.data_ptr(), C, l3.M, G, npoint, nsample, n_pts,
                                 feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
-                                out.data_ptr(), int(out_point_major), st), "sa_fused"))
+                                out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel")
     return out
