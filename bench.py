@@ -52,6 +52,7 @@ def parse():
                          "(BASELINE config 3); ops: the bare jmodt/ops suite (BASELINE config 2)")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default="", help="write the per-launch tcgen05 kernel table of one step here")
     return ap.parse_args()
 
 
@@ -341,6 +342,10 @@ def run_b200(args):
     kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in suite.kernel_ms.items()}
     kernel_calls = {k: len(v) / args.steps for k, v in suite.kernel_ms.items()}
     tc_sum = tc.profiler.summary()
+    if args.dump_launches and rank == 0:
+        with open(args.dump_launches, "w") as f:
+            for desc, kind, flops, ms in tc.profiler.table(args.steps):
+                f.write(f"{ms * 1e3:9.1f} us  {flops / (ms * 1e-3) / 1e12 if ms > 0 else 0:7.1f} TF/s  {kind:16s} {desc}\n")
     tc.profiler.enabled = False
     suite.timing = False
 

@@ -86,6 +86,12 @@ JMB_API int jmb_gather_points_grad(int b, int c, int n, int npoints, const float
 JMB_API int jmb_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
                                 int *idxs, void *stream);
 
+/* Stream gate on sampling progress (no reference counterpart: the reference serialises FPS and its consumers).
+ * Returns, in stream order, once idx[f*row_stride + k] >= 0 for every frame f < b and k0 <= k < k1.  The caller
+ * fills idx with -1 before launching jmb_furthest_point_sampling on ANOTHER stream; work queued behind the gate can
+ * then consume samples k0..k1 while the sampler continues.  Traps after timeout_ms if the producer never writes. */
+JMB_API int jmb_wait_indices(const int *idx, int b, int row_stride, int k0, int k1, int timeout_ms, void *stream);
+
 /* replaces three_nn_wrapper_fast (interpolate.cpp:15-25) -> interpolate_gpu.cu:9-74.
  * dist2 (b,n,3) SQUARED distances, idx (b,n,3). */
 JMB_API int jmb_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "jmb_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "jmb_wait_indices": [_vp, _i, _i, _i, _i, _i, _vp],
     "jmb_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

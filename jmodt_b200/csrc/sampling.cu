@@ -375,6 +375,28 @@ static int pow2_ceil(int v) {
     return p;
 }
 
+// ---- stream gate on FPS progress ---------------------------------------------------------------
+// Furthest point sampling emits its indices one per iteration and is latency-bound on a fraction of the SMs; the
+// consumers of sample k (ball query, grouping, the MLP stack) only need indices 0..k.  This kernel lets a second
+// stream start on a prefix while the sampler is still running: it returns once every idx[f][k0..k1) is >= 0 (the
+// caller pre-fills idx with -1), so work queued behind it sees a complete prefix.  The wait is bounded: if the
+// producer never shows up the kernel traps and the stream reports an error instead of hanging the device.
+__global__ void __launch_bounds__(256)
+wait_indices_kernel(const int *idx, int b, int row_stride, int k0, int k1, unsigned long long timeout_ns) {
+    const int w = k1 - k0;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int e = w * b - 1 - (int)threadIdx.x; e >= 0; e -= (int)blockDim.x) {   // newest entries first
+        const volatile int *p = idx + (size_t)(e / w) * row_stride + k0 + e % w;
+        while (*p < 0) {
+            __nanosleep(256);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) __trap();
+        }
+    }
+}
+
 // ---- gather -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gather_points_kernel(int c, int n, int m, const float *__restrict__ points,
@@ -400,6 +422,17 @@ gather_points_grad_kernel(int c, int n, int m, const float *__restrict__ grad_ou
 }
 
 }  // namespace jmb
+
+extern "C" int jmb_wait_indices(const int *idx, int b, int row_stride, int k0, int k1, int timeout_ms, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(b >= 0 && k0 >= 0 && k1 >= k0 && row_stride >= k1, "wait_indices: bad range");
+    if (b == 0 || k1 == k0) return JMB_OK;
+    JMB_REQUIRE(idx != nullptr, "wait_indices: null pointer");
+    JMB_REQUIRE(timeout_ms > 0, "wait_indices: timeout must be positive");
+    wait_indices_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(idx, b, row_stride, k0, k1,
+                                                            (unsigned long long)timeout_ms * 1000000ULL);
+    return check_launch("wait_indices");
+}
 
 extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
                                            int *idxs, void *stream) {

@@ -12,27 +12,45 @@
 //
 // fp32-grade results from bf16 tensor cores: every fp32 operand is split x = hi + lo (two bf16), and
 // the product is accumulated in fp32 as  W_hi·X_hi + W_lo·X_hi + W_hi·X_lo  (the dropped lo·lo term and
-// the split residuals are <= 2^-16 relative per product).  The reference's own cuDNN path uses single
-// TF32 (10-bit mantissa) by default; the 3-term split is ~64x more accurate than that.
+// the split residuals are <= 2^-16 relative per product).
 //
 // Prologues:  dense X from global memory, or the fused grouping of QueryAndGroup / GroupAll
 // (pointnet2_utils.py:241-290): X[k][n] = xyz[idx[n]][k] - centre[n / nsample][k] for k < 3 and
-// feats[k-3][idx[n]] otherwise — the 549 MB/frame grouped tensor of RCNN SA0 is never materialised.
+// feats[k-3][idx[n]] otherwise — the grouped tensor is never materialised.
 //
-// Structure: persistent CTAs of 5 warps.  Warps 0-3 stage operands (W chunk images by one 16 KB
-// cp.async.bulk, X chunks by vector loads + in-register bf16 split) into an mbarrier ring and run the
-// epilogue; warp 4 lane 0 issues tcgen05.mma and signals through tcgen05.commit.  64 KB smem + 128 TMEM
-// columns per CTA -> 3 CTAs per SM, so one CTA's epilogue overlaps another's MMAs.
+// Structure (v3): one persistent CTA per SM, 18 warps, every hand-off through mbarriers.
+//   warp 17      loader: claims tiles from a global atomic counter (dynamic scheduling: a CTA that shares its SM
+//                with another stream's kernel simply claims fewer tiles), publishes them in a shared-memory tile
+//                ring, and issues all bulk async copies: one 16 KB weight chunk image per K chunk and — for dense
+//                X — the raw fp32 rows of the chunk (32 rows x 512 B, one cp.async.bulk per row) into a 4-stage
+//                ring, so ~64 KB of loads are in flight per SM without holding registers.
+//   warps 0-7    converters: raw fp32 chunk (shared memory) -> bf16 hi/lo split -> MN-major core-matrix images;
+//                in gather mode they load through the neighbour index themselves (register double-buffer).
+//   warp 16      MMA issuer: six tcgen05.mma (128x128x16) per 32-deep K chunk into a double-buffered accumulator.
+//   warps 8-15   epilogue: tcgen05.ld -> bias -> ReLU -> (a) staged in shared memory, written back with one
+//                cp.async.bulk per (row, 64-column half): 256 B contiguous bursts instead of 32 scattered 16 B
+//                stores per instruction; (b) max-pool over nsample in registers; (c) point-major rows.
+// Tiles narrower than 128 columns (N = 8..64 per group, e.g. GroupAll over 32 points) pack 128/N groups into one
+// tile, so the tensor cores and the converters never work on padding columns.
 #include "tc_common.cuh"
 
 namespace jmb {
 
-// warp roles: 0-3 operand producers (X), 4-7 epilogue (TMEM lane quadrant = warp & 3), 8 MMA issuer, 9 weight loader
-constexpr int TC_XSTAGES = 3;                      // X ring: 16 KB per stage (hi + lo image)
-constexpr int TC_WSTAGES = 4;                      // W ring: 16 KB per stage, filled by cp.async.bulk, runs ahead of X
+constexpr int TC_XSTAGES = 2;                      // converted X ring: 16 KB per stage (hi + lo image)
+constexpr int TC_WSTAGES = 3;                      // W ring: 16 KB per stage
+constexpr int TC_RSTAGES = 4;                      // raw fp32 X ring
+constexpr int TC_TSLOTS = 8;                       // tile ring
 constexpr int TC_CHUNK = 2 * TC_IMG;               // hi + lo image of one 32-row chunk
-constexpr int TC_SMEM = (TC_XSTAGES + TC_WSTAGES) * TC_CHUNK;   // 112 KB -> 2 CTAs per SM
-constexpr int TC_THREADS = 320;
+constexpr int TC_RAW_ROW = TC_BN * 4 + 16;         // padded row: 8 consecutive rows hit 8 distinct bank groups
+constexpr int TC_RAW_STAGE = TC_BK * TC_RAW_ROW;   // 16 896 B
+constexpr int TC_OUT_STAGE = TC_BM * TC_RAW_ROW;   // 67 584 B
+constexpr int TC_OFF_X = 0;
+constexpr int TC_OFF_W = TC_OFF_X + TC_XSTAGES * TC_CHUNK;
+constexpr int TC_OFF_RAW = TC_OFF_W + TC_WSTAGES * TC_CHUNK;
+constexpr int TC_OFF_OUT = TC_OFF_RAW + TC_RSTAGES * TC_RAW_STAGE;
+constexpr int TC_SMEM = TC_OFF_OUT + TC_OUT_STAGE;  // 217 088 B -> one CTA per SM
+constexpr int TC_CONV_WARPS = 8, TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (TC_CONV_WARPS + TC_EPI_WARPS + 3) * 32;   // 608
 constexpr int TC_ACC_BUFS = 2;                     // double-buffered accumulator: epilogue overlaps the next tile's MMAs
 
 struct TcGemmParams {
@@ -40,7 +58,11 @@ struct TcGemmParams {
     const float *bias;            // [Mt*128] (zero padded), may be null
     int M, K, Mt, Kc;
     int G, N;                     // groups, columns per group
+    int P, Nt, Nshift;            // groups per tile (1 unless N < 128 divides 128), column tiles per group, log2(N) if P > 1
+    long long col_tiles;          // G * Nt (P == 1) or ceil(G / P)
     int mode;                     // 0 dense, 1 grouped gather
+    int use_raw;                  // dense X staged by bulk copies (needs 16-byte aligned rows)
+    int bulk_out;                 // dense Y written by bulk copies (needs 16-byte aligned rows)
     const float *x;               // dense: (G, K, N)   gather: feats (G, K-3, n_pts)
     long long x_group_stride;     // elements
     int x_row_stride;             // elements between consecutive k rows
@@ -52,26 +74,49 @@ struct TcGemmParams {
                                   // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store
     int pool, relu;
     float *y;
-    long long y_group_stride;     // elements between consecutive groups of y (>= M*N, lets a layer write into a slice of a wider tensor)
+    long long y_group_stride;     // elements between consecutive groups of y
+    int *counter, *done;          // dynamic tile scheduler (reset by the last CTA to leave)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
+// column c (0..127) of column tile ct -> group g and column n inside the group
+__device__ __forceinline__ void tc_col(const TcGemmParams &p, long long ct, int c, int &g, int &n) {
+    if (p.P == 1) {
+        g = (int)(ct / p.Nt);
+        n = (int)(ct % p.Nt) * TC_BN + c;
+    } else {
+        g = (int)ct * p.P + (c >> p.Nshift);
+        n = c & (p.N - 1);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const TcGemmParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t s_xfull[TC_XSTAGES], s_xempty[TC_XSTAGES], s_wfull[TC_WSTAGES], s_wempty[TC_WSTAGES],
-        s_acc_full[TC_ACC_BUFS], s_acc_empty[TC_ACC_BUFS];
+        s_rfull[TC_RSTAGES], s_rempty[TC_RSTAGES], s_acc_full[TC_ACC_BUFS], s_acc_empty[TC_ACC_BUFS],
+        s_tfull[TC_TSLOTS], s_tempty[TC_TSLOTS];
+    __shared__ int s_tile[TC_TSLOTS];
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int W_MMA = TC_CONV_WARPS + TC_EPI_WARPS, W_LOAD = W_MMA + 1, W_WLOAD = W_MMA + 2;
+    constexpr int N_CONSUMER_WARPS = TC_CONV_WARPS + TC_EPI_WARPS + 2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], 128); mbar_init(&s_xempty[s], 1); }
+        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], TC_CONV_WARPS * 32); mbar_init(&s_xempty[s], 1); }
         for (int s = 0; s < TC_WSTAGES; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_wempty[s], 1); }
-        for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], 128); }
+        for (int s = 0; s < TC_RSTAGES; ++s) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], TC_CONV_WARPS * 32); }
+        for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], TC_EPI_WARPS * 32); }
+        for (int s = 0; s < TC_TSLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], N_CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                      "r"((uint32_t)(TC_ACC_BUFS * TC_BN))
                      : "memory");
@@ -82,206 +127,332 @@ tc_gemm_kernel(const TcGemmParams p) {
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    const int Nt = (p.N + TC_BN - 1) / TC_BN;
-    const long long total_tiles = (long long)p.G * Nt * p.Mt;
-    uint32_t chunk_ctr = 0;  // global k-chunk counter: stage = ctr % STAGES, phase = (ctr / STAGES) & 1
-    uint32_t tile_ctr = 0;
+    const long long total_tiles = p.col_tiles * p.Mt;
+    uint32_t tctr = 0;   // position in the tile ring (every role walks it independently)
 
-    if (warp < 4) {
-        // =============================== operand producers ===============================
-        const int t = threadIdx.x;
-        const int kk = t & 7;               // k row inside a group of 8
-        const int ng = warp * 4 + ((t >> 3) & 3);   // n group of 8 columns inside the tile
-        // Operand staging is software-pipelined: the global loads of work item i+1 (the next K chunk, possibly of the
-        // next tile) are issued into registers before item i is converted and stored, so one load round trip is hidden
-        // behind the split / store / MMA of the previous chunk and behind the epilogue.
-        struct TileCoord { int mt, nt, g, n0; };
-        auto coord = [&](long long tile) {
-            TileCoord c;
-            c.mt = (int)(tile % p.Mt);
-            const long long gn = tile / p.Mt;
-            c.nt = (int)(gn % Nt);
-            c.g = (int)(gn / Nt);
-            c.n0 = c.nt * TC_BN + ng * 8;
-            return c;
-        };
-        int pidx[8];              // gather mode: point index of this thread's 8 columns, for the tile being LOADED
-        long long pidx_tile = -1;
-        auto load_chunk = [&](long long tile, int kc, float (&v)[TC_BK / 8][8]) {
-            const TileCoord tc_ = coord(tile);
-            const float *xg = p.x + (size_t)tc_.g * p.x_group_stride;
-            if (p.mode == 1 && pidx_tile != tile) {
-                pidx_tile = tile;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = tc_.n0 + j;
-                    pidx[j] = 0;
-                    if (n < p.N) pidx[j] = p.idx ? __ldg(p.idx + (size_t)tc_.g * p.N + n) : (n % p.n_pts);
-                }
+    // tile ring consumer side: read slot i (blocking), release slot i (one arrive per warp)
+    auto ring_read = [&](uint32_t i) -> int {
+        const int slot = i % TC_TSLOTS;
+        mbar_wait(&s_tfull[slot], (i / TC_TSLOTS) & 1);
+        return *reinterpret_cast<volatile int *>(&s_tile[slot]);
+    };
+    auto ring_release = [&](uint32_t i) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_tempty[i % TC_TSLOTS]);
+    };
+
+    if (warp == W_LOAD) {
+        // =============================== loader: tile scheduler + all bulk copies ===============================
+        uint32_t rctr = 0;
+        auto fetch = [&]() -> int {
+            int t = -1;
+            if (lane == 0) {
+                t = atomicAdd(p.counter, 1);
+                if ((long long)t >= total_tiles) t = -1;
             }
-#pragma unroll
-            for (int kb = 0; kb < TC_BK / 8; ++kb) {
-                const int k = kc * TC_BK + kb * 8 + kk;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[kb][j] = 0.f;
-                if (k < p.K) {
-                    if (p.mode == 0) {
-                        const float *row = xg + (size_t)k * p.x_row_stride + tc_.n0;
-                        if (tc_.n0 + 8 <= p.N && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                            const float4 a4 = __ldg(reinterpret_cast<const float4 *>(row));
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(row) + 1);
-                            v[kb][0] = a4.x; v[kb][1] = a4.y; v[kb][2] = a4.z; v[kb][3] = a4.w;
-                            v[kb][4] = b4.x; v[kb][5] = b4.y; v[kb][6] = b4.z; v[kb][7] = b4.w;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (tc_.n0 + j < p.N) v[kb][j] = __ldg(row + j);
-                        }
-                    } else if (k < 3) {
-                        const float *pts = p.xyz + (size_t)tc_.g * p.n_pts * 3;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int n = tc_.n0 + j;
-                            if (n < p.N) {
-                                float c = 0.f;
-                                if (p.centres) c = __ldg(p.centres + ((size_t)tc_.g * (p.N / p.nsample) + n / p.nsample) * 3 + k);
-                                v[kb][j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), c);
-                            }
-                        }
-                    } else {
-                        const float *row = xg + (size_t)(k - 3) * p.x_row_stride;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (tc_.n0 + j < p.N) v[kb][j] = __ldg(row + pidx[j]);
+            return __shfl_sync(0xffffffffu, t, 0);
+        };
+        auto publish = [&](int t) {
+            if (lane == 0) {
+                const int slot = tctr % TC_TSLOTS;
+                mbar_wait(&s_tempty[slot], ((tctr / TC_TSLOTS) & 1) ^ 1);
+                *reinterpret_cast<volatile int *>(&s_tile[slot]) = t;
+                mbar_arrive(&s_tfull[slot]);
+            }
+            ++tctr;
+        };
+        int cur = fetch();
+        publish(cur);
+        while (cur >= 0) {
+            const int nxt = fetch();     // published one tile ahead: the converters prefetch across tile boundaries
+            publish(nxt);
+            const long long ct = cur / p.Mt;
+            int g0, n0;
+            tc_col(p, ct, 0, g0, n0);
+            const int gv = p.P == 1 ? 1 : min(p.P, p.G - g0);                // valid groups in the tile
+            const int cols = p.P == 1 ? min(TC_BN, p.N - n0) : p.N;          // valid columns per group piece
+            if (p.use_raw) {
+                for (int kc = 0; kc < p.Kc; ++kc) {
+                    const int s = rctr % TC_RSTAGES;
+                    const int rows = min(TC_BK, p.K - kc * TC_BK);
+                    if (lane == 0) {
+                        mbar_wait(&s_rempty[s], ((rctr / TC_RSTAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&s_rfull[s], (uint32_t)(rows * gv * cols * 4));
                     }
+                    __syncwarp();
+                    if (lane < rows) {
+                        uint8_t *dst = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)lane * TC_RAW_ROW;
+                        const float *src = p.x + (size_t)g0 * p.x_group_stride + (size_t)(kc * TC_BK + lane) * p.x_row_stride + n0;
+                        for (int gi = 0; gi < gv; ++gi)
+                            bulk_g2s(dst + (size_t)gi * cols * 4, src + (size_t)gi * p.x_group_stride, (uint32_t)cols * 4, &s_rfull[s]);
+                    }
+                    ++rctr;
                 }
             }
-        };
-        auto store_chunk = [&](const float (&v)[TC_BK / 8][8]) {
-            const int s = chunk_ctr % TC_XSTAGES;
-            const uint32_t ph = (chunk_ctr / TC_XSTAGES) & 1;
-            mbar_wait(&s_xempty[s], ph ^ 1);
-            uint8_t *xhi = tc_smem + (size_t)s * TC_CHUNK, *xlo = xhi + TC_IMG;
+            cur = nxt;
+        }
+    } else if (warp == W_WLOAD) {
+        // =============================== weight loader: one 16 KB cp.async.bulk per K chunk ===============================
+        uint32_t wctr = 0;
+        int cur = ring_read(tctr);
+        while (cur >= 0) {
+            if (lane == 0) {
+                const int mt = cur % p.Mt;
+                for (int kc = 0; kc < p.Kc; ++kc, ++wctr) {
+                    const int s = wctr % TC_WSTAGES;
+                    mbar_wait(&s_wempty[s], ((wctr / TC_WSTAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&s_wfull[s], TC_CHUNK);
+                    bulk_g2s(tc_smem + TC_OFF_W + (size_t)s * TC_CHUNK, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG,
+                             TC_CHUNK, &s_wfull[s]);
+                }
+            }
+            ring_release(tctr);
+            ++tctr;
+            cur = ring_read(tctr);
+        }
+        ring_release(tctr);
+    } else if (warp < TC_CONV_WARPS) {
+        // =============================== converters ===============================
+        const int t = threadIdx.x;
+        const int kk = t & 7;                // k row inside a group of 8
+        const int ng = (t >> 3) & 15;        // group of 8 columns inside the tile
+        const int kh = t >> 7;               // this thread converts k blocks kh and kh + 2 of the chunk
+        uint32_t xctr = 0, rctr = 0;
+
+        auto store_images = [&](const float (&v)[2][8]) {
+            const int s = xctr % TC_XSTAGES;
+            mbar_wait(&s_xempty[s], ((xctr / TC_XSTAGES) & 1) ^ 1);
+            uint8_t *xhi = tc_smem + TC_OFF_X + (size_t)s * TC_CHUNK, *xlo = xhi + TC_IMG;
 #pragma unroll
-            for (int kb = 0; kb < TC_BK / 8; ++kb) {
+            for (int q = 0; q < 2; ++q) {
                 uint4 h, l;
-                split2(v[kb][0], v[kb][1], h.x, l.x);
-                split2(v[kb][2], v[kb][3], h.y, l.y);
-                split2(v[kb][4], v[kb][5], h.z, l.z);
-                split2(v[kb][6], v[kb][7], h.w, l.w);
-                const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)kb * TC_LBO + (uint32_t)kk * 16;
+                split2(v[q][0], v[q][1], h.x, l.x);
+                split2(v[q][2], v[q][3], h.y, l.y);
+                split2(v[q][4], v[q][5], h.z, l.z);
+                split2(v[q][6], v[q][7], h.w, l.w);
+                const uint32_t off = (uint32_t)ng * TC_SBO + (uint32_t)(kh + 2 * q) * TC_LBO + (uint32_t)kk * 16;
                 *reinterpret_cast<uint4 *>(xhi + off) = h;
                 *reinterpret_cast<uint4 *>(xlo + off) = l;
             }
             fence_proxy_async();
             mbar_arrive(&s_xfull[s]);
-            ++chunk_ctr;
+            ++xctr;
         };
 
-        float va[TC_BK / 8][8], vb[TC_BK / 8][8];
-        if ((long long)blockIdx.x < total_tiles) load_chunk(blockIdx.x, 0, va);
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            const TileCoord tcur = coord(tile);
-            const int mt = tcur.mt, nt = tcur.nt, g = tcur.g;
-            const long long next_tile = tile + gridDim.x;
-            for (int kc = 0; kc < p.Kc; kc += 2) {
-                // item (tile, kc) is in va; prefetch (tile, kc+1) or the next tile's first chunk into vb
-                if (kc + 1 < p.Kc) load_chunk(tile, kc + 1, vb);
-                else if (next_tile < total_tiles) load_chunk(next_tile, 0, vb);
-                store_chunk(va);
-                if (kc + 1 < p.Kc) {
-                    if (kc + 2 < p.Kc) load_chunk(tile, kc + 2, va);
-                    else if (next_tile < total_tiles) load_chunk(next_tile, 0, va);
-                    store_chunk(vb);
-                } else {
-                    // odd chunk count: the prefetched first chunk of the next tile sits in vb; move it to va
+        if (p.use_raw) {
+            int cur = ring_read(tctr);
+            while (cur >= 0) {
+                for (int kc = 0; kc < p.Kc; ++kc) {
+                    const int s = rctr % TC_RSTAGES;
+                    mbar_wait(&s_rfull[s], (rctr / TC_RSTAGES) & 1);
+                    float v[2][8];
 #pragma unroll
-                    for (int kb = 0; kb < TC_BK / 8; ++kb)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) va[kb][j] = vb[kb][j];
-                }
-            }
-
-        }
-    } else if (warp < 8) {
-        // =============================== epilogue: one output channel per thread ===============================
-        const int quad = warp & 3;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            const int mt = (int)(tile % p.Mt);
-            const long long gn = tile / p.Mt;
-            const int nt = (int)(gn % Nt);
-            const int g = (int)(gn / Nt);
-            // ---- epilogue: one output channel per thread ----
-            const int buf = tile_ctr % TC_ACC_BUFS;
-            mbar_wait(&s_acc_full[buf], (tile_ctr / TC_ACC_BUFS) & 1);
-            tc_fence_after();
-            const int m = mt * TC_BM + quad * 32 + lane;
-            const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_BN;
-            if (p.out_mode == 0) {
-                float *yrow = p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + (size_t)nt * TC_BN;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + c0, v);
-                    if (m < p.M) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float o = v[j] + bias;
-                            if (p.relu) o = fmaxf(o, 0.f);
-                            v[j] = o;
-                        }
-                        const int ncol = nt * TC_BN + c0;
-                        if (ncol + 32 <= p.N && ((reinterpret_cast<uintptr_t>(yrow + c0) & 15u) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4 *>(yrow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int q = 0; q < 2; ++q) {
+                        const int row = (kh + 2 * q) * 8 + kk;
+                        if (kc * TC_BK + row < p.K) {
+                            const float4 *src = reinterpret_cast<const float4 *>(
+                                tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)row * TC_RAW_ROW + ng * 32);
+                            const float4 a4 = src[0], b4 = src[1];
+                            v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                            v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (ncol + j < p.N) yrow[c0 + j] = v[j];
+                            for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+                        }
+                    }
+                    store_images(v);                 // consumes v, so the raw stage can be handed back afterwards
+                    mbar_arrive(&s_rempty[s]);
+                    ++rctr;
+                }
+                ring_release(tctr);
+                ++tctr;
+                cur = ring_read(tctr);
+            }
+            ring_release(tctr);
+        } else {
+            // register path: gather mode, or dense rows that are not 16-byte aligned.  Software-pipelined: the global
+            // loads of the next chunk (possibly of the next tile) are issued before the current one is converted.
+            int tg = 0, tn0 = 0;          // group / first column (inside the group) of this thread's 8 columns, for the tile being LOADED
+            int pidx[8];
+            int loaded_tile = -1;
+            auto load_chunk = [&](int tile, int kc, float (&v)[2][8]) {
+                if (loaded_tile != tile) {
+                    loaded_tile = tile;
+                    tc_col(p, tile / p.Mt, ng * 8, tg, tn0);
+                    if (p.mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int n = tn0 + j;
+                            pidx[j] = 0;
+                            if (tg < p.G && n < p.N) pidx[j] = p.idx ? __ldg(p.idx + (size_t)tg * p.N + n) : (n % p.n_pts);
                         }
                     }
                 }
-            } else if (p.out_mode == 2) {
-                float *ycol = p.y + (size_t)g * p.y_group_stride + (size_t)nt * TC_BN * p.M + m;
+                const bool gok = tg < p.G;
+                const float *xg = p.x + (size_t)(gok ? tg : 0) * p.x_group_stride;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int k = kc * TC_BK + (kh + 2 * q) * 8 + kk;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+                    if (k < p.K && gok) {
+                        if (p.mode == 0) {
+                            const float *row = xg + (size_t)k * p.x_row_stride + tn0;
+                            if (tn0 + 8 <= p.N && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(row));
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(row) + 1);
+                                v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                                v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (tn0 + j < p.N) v[q][j] = __ldg(row + j);
+                            }
+                        } else if (k < 3) {
+                            const float *pts = p.xyz + (size_t)tg * p.n_pts * 3;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int n = tn0 + j;
+                                if (n < p.N) {
+                                    float c = 0.f;
+                                    if (p.centres) c = __ldg(p.centres + ((size_t)tg * (p.N / p.nsample) + n / p.nsample) * 3 + k);
+                                    v[q][j] = __fsub_rn(__ldg(pts + (size_t)pidx[j] * 3 + k), c);
+                                }
+                            }
+                        } else {
+                            const float *row = xg + (size_t)(k - 3) * p.x_row_stride;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (tn0 + j < p.N) v[q][j] = __ldg(row + pidx[j]);
+                        }
+                    }
+                }
+            };
+
+            float va[2][8], vb[2][8];
+            int cur = ring_read(tctr);
+            if (cur >= 0) load_chunk(cur, 0, va);
+            while (cur >= 0) {
+                const int nxt = ring_read(tctr + 1);
+                for (int kc = 0; kc < p.Kc; kc += 2) {
+                    // item (cur, kc) is in va; prefetch (cur, kc+1) or the next tile's first chunk into vb
+                    if (kc + 1 < p.Kc) load_chunk(cur, kc + 1, vb);
+                    else if (nxt >= 0) load_chunk(nxt, 0, vb);
+                    store_images(va);
+                    if (kc + 1 < p.Kc) {
+                        if (kc + 2 < p.Kc) load_chunk(cur, kc + 2, va);
+                        else if (nxt >= 0) load_chunk(nxt, 0, va);
+                        store_images(vb);
+                    } else {
+                        // odd chunk count: the prefetched first chunk of the next tile sits in vb; move it to va
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) va[q][j] = vb[q][j];
+                    }
+                }
+                ring_release(tctr);
+                ++tctr;
+                cur = nxt;
+            }
+            ring_release(tctr);
+        }
+    } else if (warp < W_MMA) {
+        // =============================== epilogue: one output channel per thread, 64 columns per warp ===============================
+        const int e = warp - TC_CONV_WARPS;
+        const int quad = e & 3, half = e >> 2;
+        const int r = quad * 32 + lane;                 // accumulator row = TMEM lane
+        uint8_t *stage_row = tc_smem + TC_OFF_OUT + (size_t)r * TC_RAW_ROW;
+        uint32_t tile_ctr = 0;
+        int cur = ring_read(tctr);
+        while (cur >= 0) {
+            const int mt = cur % p.Mt;
+            const long long ct = cur / p.Mt;
+            const int buf = tile_ctr % TC_ACC_BUFS;
+            const int m = mt * TC_BM + r;
+            const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
+            // pool windows of 128 columns are reduced by the half-0 warps alone
+            const bool whole = (p.out_mode == 1 && p.pool > 64);
+            const int c_begin = whole ? 0 : half * 64;
+            const int c_end = whole ? (half == 0 ? TC_BN : 0) : c_begin + 64;
+            if (p.out_mode == 0 && p.bulk_out)
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging rows of the previous tile are free again
+            mbar_wait(&s_acc_full[buf], (tile_ctr / TC_ACC_BUFS) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_BN;
+            float run = -INFINITY;
 #pragma unroll 1
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + c0, v);
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (c0 + 32 >= c_end) {     // last read of this accumulator by this thread: hand it back to the MMA warp early
+                    tc_fence_before();
+                    mbar_arrive(&s_acc_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float o = v[j] + bias;
+                    v[j] = p.relu ? fmaxf(o, 0.f) : o;
+                }
+                if (p.out_mode == 0) {
+                    if (p.bulk_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(stage_row + (size_t)(c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else if (m < p.M) {
+                        if (p.P == 1 || p.N >= 32) {       // the 32 columns of the block belong to one group
+                            int g, n;
+                            tc_col(p, ct, c0, g, n);
+                            float *dst = p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + n;
+                            if (g < p.G) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n + j < p.N) dst[j] = v[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                int g, n;
+                                tc_col(p, ct, c0 + j, g, n);
+                                if (g < p.G && n < p.N) p.y[(size_t)g * p.y_group_stride + (size_t)m * p.N + n] = v[j];
+                            }
+                        }
+                    }
+                } else if (p.out_mode == 2) {
                     if (m < p.M) {
+                        if (p.P == 1 || p.N >= 32) {
+                            int g, n;
+                            tc_col(p, ct, c0, g, n);
+                            float *dst = p.y + (size_t)g * p.y_group_stride + (size_t)n * p.M + m;
+                            if (g < p.G) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float o = v[j] + bias;
-                            if (p.relu) o = fmaxf(o, 0.f);
-                            if (nt * TC_BN + c0 + j < p.N) ycol[(size_t)(c0 + j) * p.M] = o;
+                                for (int j = 0; j < 32; ++j)
+                                    if (n + j < p.N) dst[(size_t)j * p.M] = v[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                int g, n;
+                                tc_col(p, ct, c0 + j, g, n);
+                                if (g < p.G && n < p.N) p.y[(size_t)g * p.y_group_stride + (size_t)n * p.M + m] = v[j];
+                            }
                         }
                     }
-                }
-            } else {
-                // max-pool over windows of `pool` columns (pool divides 128; windows never straddle a tile).
-                // N % pool == 0, so a window is either fully inside [0, N) or fully outside.
-                const int groups_per_row = p.N / p.pool;
-                float *yrow = p.y + (size_t)g * p.y_group_stride + (size_t)m * groups_per_row + (size_t)(nt * TC_BN) / p.pool;
-                const int sub = p.pool < 32 ? p.pool : 32;      // window length inside one 32-column chunk
-                float run = -INFINITY;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + c0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float o = v[j] + bias;
-                        v[j] = p.relu ? fmaxf(o, 0.f) : o;
-                    }
+                } else {
+                    // max-pool over windows of `pool` columns (pool divides 128 and N: a window never straddles a tile or
+                    // a group, and is either fully valid or fully outside)
+                    const int sub = p.pool < 32 ? p.pool : 32;      // window length inside one 32-column block
+                    const int wins = p.N / p.pool;
                     if (sub == 32) {
                         float mx = v[0];
 #pragma unroll
                         for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
                         run = fmaxf(run, mx);
                         if ((c0 + 32) % p.pool == 0) {
-                            const int w = (c0 + 32) / p.pool - 1;
-                            if (m < p.M && nt * TC_BN + c0 < p.N) yrow[w] = run;
+                            int g, n;
+                            tc_col(p, ct, c0 + 32 - p.pool, g, n);
+                            if (m < p.M && g < p.G && n < p.N)
+                                p.y[(size_t)g * p.y_group_stride + (size_t)m * wins + n / p.pool] = run;
                             run = -INFINITY;
                         }
                     } else {
@@ -290,66 +461,116 @@ tc_gemm_kernel(const TcGemmParams p) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (j >= w0 && j < w0 + sub) mx = fmaxf(mx, v[j]);
-                            if (m < p.M && nt * TC_BN + c0 + w0 < p.N) yrow[(c0 + w0) / p.pool] = mx;
+                            int g, n;
+                            tc_col(p, ct, c0 + w0, g, n);
+                            if (m < p.M && g < p.G && n < p.N)
+                                p.y[(size_t)g * p.y_group_stride + (size_t)m * wins + n / p.pool] = mx;
                         }
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&s_acc_empty[buf]);
-        }
-    } else if (warp == 9) {
-        if (lane == 0) {
-            // =============================== weight loader: one 16 KB cp.async.bulk per K chunk ===============================
-            uint32_t wctr = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = (int)(tile % p.Mt);
-                for (int kc = 0; kc < p.Kc; ++kc, ++wctr) {
-                    const int s = wctr % TC_WSTAGES;
-                    mbar_wait(&s_wempty[s], ((wctr / TC_WSTAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&s_wfull[s], TC_CHUNK);
-                    bulk_g2s(tc_smem + (size_t)(TC_XSTAGES + s) * TC_CHUNK, p.wpack + ((size_t)mt * p.Kc + kc) * (size_t)TC_IMG,
-                             TC_CHUNK, &s_wfull[s]);
-                }
+            if (whole && half != 0) {       // nothing read: still hand the accumulator back
+                tc_fence_before();
+                mbar_arrive(&s_acc_empty[buf]);
             }
+            if (p.out_mode == 0 && p.bulk_out) {
+                fence_proxy_async();        // this thread's staged row -> visible to the bulk-copy engine
+                if (m < p.M) {
+                    if (p.P == 1) {
+                        int g, n;
+                        tc_col(p, ct, c_begin, g, n);
+                        const int cnt = min(64, p.N - n);
+                        if (cnt > 0)
+                            bulk_s2g(p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + n, stage_row + (size_t)c_begin * 4,
+                                     (uint32_t)cnt * 4);
+                    } else {
+                        const int piece = min(p.N, 64);
+                        for (int c = c_begin; c < c_end; c += piece) {
+                            int g, n;
+                            tc_col(p, ct, c, g, n);
+                            if (g < p.G)
+                                bulk_s2g(p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + n, stage_row + (size_t)c * 4,
+                                         (uint32_t)piece * 4);
+                        }
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++tile_ctr;
+            ring_release(tctr);
+            ++tctr;
+            cur = ring_read(tctr);
         }
-        __syncwarp();
-    } else {
-      if (lane == 0) {
+        ring_release(tctr);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (warp == W_MMA) {
         // =============================== MMA issuer ===============================
         constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            const int buf = tile_ctr % TC_ACC_BUFS;
-            mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
-            for (int kc = 0; kc < p.Kc; ++kc, ++chunk_ctr) {
-                const int sx = chunk_ctr % TC_XSTAGES, sw = chunk_ctr % TC_WSTAGES;
-                mbar_wait(&s_wfull[sw], (chunk_ctr / TC_WSTAGES) & 1);
-                mbar_wait(&s_xfull[sx], (chunk_ctr / TC_XSTAGES) & 1);
+        uint32_t xctr = 0, wctr = 0, tile_ctr = 0;
+        int cur = ring_read(tctr);
+        while (cur >= 0) {
+            if (lane == 0) {
+                const int buf = tile_ctr % TC_ACC_BUFS;
+                mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
                 tc_fence_after();
-                const uint64_t xd = make_smem_desc(smem_u32(tc_smem + (size_t)sx * TC_CHUNK));
-                const uint64_t wd = make_smem_desc(smem_u32(tc_smem + (size_t)(TC_XSTAGES + sw) * TC_CHUNK));
-                umma_ss(acc, wd, xd, kc != 0);
-                umma_ss(acc, wd + D_IMG, xd, 1);
-                umma_ss(acc, wd, xd + D_IMG, 1);
-                umma_ss(acc, wd + D_K16, xd + D_K16, 1);
-                umma_ss(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
-                umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
-                umma_commit(&s_xempty[sx]);
-                umma_commit(&s_wempty[sw]);
+                const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
+                for (int kc = 0; kc < p.Kc; ++kc, ++xctr, ++wctr) {
+                    const int sx = xctr % TC_XSTAGES, sw = wctr % TC_WSTAGES;
+                    mbar_wait(&s_wfull[sw], (wctr / TC_WSTAGES) & 1);
+                    mbar_wait(&s_xfull[sx], (xctr / TC_XSTAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t xd = make_smem_desc(smem_u32(tc_smem + TC_OFF_X + (size_t)sx * TC_CHUNK));
+                    const uint64_t wd = make_smem_desc(smem_u32(tc_smem + TC_OFF_W + (size_t)sw * TC_CHUNK));
+                    umma_ss(acc, wd, xd, kc != 0);
+                    umma_ss(acc, wd + D_IMG, xd, 1);
+                    umma_ss(acc, wd, xd + D_IMG, 1);
+                    umma_ss(acc, wd + D_K16, xd + D_K16, 1);
+                    umma_ss(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
+                    umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
+                    umma_commit(&s_xempty[sx]);
+                    umma_commit(&s_wempty[sw]);
+                }
+                umma_commit(&s_acc_full[buf]);
             }
-            umma_commit(&s_acc_full[buf]);
+            ++tile_ctr;
+            ring_release(tctr);
+            ++tctr;
+            cur = ring_read(tctr);
         }
-      }
-      __syncwarp();
+        ring_release(tctr);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_ACC_BUFS * TC_BN)) : "memory");
     }
+    if (threadIdx.x == 0) {
+        // the last CTA to leave re-arms the scheduler for the next launch that uses this slot
+        __threadfence();
+        const int old = atomicAdd(p.done, 1);
+        if (old == (int)gridDim.x - 1) {
+            *p.counter = 0;
+            *p.done = 0;
+            __threadfence();
+        }
+    }
+}
+
+// Scheduler counters: 64 (counter, done) pairs per device, used round-robin so that launches which may overlap on
+// different streams never share a pair.  512 bytes, allocated once per device (the only allocation in the library).
+constexpr int TC_SCHED_SLOTS = 64;
+static int *tc_sched_buffer(int dev) {
+    static int *bufs[64] = {nullptr};
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!bufs[dev]) {
+        int *b = nullptr;
+        if (cudaMalloc(&b, 2 * TC_SCHED_SLOTS * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(b, 0, 2 * TC_SCHED_SLOTS * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaDeviceSynchronize();
+        bufs[dev] = b;
+    }
+    return bufs[dev];
 }
 
 }  // namespace jmb
@@ -375,20 +596,39 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.idx = idx; p.xyz = xyz; p.centres = centres; p.nsample = nsample; p.n_pts = n_pts;
     p.out_mode = out_mode; p.pool = pool; p.relu = relu; p.y = y;
     p.y_group_stride = y_group_stride > 0 ? y_group_stride : (long long)M * (out_mode == 1 ? N / pool : N);
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        JMB_CUDA(cudaGetDevice(&dev));
-        JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // narrow groups (N = 8, 16, 32, 64) are packed 128/N to a tile
+    p.P = 1; p.Nshift = 0;
+    if (N >= 8 && N < TC_BN && (N & (N - 1)) == 0 && G > 1) {
+        p.P = TC_BN / N;
+        while ((1 << p.Nshift) < N) ++p.Nshift;
     }
+    p.Nt = p.P == 1 ? div_up(N, TC_BN) : 1;
+    p.col_tiles = p.P == 1 ? (long long)G * p.Nt : (long long)div_up(G, p.P);
+    const long long tiles = p.col_tiles * p.Mt;
+    JMB_REQUIRE(tiles < (1LL << 30), "tc_mlp_layer: too many tiles");
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    p.use_raw = (mode == 0 && al16(x) && N % 4 == 0 && x_row_stride % 4 == 0 && x_group_stride % 4 == 0) ? 1 : 0;
+    p.bulk_out = (out_mode == 0 && al16(y) && N % 4 == 0 && p.y_group_stride % 4 == 0) ? 1 : 0;
+
+    static int sms[64] = {0};
+    int dev = 0;
+    JMB_CUDA(cudaGetDevice(&dev));
+    JMB_REQUIRE(dev >= 0 && dev < 64, "tc_mlp_layer: device index %d", dev);
+    if (sms[dev] == 0) JMB_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    int *sched = tc_sched_buffer(dev);
+    JMB_REQUIRE(sched != nullptr, "tc_mlp_layer: cannot allocate the scheduler counters");
+    static unsigned launch_seq = 0;
+    const unsigned slot = (launch_seq++) % TC_SCHED_SLOTS;
+    p.counter = sched + 2 * slot;
+    p.done = sched + 2 * slot + 1;
+
     const size_t smem = (size_t)TC_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
         JMB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const long long tiles = (long long)G * div_up(N, TC_BN) * p.Mt;
-    const int grid = (int)(tiles < (long long)sms * 2 ? tiles : (long long)sms * 2);
+    const int grid = (int)(tiles < (long long)sms[dev] ? tiles : (long long)sms[dev]);
     tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("tc_mlp_layer");
 }

@@ -26,7 +26,7 @@ from . import _lib, box_utils, tc
 from .head import RCNN, HeadConfig, affinity, affinity_batched
 from .iou3d import iou3d_cuda
 from .pointnet2 import pytorch_utils as pt_utils
-from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG, SAPlan
 
 
 @dataclass
@@ -205,6 +205,70 @@ class PointNet2MSG(nn.Module):
         fused = F.relu(self.image_fusion_bn(self.image_fusion_conv(de)))
         return maps, fused
 
+    overlap_geometry = True
+    l0_chunks = 4
+
+    def _geometry(self, xyz):
+        """FPS, ball query and three_nn depend on coordinates only, the MLP stacks on features only.  In eval mode the
+        coordinate chain of all levels (FPS0 -> FPS1 -> ..., the neighbour lists, the interpolation weights) runs on a
+        high-priority side stream, one event per level, and the feature chain on the caller's stream waits for the
+        level it needs: the narrow, latency-bound FPS kernels and the three_nn searches then overlap the tensor-core
+        work instead of stalling it.  Level 0 goes one step further: its FPS (4 096 dependent iterations on 64 SMs,
+        the longest kernel of the step) publishes indices as it goes, and the caller's stream consumes them in
+        `l0_chunks` prefixes behind `wait_indices` gates (see forward()).  Same kernels, same results."""
+        if not (self.overlap_geometry and not self.training and xyz.is_cuda):
+            return None, None
+        from .pointnet2 import pointnet2_cuda, pointnet2_utils
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_geo_stream", None)
+        if side is None or side.device != xyz.device:
+            side = self._geo_stream = torch.cuda.Stream(device=xyz.device, priority=-1)
+        side.wait_stream(main)
+        sa_plans, fp_plans = [], {}
+        with torch.cuda.stream(side):
+            xs = [xyz]
+            for li, sa in enumerate(self.SA_modules):
+                if li == 0 and self.l0_chunks > 1 and sa.npoint % self.l0_chunks == 0:
+                    B, N, _ = xyz.shape
+                    idx = torch.full((B, sa.npoint), -1, dtype=torch.int32, device=xyz.device)
+                    filled = torch.cuda.Event()     # the gates must not look at the buffer before it is reset
+                    filled.record(side)
+                    pointnet2_cuda.farthest_point_sampling_wrapper(B, N, sa.npoint, xyz, None, idx)
+                    new_xyz = pointnet2_utils.gather_operation(
+                        xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+                    p = SAPlan(idx, new_xyz, None)      # neighbour lists are built per chunk on the caller's stream
+                    p.filled = filled
+                else:
+                    p = sa.plan(xs[-1])
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for t in p.tensors():
+                    t.record_stream(main)
+                sa_plans.append((p, ev))
+                xs.append(p.new_xyz)
+            for i in range(-1, -(len(self.FP_modules) + 1), -1):
+                p = self.FP_modules[i].plan(xs[i - 1], xs[i])
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for t in p:
+                    t.record_stream(main)
+                fp_plans[i] = (p, ev)
+        return sa_plans, fp_plans
+
+    def _sa0_chunked(self, sa, xyz, features, plan):
+        """Level-0 set abstraction on prefixes of the FPS output while the sampler is still running."""
+        from .pointnet2 import pointnet2_cuda, pointnet2_utils
+        step = sa.npoint // self.l0_chunks
+        xyz_t = xyz.transpose(1, 2).contiguous()
+        outs = []
+        torch.cuda.current_stream().wait_event(plan.filled)
+        for k0 in range(0, sa.npoint, step):
+            pointnet2_cuda.wait_indices(plan.idx, k0, k0 + step)
+            idx_c = plan.idx[:, k0:k0 + step].contiguous()
+            ctr = pointnet2_utils.gather_operation(xyz_t, idx_c).transpose(1, 2).contiguous()
+            outs.append(sa(xyz, features, plan=sa.plan(xyz, ctr))[1])
+        return torch.cat(outs, dim=2)
+
     @torch.no_grad()
     def forward(self, pc, image=None, xy=None, image_maps=None):
         """image_maps = (maps, fused) from image_features() may be passed to skip the image stack."""
@@ -212,8 +276,20 @@ class PointNet2MSG(nn.Module):
         l_xyz, l_features, l_xy = [xyz], [features], [xy]
         if self.cfg.li_fusion and image_maps is None:
             image_maps = self.image_features(image)
+        sa_plans, fp_plans = self._geometry(xyz)
+        main = torch.cuda.current_stream()
         for i, sa in enumerate(self.SA_modules):
-            li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i])
+            if sa_plans is not None:
+                plan_i, ev = sa_plans[i]
+                if plan_i.nbr is None:     # level 0, consumed in prefixes while FPS runs
+                    li_features = self._sa0_chunked(sa, l_xyz[i], l_features[i], plan_i)
+                    main.wait_event(ev)
+                    li_xyz, li_index = plan_i.new_xyz, plan_i.idx
+                else:
+                    main.wait_event(ev)
+                    li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i], plan=plan_i)
+            else:
+                li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i])
             if self.cfg.li_fusion:
                 li_xy = torch.gather(l_xy[i], 1, li_index.long().unsqueeze(-1).repeat(1, 1, 2))
                 img_gather = feature_gather(image_maps[0][i], li_xy)
@@ -222,7 +298,12 @@ class PointNet2MSG(nn.Module):
             l_xyz.append(li_xyz)
             l_features.append(li_features)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):
-            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+            plan_i = None
+            if fp_plans is not None:
+                plan_i, ev = fp_plans[i]
+                main.wait_event(ev)
+            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i],
+                                                   plan=plan_i)
         if self.cfg.li_fusion:
             l_features[0] = self.final_fusion_img_point(l_features[0], feature_gather(image_maps[1], xy))
         return l_xyz[0], l_features[0]

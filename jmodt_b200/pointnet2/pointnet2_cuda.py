@@ -65,6 +65,15 @@ def farthest_point_sampling_wrapper(b, n, m, points, temp, idx):
     return 1
 
 
+def wait_indices(idx, k0, k1, timeout_ms=2000):
+    """Stream gate (no reference counterpart): returns in stream order once idx[:, k0:k1] >= 0 everywhere."""
+    _chk(idx)
+    st = _lib.stream_and_device(idx)
+    _lib.check(_lib.lib().jmb_wait_indices(idx.data_ptr(), idx.shape[0], idx.stride(0), k0, k1, timeout_ms, st),
+               "wait_indices")
+    return 1
+
+
 def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     _chk(unknown, known, dist2, idx)
     st = _lib.stream_and_device(unknown)

@@ -35,6 +35,18 @@ def pack_shared_mlp(mlp) -> list:
     return packed
 
 
+class SAPlan:
+    """Coordinate-only part of a set-abstraction layer: FPS indices (B, npoint) | None, centres (B, npoint, 3) | None,
+    one neighbour list (B, npoint, nsample) int32 per scale (None for GroupAll)."""
+    __slots__ = ("idx", "new_xyz", "nbr", "filled")
+
+    def __init__(self, idx, new_xyz, nbr):
+        self.idx, self.new_xyz, self.nbr = idx, new_xyz, nbr
+
+    def tensors(self):
+        return [t for t in (self.idx, self.new_xyz, *(self.nbr or ())) if t is not None]
+
+
 class _PointnetSAModuleBase(nn.Module):
     def __init__(self):
         super().__init__()
@@ -43,19 +55,44 @@ class _PointnetSAModuleBase(nn.Module):
         self.mlps = None
         self.pool_method = 'max_pool'
 
-    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None):
-        """
-        :param xyz: (B, N, 3), features: (B, C, N)
-        :return: new_xyz (B, npoint, 3), new_features (B, sum_k mlps[k][-1], npoint), idx (B, npoint) | None
-        """
+    def plan(self, xyz: torch.Tensor, new_xyz=None):
+        """Everything of the layer that depends on coordinates only — FPS indices, the sampled centres and the
+        ball-query neighbour lists (pointnet2_modules.py:36-50, pointnet2_utils.py:236-252).  A caller that knows
+        xyz early can run this on a side stream while the previous level's features are still being computed and
+        pass the result to forward(plan=...)."""
         idx = None
         if new_xyz is None and self.npoint is not None:
             idx = pointnet2_utils.farthest_point_sample(xyz, self.npoint)
             new_xyz = pointnet2_utils.gather_operation(
                 xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        nbr = [None] * len(self.groupers)
+        qg = [isinstance(g, pointnet2_utils.QueryAndGroup) for g in self.groupers]
+        if len(self.groupers) == 2 and all(qg):
+            ga, gb = self.groupers      # both scales of an MSG level query the same centres: one scan of the cloud
+            nbr[0], nbr[1] = pointnet2_utils.ball_query_msg2(ga.radius, ga.nsample, gb.radius, gb.nsample, xyz, new_xyz)
+        else:
+            for gi, g in enumerate(self.groupers):
+                if qg[gi]:
+                    nbr[gi] = pointnet2_utils.ball_query(g.radius, g.nsample, xyz, new_xyz)
+        return SAPlan(idx, new_xyz, nbr)
 
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None, plan=None):
+        """
+        :param xyz: (B, N, 3), features: (B, C, N)
+        :return: new_xyz (B, npoint, 3), new_features (B, sum_k mlps[k][-1], npoint), idx (B, npoint) | None
+        """
         if _use_fused(self) and self.pool_method == 'max_pool':
-            return new_xyz, self._forward_fused(xyz, features, new_xyz), idx
+            if plan is None:
+                plan = self.plan(xyz, new_xyz)
+            return plan.new_xyz, self._forward_fused(xyz, features, plan.new_xyz, plan.nbr), plan.idx
+
+        idx = None
+        if plan is not None:
+            idx, new_xyz = plan.idx, plan.new_xyz
+        elif new_xyz is None and self.npoint is not None:
+            idx = pointnet2_utils.farthest_point_sample(xyz, self.npoint)
+            new_xyz = pointnet2_utils.gather_operation(
+                xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
 
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
@@ -79,21 +116,15 @@ class _PointnetSAModuleBase(nn.Module):
         self._packed = [pack_shared_mlp(m) for m in self.mlps]
         return self._packed
 
-    def _forward_fused(self, xyz, features, new_xyz):
+    def _forward_fused(self, xyz, features, new_xyz, nbr):
         packed = getattr(self, "_packed", None) or self.pack()
         outs = []
         if features is not None:
             features = features.contiguous()
-        pre_idx = {}
-        if len(self.groupers) == 2 and all(isinstance(g, pointnet2_utils.QueryAndGroup) for g in self.groupers):
-            ga, gb = self.groupers      # both scales of an MSG level query the same centres: one scan of the cloud
-            pre_idx[0], pre_idx[1] = pointnet2_utils.ball_query_msg2(ga.radius, ga.nsample, gb.radius, gb.nsample,
-                                                                     xyz, new_xyz)
         for gi, (grouper, layers) in enumerate(zip(self.groupers, packed)):
             if isinstance(grouper, pointnet2_utils.QueryAndGroup):
                 assert grouper.use_xyz, "the fused path groups xyz with the features"
-                idx = pre_idx[gi] if gi in pre_idx else \
-                    pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+                idx = nbr[gi]
                 pool = grouper.nsample
                 if getattr(self, "fuse_chain", True) and features is not None and \
                         tc.sa_fused_supported(layers, features.shape[1], new_xyz.shape[1], grouper.nsample):
@@ -151,16 +182,23 @@ class PointnetFPModule(nn.Module):
         self._packed = None
         return super().train(mode)
 
+    @staticmethod
+    def plan(unknown: torch.Tensor, known: torch.Tensor):
+        """Coordinate-only part (pointnet2_modules.py:148-151): the three nearest known points of every unknown
+        point and their normalised inverse-distance weights."""
+        dist, idx = pointnet2_utils.three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+        return idx, weight
+
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
-                known_feats: torch.Tensor) -> torch.Tensor:
+                known_feats: torch.Tensor, plan=None) -> torch.Tensor:
         """
         :param unknown: (B, n, 3), known: (B, m, 3), unknow_feats: (B, C1, n), known_feats: (B, C2, m)
         :return: (B, mlp[-1], n)
         """
         if known is not None:
-            dist, idx = pointnet2_utils.three_nn(unknown, known)
-            dist_recip = 1.0 / (dist + 1e-8)
-            weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+            idx, weight = plan if plan is not None else self.plan(unknown, known)
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))

@@ -25,7 +25,7 @@ class Profiler:
     def reset(self):
         self.records, self.launches = [], 0
 
-    def launch(self, flops, fn, kind="tc_gemm_kernel"):
+    def launch(self, flops, fn, kind="tc_gemm_kernel", desc=""):
         self.launches += 1
         if not self.enabled:
             return fn()
@@ -33,13 +33,22 @@ class Profiler:
         e0.record()
         out = fn()
         e1.record()
-        self.records.append((flops, e0, e1, kind))
+        self.records.append((flops, e0, e1, kind, desc))
         return out
 
     def summary(self, kind=None):
         recs = [r for r in self.records if kind is None or r[3] == kind]
-        ms = sum(a.elapsed_time(b) for _, a, b, _ in recs)
+        ms = sum(r[1].elapsed_time(r[2]) for r in recs)
         return {"flops": float(sum(r[0] for r in recs)), "ms": float(ms), "launches": len(recs)}
+
+    def table(self, steps):
+        """Per-launch list of one step (averaged over `steps` identical steps): (desc, kind, flops, ms)."""
+        per = len(self.records) // max(1, steps)
+        rows = []
+        for i in range(per):
+            rs = [self.records[s * per + i] for s in range(steps)]
+            rows.append((rs[0][4], rs[0][3], rs[0][0], sum(r[1].elapsed_time(r[2]) for r in rs) / steps))
+        return rows
 
 
 profiler = Profiler()
@@ -103,7 +112,8 @@ def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None =
         profiler.launch(2.0 * layer.M * K * G * N, lambda: _lib.check(
             _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
                                         x.data_ptr(), K * N, N, None, None, None, 0, 0, 2, 0, int(layer.relu),
-                                        y.data_ptr(), 0, st), "tc_mlp_layer"))
+                                        y.data_ptr(), 0, st), "tc_mlp_layer"),
+            desc=f"dense M={layer.M} K={K} G={G} N={N} point-major-out")
         return y
     shape = (G, layer.M, N // pool) if pool else (G, layer.M, N)
     y = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
@@ -113,7 +123,8 @@ def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None =
     profiler.launch(2.0 * layer.M * K * G * N, lambda: _lib.check(
         _lib.lib().jmb_tc_mlp_layer(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, 0,
                                     x.data_ptr(), K * N, N, None, None, None, 0, 0,
-                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), y_gs, st), "tc_mlp_layer"))
+                                    1 if pool else 0, pool, int(layer.relu), y.data_ptr(), y_gs, st), "tc_mlp_layer"),
+        desc=f"dense M={layer.M} K={K} G={G} N={N} pool={pool}")
     return y
 
 
@@ -136,7 +147,7 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
                                     fx.data_ptr(), C * n_pts, n_pts, _lib.ptr(idx), xyz.data_ptr(),
                                     _lib.ptr(centres), nsample if centres is not None else 0, n_pts,
                                     1 if pool else 0, pool, int(layer.relu), y.data_ptr(), 0, st),
-        "tc_mlp_layer(grouped)"))
+        "tc_mlp_layer(grouped)"), desc=f"grouped M={layer.M} K={layer.K} G={G} N={N} ns={nsample} pool={pool}")
     return y
 
 
@@ -171,5 +182,6 @@ def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, 
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
                                 l3.wpack.data_ptr(), l3.bias.data_ptr(), C, l3.M, G, npoint, nsample, n_pts,
                                 feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
-                                out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel")
+                                out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel",
+        desc=f"sa_fused C={C} C3={l3.M} G={G} npoint={npoint} ns={nsample}")
     return out

@@ -195,3 +195,48 @@ def test_batched_proposal_layer_equals_reference_loop(cuda):
         assert torch.equal(scores_b, scores_l), case
         assert torch.equal(boxes_b, boxes_l), case
         assert (scores_b != 0).any()
+
+
+@pytest.mark.gpu
+def test_geometry_overlap_and_chunked_level0_are_bit_identical_to_serial(cuda):
+    """The side-stream coordinate chain and the gated, chunked level-0 set abstraction (detector.PointNet2MSG._geometry)
+    reorder launches only: features and coordinates must equal the single-stream run bit for bit, repeatedly (the index
+    buffer is recycled between calls, which is what the `filled` event protects)."""
+    from jmodt_b200.detector import PointNet2MSG, RpnConfig
+    from jmodt_b200.synth import fill_deterministic, make_batch
+    net = fill_deterministic(PointNet2MSG(input_channels=0, cfg=RpnConfig())).to(cuda).eval()
+    b = make_batch(70, 2)
+    xyz, xy, img = (torch.from_numpy(b[k]).to(cuda) for k in ("pts", "pts_xy", "img"))
+    maps = net.image_features(img)
+    net.overlap_geometry = False
+    want_xyz, want = net(xyz, None, xy, image_maps=maps)
+    net.overlap_geometry = True
+    for chunks in (4, 1, 8, 4):
+        net.l0_chunks = chunks
+        got_xyz, got = net(xyz, None, xy, image_maps=maps)
+        torch.cuda.synchronize()
+        assert torch.equal(got_xyz, want_xyz) and torch.equal(got, want), chunks
+
+
+@pytest.mark.gpu
+def test_wait_indices_gate_orders_a_consumer_behind_a_running_sampler(cuda):
+    """jmb_wait_indices: a copy queued behind the gate on stream B sees the complete prefix that FPS on stream A has
+    produced, for every prefix length."""
+    from jmodt_b200.pointnet2 import pointnet2_cuda, pointnet2_utils
+    from jmodt_b200.synth import make_batch
+    xyz = torch.from_numpy(make_batch(80, 4)["pts"]).to(cuda)
+    want = pointnet2_utils.farthest_point_sample(xyz, 4096)
+    a, bstream = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for k1 in (64, 1024, 4096):
+        with torch.cuda.stream(a):
+            idx = torch.full((4, 4096), -1, dtype=torch.int32, device=cuda)
+            filled = torch.cuda.Event()
+            filled.record(a)
+            pointnet2_cuda.farthest_point_sampling_wrapper(4, 16384, 4096, xyz, None, idx)
+        with torch.cuda.stream(bstream):
+            bstream.wait_event(filled)
+            pointnet2_cuda.wait_indices(idx, 0, k1)
+            seen = idx[:, :k1].clone()
+        torch.cuda.synchronize()
+        assert torch.equal(seen, want[:, :k1]), k1

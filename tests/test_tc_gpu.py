@@ -65,6 +65,60 @@ def test_maxpool_epilogue_and_grouped_prologue(cuda):
     _check(ga.double(), want_ga.clamp_min(0).view(G, M, n_pts // 128, 128).max(dim=3)[0])
 
 
+@pytest.mark.parametrize("G,K,N,M", [(5, 64, 32, 128), (1024, 70, 32, 200), (7, 259, 64, 256), (9, 40, 8, 64), (3, 96, 16, 128),
+                                     (2, 33, 130, 128), (3, 64, 1026, 96), (2, 48, 12, 16)])
+def test_narrow_groups_packed_into_one_tile_and_unaligned_rows(cuda, G, K, N, M):
+    """N < 128 dividing 128 packs 128/N groups per tile (bulk-copy paths), N % 4 != 0 takes the register / direct-store
+    paths; both against fp64, for the dense, pooled and point-major epilogues and for a channel-slice output."""
+    from jmodt_b200 import tc
+    g = torch.Generator(device="cpu").manual_seed(G * 7 + K * 1000 + N)
+    w = torch.randn(M, K, generator=g) / K ** 0.5
+    b = torch.randn(M, generator=g)
+    x = torch.randn(G, K, N, generator=g)
+    layer = tc.PackedLayer(w.to(cuda), b.to(cuda), True)
+    xd = x.to(cuda).contiguous()
+    want = (torch.einsum("mk,gkn->gmn", w.double(), x.double()) + b.double()[None, :, None]).clamp_min(0)
+    _check(tc.mlp_layer(layer, xd).cpu().double(), want)
+    _check(tc.mlp_layer(layer, xd, point_major_out=True).cpu().double(), want.transpose(1, 2))
+    wide = torch.full((G, M + 24, N), -7.0, device=cuda)
+    tc.mlp_layer(layer, xd, out=wide[:, 8:8 + M])
+    _check(wide[:, 8:8 + M].cpu().double(), want)
+    assert (wide[:, :8] == -7).all() and (wide[:, 8 + M:] == -7).all()
+    for pool in (8, 32, 64, 128):
+        if N % pool == 0:
+            _check(tc.mlp_layer(layer, xd, pool=pool).cpu().double(), want.view(G, M, N // pool, pool).max(dim=3)[0])
+
+
+def test_group_all_gather_with_packed_groups(cuda):
+    """GroupAll prologue (no idx, no centring) over 32 points per group: four groups share a tile."""
+    from jmodt_b200 import tc
+    g = torch.Generator(device="cpu").manual_seed(11)
+    G, n_pts, C, M = 37, 32, 256, 256
+    xyz = torch.rand(G, n_pts, 3, generator=g).to(cuda)
+    feats = torch.randn(G, C, n_pts, generator=g).to(cuda)
+    w = (torch.randn(M, 3 + C, generator=g) / 16).to(cuda)
+    b = torch.randn(M, generator=g).to(cuda)
+    layer = tc.PackedLayer(w, b, True)
+    want = (torch.einsum("mk,gkn->gmn", w.double(), torch.cat([xyz.transpose(1, 2), feats], 1).double())
+            + b.double()[None, :, None]).clamp_min(0)
+    _check(tc.grouped_first_layer(layer, xyz, feats, None, None, 0).double(), want)
+    _check(tc.grouped_first_layer(layer, xyz, feats, None, None, 0, pool=32).double(), want.max(dim=2, keepdim=True)[0])
+
+
+def test_many_launches_reuse_the_scheduler_slots(cuda):
+    """More launches than scheduler slots, alternating shapes: every launch must see a re-armed tile counter."""
+    from jmodt_b200 import tc
+    g = torch.Generator(device="cpu").manual_seed(3)
+    w = torch.randn(128, 64, generator=g) / 8
+    layer = tc.PackedLayer(w.to(cuda), None, False)
+    xs = [torch.randn(2, 64, n, generator=g).to(cuda) for n in (128, 4096, 640)]
+    wants = [torch.einsum("mk,gkn->gmn", w.double(), x.cpu().double()) for x in xs]
+    for i in range(200):
+        got = tc.mlp_layer(layer, xs[i % 3])
+        if i % 17 == 0 or i > 190:
+            _check(got.cpu().double(), wants[i % 3])
+
+
 @pytest.mark.parametrize("C,npoint,ns,C3", [(128, 128, 64, 128), (128, 32, 64, 256), (64, 64, 16, 128), (128, 16, 8, 256)])
 def test_sa_fused_single_kernel_matches_layerwise_and_torch(cuda, C, npoint, ns, C3):
     """The one-kernel set-abstraction layer vs (a) the layer-by-layer tcgen05 path and (b) torch fp32."""
