@@ -52,6 +52,8 @@ def parse():
                          "(BASELINE config 3); ops: the bare jmodt/ops suite (BASELINE config 2)")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="e2e workload: enqueue every kernel from Python each step instead of replaying the captured step")
     ap.add_argument("--dump-launches", default="", help="write the per-launch tcgen05 kernel table of one step here")
     return ap.parse_args()
 
@@ -93,19 +95,11 @@ class OpsSuite:
         from jmodt_b200.roipool3d import roipool3d_utils as ru
         self.torch, self.pu, self.ru, self.iou, self.iouc = torch, pu, ru, iou3d_utils, iou3d_cuda
         self.dev, self.frames = dev, frames
-        self.kernel_ms = {}
-        self.timing = False
+        from jmodt_b200.runtime import EventLog
+        self.log = EventLog()
 
     def _t(self, name, fn, launches=1):
-        if not self.timing:
-            return fn()
-        torch = self.torch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        self.kernel_ms.setdefault(name, []).append((e0, e1))
-        return out
+        return self.log.timed(name, fn)
 
     def step(self, d):
         torch, pu = self.torch, self.pu
@@ -179,20 +173,11 @@ class FusionE2E:
             maps, fused = self.model.rpn.backbone_net.image_features(img)
             self.image_maps = ([m.contiguous() for m in maps], fused.contiguous())
         del img
-        self.launches = 0
-        self.kernel_ms = {}
-        self.timing = False
+        from jmodt_b200.runtime import EventLog
+        self.log = EventLog()
 
     def _t(self, name, fn):
-        if not self.timing:
-            return fn()
-        torch = self.torch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        self.kernel_ms.setdefault(name, []).append((e0, e1))
-        return out
+        return self.log.timed(name, fn)
 
     def step(self, d):
         torch, m = self.torch, self.model
@@ -317,42 +302,76 @@ def run_b200(args):
     for _ in range(args.warmup):
         suite.step(d)
     barrier()
-    suite.timing = True
-    tc.profiler.reset()
-    tc.profiler.enabled = True
-    launches0 = _lib.launch_count
+    graph_mode = e2e_mode and not args.no_graph
+    evs = []
+    if graph_mode:
+        # The whole step (this library's kernels, the torch glue and the side-stream fork/join) is captured ONCE and
+        # replayed with one launch per step (jmodt_b200/runtime.py).  Two captures of the same step: `clean` is the one
+        # timed for `value` / `e2e`; `probe` additionally holds external CUDA-event nodes around every tcgen05 launch
+        # and every stage, and is replayed in its own loop for the roofline / stage numbers.
+        from jmodt_b200.runtime import CapturedPath
+        clean = CapturedPath(suite.step, d, warmup=1)
+        suite.log.reset(); tc.profiler.reset()
+        suite.log.enabled = tc.profiler.enabled = True
+        suite.log.external = tc.profiler.external = True
+        probe = CapturedPath(suite.step, d, warmup=0)
+        suite.log.enabled = tc.profiler.enabled = False
+        suite.log.external = tc.profiler.external = False
+        for _ in range(2):
+            clean.replay(); probe.replay()
+        run_step = clean.replay
+        launches_per_step = clean.launches_per_replay
+    else:
+        suite.log.reset(); tc.profiler.reset()
+        suite.log.enabled = tc.profiler.enabled = True
+        run_step = lambda: suite.step(d)
+        launches0 = _lib.launch_count
     sampler = ClockSampler(local)
     sampler.start()
-    evs = []
     barrier()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()                                    # L2 flush, outside the per-step event pair
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        suite.step(d)
+        run_step()
         e1.record()
         evs.append((e0, e1))
     barrier()
     wall_s = time.perf_counter() - t_wall
-    clocks = sampler.stop()
-    launches = _lib.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
-    kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in suite.kernel_ms.items()}
-    kernel_calls = {k: len(v) / args.steps for k, v in suite.kernel_ms.items()}
+    if graph_mode:
+        n_probe = args.steps
+        for _ in range(n_probe):                         # same step, same flush, with the event nodes
+            flush.zero_()
+            probe.replay()
+            torch.cuda.synchronize()
+            suite.log.collect(); tc.profiler.collect()
+        launches = launches_per_step * args.steps
+    else:
+        n_probe = args.steps
+        suite.log.collect_pending(); tc.profiler.collect_pending()
+        suite.log.enabled = tc.profiler.enabled = False
+        launches = _lib.launch_count - launches0
+    clocks = sampler.stop()
+    names = list(dict.fromkeys(r.name for r in suite.log.records))
+    stage = {k: suite.log.summary(name=k) for k in names}
+    kernel_ms = {k: v["ms"] / max(1, v["launches"]) for k, v in stage.items()}
+    kernel_calls = {k: v["launches"] / n_probe for k, v in stage.items()}
     tc_sum = tc.profiler.summary()
     if args.dump_launches and rank == 0:
         with open(args.dump_launches, "w") as f:
-            for desc, kind, flops, ms in tc.profiler.table(args.steps):
+            for desc, kind, flops, ms in tc.profiler.table():
                 f.write(f"{ms * 1e3:9.1f} us  {flops / (ms * 1e-3) / 1e12 if ms > 0 else 0:7.1f} TF/s  {kind:16s} {desc}\n")
-    tc.profiler.enabled = False
-    suite.timing = False
 
     # ---- e2e: same work through the public API with HOST (pinned) inputs and a host read of the results
     def e2e_step():
-        dd = upload(host, dev, torch)
-        out = suite.step(dd)
+        if graph_mode:
+            clean.load(host)                              # H2D from pinned memory into the graph's input buffers
+            out = clean.replay()
+        else:
+            out = suite.step(upload(host, dev, torch))
         if e2e_mode:
             keys = ("rcnn_cls", "rcnn_reg", "proposals", "empty", "link", "start", "end")
             return [out[k].cpu() for k in keys]
@@ -400,12 +419,12 @@ def run_b200(args):
                         if peaks else "fallback 1590 TFLOP/s",
                         "algorithmic_flops_per_launch": sa_sum["flops"] / max(1, sa_sum["launches"]),
                         "kernel_ms_per_launch": sa_sum["ms"] / max(1, sa_sum["launches"]),
-                        "launches_per_step": sa_sum["launches"] / args.steps,
-                        "share_of_step": sa_sum["ms"] / total_ms if total_ms else None,
+                        "launches_per_step": sa_sum["launches"] / n_probe,
+                        "share_of_step": sa_sum["ms"] / n_probe / ms_per_step,
                         "issued_bf16_tflops": 3 * achieved, "issued_frac": 3 * achieved / tf_peak,
-                        "all_tensor_kernels": {"achieved": ach(tc_sum), "ms_per_step": tc_sum["ms"] / args.steps,
-                                               "launches_per_step": tc_sum["launches"] / args.steps,
-                                               "share_of_step": tc_sum["ms"] / total_ms if total_ms else None},
+                        "all_tensor_kernels": {"achieved": ach(tc_sum), "ms_per_step": tc_sum["ms"] / n_probe,
+                                               "launches_per_step": tc_sum["launches"] / n_probe,
+                                               "share_of_step": tc_sum["ms"] / n_probe / ms_per_step},
                         "note": "fp32-grade result = 3 bf16 MMAs per product (W_hi.X_hi + W_lo.X_hi + W_hi.X_lo)"}
             workload = ("end-to-end region-proposal fusion + link/start-end affinity (BASELINE config 3): RPN point path "
                         "with LI-Fusion on precomputed image maps, proposal layer, roipool3d+canonical, per-proposal "
@@ -430,7 +449,11 @@ def run_b200(args):
                        "frames_per_gpu_per_step": B, "points_per_frame": N_PTS, "rois_per_frame": N_ROI,
                        "weights": "random (name-hashed) init of the reference architecture",
                        "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event pair)",
-                       "timing": "sum of per-step CUDA-event pairs on torch's current stream (the launching stream)"},
+                       "timing": "sum of per-step CUDA-event pairs on torch's current stream (the launching stream)",
+                       "launch": ("one CUDA-graph replay per step (the step captured once: jmodt_b200/runtime.py); "
+                                  "per-kernel / per-stage times from a second capture of the same step carrying "
+                                  "external event nodes, replayed after the timed region") if graph_mode
+                                 else "every kernel enqueued from Python each step; per-kernel event pairs inline"},
             "e2e": {"value": proposals_per_step / (e2e_ms * 1e-3), "unit": "proposals/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches,

@@ -371,7 +371,7 @@ def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bi
                                ry_bin.unsqueeze(1)).squeeze(1)
     angle_per_class = (2 * np.pi) / num_head_bin
     ry = (ry_bin.float() * angle_per_class + ry_res_norm * (angle_per_class / 2)) % (2 * np.pi)
-    ry[ry > np.pi] -= 2 * np.pi
+    ry = torch.where(ry > np.pi, ry - 2 * np.pi, ry)       # `ry[ry > pi] -= 2*pi` without the nonzero() host sync
     size_l = start + 2 * num_head_bin
     size_res_norm = pred_reg[:, size_l:size_l + 3]
     hwl = size_res_norm * anchor_size + anchor_size
@@ -382,7 +382,8 @@ def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bi
         roi_ry = roi_box3d[:, 6]
         ret = box_utils.rotate_pc_along_y_torch(shift_ret.unsqueeze(1), -roi_ry).squeeze(1)
         ret[:, 6] += roi_ry
-    ret[:, [0, 2]] += roi_center[:, [0, 2]]
+    ret[:, 0] += roi_center[:, 0]          # `ret[:, [0, 2]] += roi_center[:, [0, 2]]` without host-built index tensors
+    ret[:, 2] += roi_center[:, 2]
     return ret
 
 
@@ -393,12 +394,15 @@ class ProposalLayer(nn.Module):
         super().__init__()
         self.mode, self.cfg = mode, cfg or RpnConfig()
         self.batched = True       # False: the reference's per-frame / per-bin loop (same results, host syncs)
+        self._mean_size = {}
 
     @torch.no_grad()
     def forward(self, rpn_scores, rpn_reg, xyz):
         cfg = self.cfg
         B = xyz.shape[0]
-        mean_size = torch.tensor(cfg.mean_size, dtype=torch.float32, device=xyz.device)
+        mean_size = self._mean_size.get(xyz.device)
+        if mean_size is None:       # built once per device: a pageable H2D copy per call would also break graph capture
+            mean_size = self._mean_size[xyz.device] = torch.tensor(cfg.mean_size, dtype=torch.float32, device=xyz.device)
         proposals = decode_bbox_target(xyz.view(-1, 3), rpn_reg.view(-1, rpn_reg.shape[-1]), cfg.loc_scope,
                                        cfg.loc_bin_size, cfg.num_head_bin, mean_size)
         proposals[:, 1] += proposals[:, 3] / 2

@@ -1,0 +1,106 @@
+"""Stream / CUDA-graph runtime around the hot path (no reference counterpart: the reference launches ≈150 kernels
+per frame one by one on the legacy default stream, `tools/eval.py:55-107`).
+
+`CapturedPath` records ONE invocation of a step function — every kernel of this library, the torch glue between them
+and the fork/join of the coordinate side stream (detector.PointNet2MSG._geometry) — into a CUDA graph over static
+buffers, and replays it with a single launch.  The step of BASELINE config 3 is ≈350 device activities; replaying
+it as a graph takes the Python / ctypes enqueue cost (≈10 ms of host time per step) off the critical path.
+
+`TimedRecord` / `EventLog` are the CUDA-event bookkeeping bench.py uses to time individual launches; inside a
+captured graph the events are *external* event-record nodes, so they are re-recorded by every replay.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import torch
+
+from . import _lib
+
+
+class TimedRecord:
+    __slots__ = ("name", "flops", "kind", "desc", "e0", "e1", "ms")
+
+    def __init__(self, name, flops, kind, desc, e0, e1):
+        self.name, self.flops, self.kind, self.desc, self.e0, self.e1, self.ms = name, flops, kind, desc, e0, e1, []
+
+    def collect(self):
+        """Read the pair's elapsed time (call after a synchronize; once per replay for graph-resident pairs)."""
+        self.ms.append(self.e0.elapsed_time(self.e1))
+
+
+class EventLog:
+    """CUDA-event pairs on the launching stream.  `external=True` while a graph is being captured."""
+
+    def __init__(self):
+        self.enabled = False
+        self.external = False
+        self.records = []
+        self.launches = 0
+
+    def reset(self):
+        self.records, self.launches = [], 0
+
+    def timed(self, name, fn, flops=0.0, kind="", desc=""):
+        self.launches += 1
+        if not self.enabled:
+            return fn()
+        e0 = torch.cuda.Event(enable_timing=True, external=self.external)
+        e1 = torch.cuda.Event(enable_timing=True, external=self.external)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.records.append(TimedRecord(name, flops, kind, desc, e0, e1))
+        return out
+
+    def collect(self):
+        for r in self.records:
+            r.collect()
+
+    def collect_pending(self):
+        """Eager mode: every record is one launch; read those not read yet."""
+        for r in self.records:
+            if not r.ms:
+                r.collect()
+
+    def summary(self, kind=None, name=None):
+        recs = [r for r in self.records if (kind is None or r.kind == kind) and (name is None or r.name == name)]
+        return {"flops": float(sum(r.flops * len(r.ms) for r in recs)), "ms": float(sum(sum(r.ms) for r in recs)),
+                "launches": int(sum(len(r.ms) for r in recs))}
+
+
+class CapturedPath:
+    """fn(inputs) -> dict of tensors, captured once and replayed as one CUDA graph.
+
+    `inputs` is a dict of device tensors that become the graph's static input buffers: `load()` copies new data into
+    them (from pinned host memory or device tensors) in stream order, `replay()` launches the graph and returns the
+    static output tensors (overwritten by the next replay).  fn must be free of host synchronisation, and must have
+    been called at least once before (lazy initialisation — weight packing, cudaFuncSetAttribute, stream creation —
+    cannot happen during capture)."""
+
+    def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], Dict[str, torch.Tensor]],
+                 inputs: Dict[str, torch.Tensor], warmup: int = 2):
+        assert all(t.is_cuda for t in inputs.values()), "static inputs live on the device"
+        self.inputs = inputs
+        self.fn = fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.outputs = fn(inputs)
+        self.launches_per_replay = _lib.launch_count - n0     # this library's kernels inside one replay
+        torch.cuda.synchronize()
+
+    def load(self, src: Dict[str, torch.Tensor], non_blocking: bool = True):
+        for k, t in self.inputs.items():
+            t.copy_(src[k], non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

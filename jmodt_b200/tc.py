@@ -9,46 +9,22 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .runtime import EventLog
 
 BM, BK = 128, 32
 
 
-class Profiler:
+class Profiler(EventLog):
     """Optional per-launch accounting for bench.py: algorithmic FLOPs (2*M*K*columns, unpadded) and a CUDA-event
-    pair per launch on the launching stream."""
-
-    def __init__(self):
-        self.enabled = False
-        self.records = []          # (flops, start_event, end_event)
-        self.launches = 0
-
-    def reset(self):
-        self.records, self.launches = [], 0
+    pair per launch on the launching stream (runtime.EventLog; graph-resident when a capture is in progress)."""
 
     def launch(self, flops, fn, kind="tc_gemm_kernel", desc=""):
-        self.launches += 1
-        if not self.enabled:
-            return fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        self.records.append((flops, e0, e1, kind, desc))
-        return out
+        return self.timed(kind, fn, flops=flops, kind=kind, desc=desc)
 
-    def summary(self, kind=None):
-        recs = [r for r in self.records if kind is None or r[3] == kind]
-        ms = sum(r[1].elapsed_time(r[2]) for r in recs)
-        return {"flops": float(sum(r[0] for r in recs)), "ms": float(ms), "launches": len(recs)}
-
-    def table(self, steps):
-        """Per-launch list of one step (averaged over `steps` identical steps): (desc, kind, flops, ms)."""
-        per = len(self.records) // max(1, steps)
-        rows = []
-        for i in range(per):
-            rs = [self.records[s * per + i] for s in range(steps)]
-            rows.append((rs[0][4], rs[0][3], rs[0][0], sum(r[1].elapsed_time(r[2]) for r in rs) / steps))
-        return rows
+    def table(self):
+        """Per-launch list of one step: (desc, kind, flops, mean ms).  Graph mode: one record per launch site;
+        eager mode: the records of the first recorded step."""
+        return [(r.desc, r.kind, r.flops, sum(r.ms) / max(1, len(r.ms))) for r in self.records]
 
 
 profiler = Profiler()
