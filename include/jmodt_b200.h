@@ -126,6 +126,14 @@ JMB_API int jmb_roipool3d_canonical(int batch, int pts_num, int boxes_num, int f
                             const float *pts_feature, float *pooled_features,
                             int *pooled_empty_flag, void *stream);
 
+/* jmb_roipool3d_canonical writing the "head layout" consumed by jmb_rcnn_input_fused: a pooled row is
+ * [feature lead..feat_len-1 | x, y, z | feature 0..lead-1 | zero padding], pitch round_up(3+feat_len, 8) floats
+ * (lead = 2 for the reference's [mask, depth, 128 channels] feature vector, proposal_target_layer.py:17-34). */
+JMB_API int jmb_roipool3d_canonical_head(int batch, int pts_num, int boxes_num, int feat_len, int sampled,
+                                 float pool_extra_width, int lead, const float *xyz, const float *boxes3d,
+                                 const float *pts_feature, float *pooled_features,
+                                 int *pooled_empty_flag, void *stream);
+
 /* ---- iou3d (jmodt/ops/iou3d/src/iou3d.cpp:170-175) --------------------------------------- */
 
 /* replaces boxes_overlap_bev_gpu (iou3d.cpp:31-50) -> iou3d_kernel.cu:223-234,355-365.
@@ -193,6 +201,14 @@ JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const 
                          const float *b3, int C_in, int C3, int G, int npoint, int nsample, int n_pts,
                          const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                          int out_point_major, void *stream);
+
+/* Input stage of the per-proposal network (reference rcnn.py:172-186: xyz_up_layer 5->128->128, cat with the 128
+ * RPN channels, merge_down_layer 256->128) in ONE kernel over consecutive rows of the pooled tensor in the
+ * "head layout" written by jmb_roipool3d_canonical_head: in (rows, 136) = [128 channels | x,y,z,mask,depth | 0,0,0]
+ * -> out (rows, 128) point-major.  w1 is the packed 128 x 8 first layer, w2 128 x 128, w3 128 x 256. */
+JMB_API int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
+                                 const float *b3, long long rows, int row_pitch, const float *in, float *out,
+                                 void *stream);
 
 /* ---- proposal layer ---------------------------------------------------------------------- */
 

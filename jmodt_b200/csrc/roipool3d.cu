@@ -39,9 +39,13 @@ struct BoxTest {
 // CANON: also apply the eval-branch canonical transform of
 // proposal_target_layer.py:107-112 (centre on the roi, rotate by ry about y), with the box
 // enlarged in-kernel as kitti_utils.enlarge_box3d (kitti_utils.py:152-162) does.
+// lead > 0 selects the "head layout" consumed by jmb_rcnn_input_fused: a row is
+//   [feature lead .. feat_len-1 | x, y, z | feature 0 .. lead-1 | zero padding]  with pitch round_up(3 + feat_len, 8)
+// i.e. the 128 RPN channels first (one 16-byte aligned block) and the 5 inputs of xyz_up_layer (rcnn.py:172-180:
+// xyz, seg mask, depth) behind them.  lead == 0 is the reference layout [x, y, z | features], pitch 3 + feat_len.
 template <bool CANON>
 __global__ void __launch_bounds__(RP_THREADS)
-roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float extra,
+roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float extra, int lead,
                  const float *__restrict__ xyz, const float *__restrict__ boxes3d,
                  const float *__restrict__ pts_feature, float *__restrict__ pooled,
                  int *__restrict__ empty_flag) {
@@ -103,7 +107,8 @@ roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float ex
         if (my_off + i < sampled) s_final[my_off + i] = mine[i];
     __syncthreads();
 
-    const int row = 3 + feat_len;
+    const int row = lead > 0 ? ((3 + feat_len + 7) / 8) * 8 : 3 + feat_len;
+    const int xoff = lead > 0 ? feat_len - lead : 0;      // column of x inside a row
     float *dst_box = pooled + ((size_t)b * boxes_num + box) * (size_t)sampled * row;
     if (threadIdx.x == 0) empty_flag[(size_t)b * boxes_num + box] = (have == 0) ? 1 : 0;
 
@@ -124,7 +129,7 @@ roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float ex
         const size_t nflt = (size_t)sampled * row;
         for (size_t e = threadIdx.x; e < nflt; e += RP_THREADS) {
             const int j = (int)(e % row);
-            dst_box[e] = j == 0 ? zx : (j == 1 ? zy : (j == 2 ? zz : 0.f));
+            dst_box[e] = j == xoff ? zx : (j == xoff + 1 ? zy : (j == xoff + 2 ? zz : 0.f));
         }
         return;
     }
@@ -145,13 +150,18 @@ roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float ex
                 else if (lane == 1) v = v - oy;
                 else v = __fmaf_rn(tz, rc, __fmul_rn(tx, rs));
             }
-            dst[lane] = v;
+            dst[xoff + lane] = v;
         }
-        for (int j = lane; j < feat_len; j += 32) dst[3 + j] = __ldg(f + j);
+        if (lead > 0) {
+            for (int j = lane; j < xoff; j += 32) dst[j] = __ldg(f + lead + j);
+            for (int j = lane; j < row - xoff - 3; j += 32) dst[xoff + 3 + j] = j < lead ? __ldg(f + j) : 0.f;
+        } else {
+            for (int j = lane; j < feat_len; j += 32) dst[3 + j] = __ldg(f + j);
+        }
     }
 }
 
-static int launch_roipool(bool canon, int batch, int pts_num, int boxes_num, int feat_len,
+static int launch_roipool(bool canon, int lead, int batch, int pts_num, int boxes_num, int feat_len,
                           int sampled, float extra, const float *xyz, const float *boxes3d,
                           const float *pts_feature, float *pooled, int *empty_flag, void *stream) {
     JMB_REQUIRE(batch >= 0 && pts_num >= 0 && boxes_num >= 0 && feat_len >= 0 && sampled >= 0,
@@ -168,7 +178,8 @@ static int launch_roipool(bool canon, int batch, int pts_num, int boxes_num, int
     if (smem > 48 * 1024)
         JMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(boxes_num, batch);
-    kern<<<grid, RP_THREADS, smem, (cudaStream_t)stream>>>(pts_num, boxes_num, feat_len, sampled, extra,
+    JMB_REQUIRE(lead >= 0 && lead <= feat_len, "roipool3d: bad head-layout split %d", lead);
+    kern<<<grid, RP_THREADS, smem, (cudaStream_t)stream>>>(pts_num, boxes_num, feat_len, sampled, extra, lead,
                                                           xyz, boxes3d, pts_feature, pooled, empty_flag);
     return check_launch("roipool3d");
 }
@@ -178,7 +189,7 @@ static int launch_roipool(bool canon, int batch, int pts_num, int boxes_num, int
 extern "C" int jmb_roipool3d(int batch, int pts_num, int boxes_num, int feat_len, int sampled,
                              const float *xyz, const float *boxes3d, const float *pts_feature,
                              float *pooled_features, int *pooled_empty_flag, void *stream) {
-    return jmb::launch_roipool(false, batch, pts_num, boxes_num, feat_len, sampled, 0.f, xyz, boxes3d,
+    return jmb::launch_roipool(false, 0, batch, pts_num, boxes_num, feat_len, sampled, 0.f, xyz, boxes3d,
                                pts_feature, pooled_features, pooled_empty_flag, stream);
 }
 
@@ -186,6 +197,17 @@ extern "C" int jmb_roipool3d_canonical(int batch, int pts_num, int boxes_num, in
                                        int sampled, float pool_extra_width, const float *xyz,
                                        const float *boxes3d, const float *pts_feature,
                                        float *pooled_features, int *pooled_empty_flag, void *stream) {
-    return jmb::launch_roipool(true, batch, pts_num, boxes_num, feat_len, sampled, pool_extra_width,
+    return jmb::launch_roipool(true, 0, batch, pts_num, boxes_num, feat_len, sampled, pool_extra_width,
+                               xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, stream);
+}
+
+// jmb_roipool3d_canonical writing the head layout (see roipool3d_kernel): pooled_features is
+// (B, M, sampled, round_up(3 + feat_len, 8)) with the first `lead` feature columns moved behind xyz.
+extern "C" int jmb_roipool3d_canonical_head(int batch, int pts_num, int boxes_num, int feat_len,
+                                            int sampled, float pool_extra_width, int lead, const float *xyz,
+                                            const float *boxes3d, const float *pts_feature,
+                                            float *pooled_features, int *pooled_empty_flag, void *stream) {
+    JMB_REQUIRE(lead > 0, "roipool3d_canonical_head: lead must be positive");
+    return jmb::launch_roipool(true, lead, batch, pts_num, boxes_num, feat_len, sampled, pool_extra_width,
                                xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, stream);
 }

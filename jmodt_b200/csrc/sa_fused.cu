@@ -59,6 +59,9 @@ struct SaFusedParams {
     const float *centres;  // (G, npoint, 3)
     float *out;            // (G, 128*Mt3, npoint), or (G, npoint, 128*Mt3) if out_point_major
     int out_point_major;
+    int w3_blocks;         // 128 x 128 blocks of W3 resident in tensor memory (SA: Mt3 row blocks; ROWS: 2 K blocks)
+    long long rows;        // ROWS mode: number of input rows (points), a multiple of 128
+    int row_pitch;         // ROWS mode: floats per input row (multiple of 4; 128 channels, then <= 8 extra inputs)
     long long *dbg;        // optional timeline buffer (profiling aid): CTA 0 writes clock64() stamps
 };
 
@@ -74,6 +77,13 @@ __device__ __forceinline__ void umma_ts64(uint32_t d_tmem, uint32_t a_tmem, uint
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(SF_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts64_kmajor(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(SF_IDESC_L1), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -108,6 +118,14 @@ __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_b
     }
 }
 
+// ROWS = false: set abstraction (gather through idx, three layers, max-pool over nsample).
+// ROWS = true : the input stage of the per-proposal network (reference rcnn.py:172-186: xyz_up_layer 5 -> 128 -> 128,
+//   cat with the 128 RPN channels, merge_down_layer 256 -> 128) on consecutive rows [128 channels | up to 8 extra
+//   inputs] of pitch `row_pitch`: layer 1 reads only the extra inputs (k-groups 16, 17 of the row image), layer 3 is
+//   W3[:, 0:128] . act2 + W3[:, 128:256] . channels (both A blocks in tensor memory, the second with the K-major row
+//   image as B), and every column is written point-major (rows, 128) — no pooling.  The (G, 256, 512) concat, both
+//   transposes of the pooled tensor and two activation round trips of the unfused path disappear.
+template <bool ROWS>
 __global__ void __launch_bounds__(SF_THREADS, 1)
 sa_fused_kernel(const SaFusedParams p) {
     extern __shared__ __align__(1024) uint8_t sf_smem[];
@@ -157,7 +175,7 @@ sa_fused_kernel(const SaFusedParams p) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
         weight_rows_to_tmem(p.w2, 0, m, lane_base + SF_TMEM_W2);
         weight_rows_to_tmem(p.w2, 1, m, lane_base + SF_TMEM_W2 + 64);
-        for (int mt = 0; mt < p.Mt3; ++mt) {
+        for (int mt = 0; mt < p.w3_blocks; ++mt) {
             const __nv_bfloat16 *blk = p.w3 + (size_t)mt * 4 * (SF_CHUNK / 2);
             weight_rows_to_tmem(blk, 0, m, lane_base + SF_TMEM_W3 + mt * 128);
             weight_rows_to_tmem(blk, 1, m, lane_base + SF_TMEM_W3 + mt * 128 + 64);
@@ -168,9 +186,9 @@ sa_fused_kernel(const SaFusedParams p) {
     __syncthreads();
     tc_fence_after();
 
-    const int N = p.npoint * p.nsample;
+    const int N = ROWS ? TC_BN : p.npoint * p.nsample;
     const int Nt = N / TC_BN;
-    const long long total_tiles = (long long)p.G * Nt;
+    const long long total_tiles = ROWS ? p.rows / TC_BN : (long long)p.G * Nt;
     const int kmax16 = ((p.K1 + 15) / 16) * 16;  // rows the layer-1 MMAs actually read
 
     if (warp < SF_EPI_WARPS) {
@@ -245,6 +263,17 @@ sa_fused_kernel(const SaFusedParams p) {
             }
         };
 
+        // ROWS: every column is an output row; a warp's 32 channels of one column are one 128-byte store
+        auto epilogue_rows = [&](long long tile) {
+            const float bias = __ldg(p.b3 + m);
+            const int c0 = sblk * 32;
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            float *dst = p.out + ((size_t)tile * TC_BN + h * SF_HALF + c0) * TC_BM + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+        };
+
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
         int di = 0;
 #define SF_ESTAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
@@ -264,7 +293,8 @@ sa_fused_kernel(const SaFusedParams p) {
             for (int mt = 0; mt < p.Mt3; ++mt) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
-                if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools the whole 64-column half
+                if (ROWS) epilogue_rows(tile);
+                else if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools the whole 64-column half
                 tc_fence_before();
                 mbar_arrive(&s_epi_done[h]);
             }
@@ -273,7 +303,7 @@ sa_fused_kernel(const SaFusedParams p) {
         // ====================================== gather warps ======================================
         const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
         const int h = tg >> 6, nl = tg & 63;
-        const int n_groups = p.C / 8;                 // feature k-groups; group n_groups holds (dx, dy, dz, 0...)
+        const int n_groups = ROWS ? p.row_pitch / 8 : p.C / 8;   // feature k-groups; SA: group n_groups holds (dx, dy, dz, 0...)
         // One thread = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
         // channels in flight), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
         // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots: conflict-free).
@@ -281,8 +311,9 @@ sa_fused_kernel(const SaFusedParams p) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
             const int n = nt * TC_BN + h * SF_HALF + nl;
-            const int pi = __ldg(p.idx + (size_t)g * N + n);
-            const float *frow = p.feats + ((size_t)g * p.n_pts + pi) * p.C;
+            const int pi = ROWS ? 0 : __ldg(p.idx + (size_t)g * N + n);
+            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + h * SF_HALF + nl) * p.row_pitch
+                                     : p.feats + ((size_t)g * p.n_pts + pi) * p.C;
             const uint32_t noff = (uint32_t)(h * 8 + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
             auto put = [&](int kg, const float (&v)[8]) {
                 uint4 hh, ll;
@@ -294,7 +325,7 @@ sa_fused_kernel(const SaFusedParams p) {
                 *reinterpret_cast<uint4 *>(img) = hh;
                 *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
             };
-            {   // relative coordinates: k-group n_groups
+            if (!ROWS) {   // relative coordinates: k-group n_groups
                 const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
                 const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
                 float v[8] = {__fsub_rn(__ldg(pt), __ldg(cen)), __fsub_rn(__ldg(pt + 1), __ldg(cen + 1)),
@@ -322,7 +353,18 @@ sa_fused_kernel(const SaFusedParams p) {
 
         uint32_t tile_ctr = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            if (tile_ctr > 0) mbar_wait(&s_x1_free[h], (tile_ctr - 1) & 1);   // layer-1 MMAs of the previous tile have read this half
+            if (ROWS && nl == 0) {
+                // the rows of this CTA's next two tiles are contiguous: pull this half's share into L2 ahead of the
+                // gather, whose 64 threads alone cannot keep enough HBM requests in flight
+                const uint32_t bytes = (uint32_t)(SF_HALF * p.row_pitch * 4);
+                for (int a = (tile_ctr == 0 ? 1 : 2); a <= 2; ++a) {
+                    const long long t2 = tile + (long long)a * gridDim.x;
+                    if (t2 < total_tiles)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                                         p.feats + ((size_t)t2 * TC_BN + h * SF_HALF) * p.row_pitch), "r"(bytes) : "memory");
+                }
+            }
+            if (tile_ctr > 0) mbar_wait(&s_x1_free[h], (tile_ctr - 1) & 1);   // the MMAs that read this half of the previous tile are done
             produce_x1(tile);
         }
     } else {
@@ -358,7 +400,13 @@ sa_fused_kernel(const SaFusedParams p) {
                 mbar_wait(&s_x1_full[h], tile_ctr & 1);
                 tc_fence_after();
                 SF_STAMP(3);
-                for (int c = 0; c < p.Kc1; ++c) {
+                if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
+                    const uint64_t xd = x1_desc + 4 * D_CHUNK;
+                    umma_ss64(acc, w1_desc, xd, 0);
+                    umma_ss64(acc, w1_desc + D_IMG, xd, 1);
+                    umma_ss64(acc, w1_desc, xd + D_IMG, 1);
+                }
+                for (int c = 0; !ROWS && c < p.Kc1; ++c) {
                     const int steps = c == p.Kc1 - 1 ? last_steps : 2;
                     const uint64_t wd = w1_desc + (uint64_t)c * D_CHUNK, xd = x1_desc + (uint64_t)c * D_CHUNK;
                     umma_ss64(acc, wd, xd, c != 0);
@@ -370,7 +418,7 @@ sa_fused_kernel(const SaFusedParams p) {
                         umma_ss64(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
                     }
                 }
-                umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
+                if (!ROWS) umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
                 umma_commit(&s_acc_full[h]);
                 SF_STAMP(4);
                 // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
@@ -385,6 +433,17 @@ sa_fused_kernel(const SaFusedParams p) {
                         umma_ts64(acc, ahi, xd, k16 != 0);
                         umma_ts64(acc, ahi + 64, xd, 1);
                         umma_ts64(acc, ahi, xd + D_IMG, 1);
+                    }
+                    if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
+#pragma unroll
+                        for (int k16 = 0; k16 < 8; ++k16) {
+                            const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                            const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
+                            umma_ts64_kmajor(acc, ahi, xd, 1);
+                            umma_ts64_kmajor(acc, ahi + 64, xd, 1);
+                            umma_ts64_kmajor(acc, ahi, xd + D_IMG, 1);
+                        }
+                        umma_commit(&s_x1_free[h]);
                     }
                     umma_commit(&s_acc_full[h]);
                     SF_STAMP(8 + l);
@@ -428,6 +487,7 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
     p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM; p.C = C;
+    p.w3_blocks = p.Mt3; p.rows = 0; p.row_pitch = 0;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
     p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
     static int sms = 0;
@@ -435,11 +495,11 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         int dev = 0;
         JMB_CUDA(cudaGetDevice(&dev));
         JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     }
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    sa_fused_kernel<<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    sa_fused_kernel<false><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
     if (dbg_on) {
         long long hbuf[1024];
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -453,4 +513,37 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         cudaMemset(dbg_buf, 0, 1024 * sizeof(long long));
     }
     return check_launch("sa_fused");
+}
+
+// Input stage of the per-proposal network in one kernel (reference rcnn.py:172-186):
+//   in  (rows, row_pitch) fp32: [128 RPN channels | x, y, z, mask, depth | zero padding]  (roipool3d "head layout")
+//   out (rows, 128) fp32 point-major = merge_down( cat( xyz_up(extra inputs), channels ) )
+// w1: 128 x 8 (extra inputs, zero padded), w2: 128 x 128, w3: 128 x 256, all packed as tc.PackedLayer images.
+extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
+                                    const float *b3, long long rows, int row_pitch, const float *in, float *out,
+                                    void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(rows >= 0, "rcnn_input_fused: negative size");
+    if (rows == 0) return JMB_OK;
+    JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && in && out, "rcnn_input_fused: null pointer");
+    JMB_REQUIRE(rows % TC_BN == 0, "rcnn_input_fused: rows = %lld must be a multiple of 128", rows);
+    JMB_REQUIRE(row_pitch == 136, "rcnn_input_fused: row pitch %d (expected 128 channels + 8 extra inputs)", row_pitch);
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15u) == 0, "rcnn_input_fused: input must be 16-byte aligned");
+    SaFusedParams p = {};
+    p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
+    p.b1 = b1; p.b2 = b2; p.b3 = b3;
+    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C = 128; p.w3_blocks = 2;
+    p.G = 1; p.npoint = 1; p.nsample = TC_BN; p.n_pts = 0;
+    p.feats = in; p.out = out; p.out_point_major = 1; p.rows = rows; p.row_pitch = row_pitch;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        JMB_CUDA(cudaGetDevice(&dev));
+        JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    }
+    const long long tiles = rows / TC_BN;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    sa_fused_kernel<true><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    return check_launch("rcnn_input_fused");
 }

@@ -109,6 +109,7 @@ class RCNN(nn.Module):
         self.init_weights()
         self._packed = None
         self.fuse_chain = True      # run qualifying SA layers as ONE kernel (csrc/sa_fused.cu)
+        self.fuse_input = True      # RoI pooling writes the head layout and xyz_up + merge_down run as ONE kernel
 
     def init_weights(self):  # rcnn.py:116-134, weight_init='xavier'
         for m in self.modules():
@@ -131,6 +132,11 @@ class RCNN(nn.Module):
             "cls": _pack_stack(self.cls_layer), "reg": _pack_stack(self.reg_layer),
             "link": _pack_stack(self.link_layer), "se": _pack_stack(self.se_layer),
         }
+        up = self._packed["xyz_up"]
+        if len(up) == 2 and up[0].K <= 8 and up[0]._w32 is not None:
+            w8 = torch.zeros(up[0].M, 8, dtype=torch.float32, device=up[0].bias.device)
+            w8[:, : up[0].K] = up[0]._w32
+            self._packed["xyz_up_w8"] = tc.PackedLayer(w8, up[0].bias[: up[0].M], up[0].relu)
         return self._packed
 
     @property
@@ -139,13 +145,32 @@ class RCNN(nn.Module):
 
     # ---- forward ----------------------------------------------------------------------------
     @torch.no_grad()
+    def _input_fusable(self, n_extra: int, n_feat: int) -> bool:
+        """The single-kernel input stage (csrc/sa_fused.cu, ROWS mode) covers the reference configuration:
+        xyz_up_layer [3 + extras <= 8, 128, 128], 128 RPN channels, merge_down_layer [256, 128], SA0 on the fused path."""
+        P = self.packed
+        sa0, pk0 = self.SA_modules[0], P["sa"][0]
+        return (self.fuse_input and self.fuse_chain and "xyz_up_w8" in P and n_feat == 128 and 3 + n_extra <= 8
+                and [(l.M, l.K) for l in P["xyz_up"][1:]] == [(128, 128)] and [(l.M, l.K) for l in P["merge_down"]] == [(128, 256)]
+                and all(l.relu for l in P["xyz_up"] + P["merge_down"]) and sa0.npoint is not None
+                and tc.sa_fused_supported(pk0, pk0[0].K - 3, sa0.npoint, sa0.groupers[0].nsample))
+
+    @torch.no_grad()
     def pool_rois(self, input_data):
-        """ProposalTargetLayer.forward eval branch (proposal_target_layer.py:17-34, 99-115)."""
+        """ProposalTargetLayer.forward eval branch (proposal_target_layer.py:17-34, 99-115).  Returns the pooled points
+        either as the reference's pts_input (G, S, 3 + extras + C) or — when the fused input stage applies — in the
+        head layout (G, S, round_up(3 + extras + C, 8)) = [C channels | x, y, z, extras | zeros], which
+        forward_points recognises by its row length."""
         cfg = self.cfg
         extra = [input_data["seg_mask"].unsqueeze(2)]
         if cfg.use_depth:
             extra.append((input_data["pts_depth"] / 70.0 - 0.5).unsqueeze(2))
         pts_feature = torch.cat(extra + [input_data["rpn_features"]], dim=2)
+        if self._input_fusable(len(extra), input_data["rpn_features"].shape[2]):
+            pooled, empty = roipool3d_utils.roipool3d_gpu_canonical_head(
+                input_data["rpn_xyz"], pts_feature, input_data["roi_boxes3d"], cfg.pool_extra_width, len(extra),
+                sampled_pt_num=cfg.num_points)
+            return pooled.view(-1, pooled.shape[2], pooled.shape[3]), empty
         pooled, empty = roipool3d_utils.roipool3d_gpu_canonical(input_data["rpn_xyz"], pts_feature,
                                                                 input_data["roi_boxes3d"], cfg.pool_extra_width,
                                                                 sampled_pt_num=cfg.num_points)
@@ -156,25 +181,31 @@ class RCNN(nn.Module):
         """rcnn.py:172-202 on pts_input (G, 512, 3 + extra + C): returns rcnn_cls (G,1), rcnn_reg (G,46), rcnn_feat (G,512,1)."""
         P = self.packed
         cin = self.rcnn_input_channel
-        xyz = pts_input[..., 0:3].contiguous()
-        xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()                   # (G, 5, 512)
-        rpn_feature = pts_input[..., cin:].transpose(1, 2)                                # (G, 128, 512)
-        c_up = P["xyz_up"][-1].M
-        both = torch.empty((xyz.shape[0], c_up + rpn_feature.shape[1], xyz.shape[1]), dtype=torch.float32,
-                           device=xyz.device)                                          # cat((xyz_feature, rpn_feature))
-        both[:, c_up:].copy_(rpn_feature)
-        h = xyz_input
-        for i, layer in enumerate(P["xyz_up"]):
-            h = tc.mlp_layer(layer, h, out=both[:, :c_up] if i == len(P["xyz_up"]) - 1 else None)
-        # The fused set-abstraction kernel gathers from POINT-MAJOR features, so the producers write that layout
-        # directly: merge_down -> (G, 512, 128), SA0 -> (G, 128, 128); no transposes in between.
         sa_list = list(zip(self.SA_modules, P["sa"]))
         chain_ok = [self.fuse_chain and sa.npoint is not None and
                     tc.sa_fused_supported(pk, pk[0].K - 3, sa.npoint, sa.groupers[0].nsample) for sa, pk in sa_list]
-        md = P["merge_down"]
-        h = both
-        for i, layer in enumerate(md):
-            h = tc.mlp_layer(layer, h, point_major_out=(chain_ok[0] and i == len(md) - 1))
+        head_pitch = (cin + 128 + 7) // 8 * 8
+        if pts_input.shape[-1] == head_pitch and head_pitch != cin + 128:
+            # head layout from pool_rois: [128 channels | x, y, z, extras | 0...]; one kernel for the whole input stage
+            xyz = pts_input[..., 128:131].contiguous()
+            h = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], pts_input.contiguous())
+        else:
+            xyz = pts_input[..., 0:3].contiguous()
+            xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()               # (G, 5, 512)
+            rpn_feature = pts_input[..., cin:].transpose(1, 2)                            # (G, 128, 512)
+            c_up = P["xyz_up"][-1].M
+            both = torch.empty((xyz.shape[0], c_up + rpn_feature.shape[1], xyz.shape[1]), dtype=torch.float32,
+                               device=xyz.device)                                      # cat((xyz_feature, rpn_feature))
+            both[:, c_up:].copy_(rpn_feature)
+            h = xyz_input
+            for i, layer in enumerate(P["xyz_up"]):
+                h = tc.mlp_layer(layer, h, out=both[:, :c_up] if i == len(P["xyz_up"]) - 1 else None)
+            # The fused set-abstraction kernel gathers from POINT-MAJOR features, so the producers write that layout
+            # directly: merge_down -> (G, 512, 128), SA0 -> (G, 128, 128); no transposes in between.
+            md = P["merge_down"]
+            h = both
+            for i, layer in enumerate(md):
+                h = tc.mlp_layer(layer, h, point_major_out=(chain_ok[0] and i == len(md) - 1))
         l_xyz, l_feat, pm = xyz, h, chain_ok[0]                                           # pm: l_feat is point-major
         for k, (sa, packed) in enumerate(sa_list):
             grouper = sa.groupers[0]

@@ -40,3 +40,15 @@ def forward_canonical(xyz, boxes3d, pts_feature, pool_extra_width, pooled_featur
         float(pool_extra_width), xyz.data_ptr(), boxes3d.data_ptr(), pts_feature.data_ptr(),
         pooled_features.data_ptr(), pooled_empty_flag.data_ptr(), st), "roipool3d_canonical")
     return 1
+
+
+def forward_canonical_head(xyz, boxes3d, pts_feature, pool_extra_width, lead, pooled_features, pooled_empty_flag):
+    """forward_canonical writing rows as [features lead.. | x, y, z | features 0..lead-1 | 0...] with a pitch of
+    round_up(3 + C, 8) floats: the layout the fused input stage of the per-proposal network reads (tc.rcnn_input_fused)."""
+    _chk(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag)
+    st = _lib.stream_and_device(xyz)
+    _lib.check(_lib.lib().jmb_roipool3d_canonical_head(
+        xyz.size(0), xyz.size(1), boxes3d.size(1), pts_feature.size(2), pooled_features.size(2),
+        float(pool_extra_width), int(lead), xyz.data_ptr(), boxes3d.data_ptr(), pts_feature.data_ptr(),
+        pooled_features.data_ptr(), pooled_empty_flag.data_ptr(), st), "roipool3d_canonical_head")
+    return 1

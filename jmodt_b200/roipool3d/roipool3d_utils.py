@@ -37,3 +37,16 @@ def roipool3d_gpu_canonical(pts, pts_feature, boxes3d, pool_extra_width, sampled
     roipool3d_cuda.forward_canonical(pts.contiguous(), boxes3d.contiguous(), pts_feature.contiguous(),
                                      pool_extra_width, pooled_features, pooled_empty_flag)
     return pooled_features, pooled_empty_flag
+
+
+def roipool3d_gpu_canonical_head(pts, pts_feature, boxes3d, pool_extra_width, lead, sampled_pt_num=512):
+    """roipool3d_gpu_canonical in the head layout: returns (B, M, S, P) with P = round_up(3 + C, 8) and rows
+    [pts_feature[lead:] | canonical x, y, z | pts_feature[:lead] | zeros], plus pooled_empty_flag."""
+    batch_size, boxes_num, feature_len = pts.shape[0], boxes3d.shape[1], pts_feature.shape[2]
+    pitch = (3 + feature_len + 7) // 8 * 8
+    pooled_features = torch.empty((batch_size, boxes_num, sampled_pt_num, pitch), dtype=torch.float32,
+                                  device=pts.device)
+    pooled_empty_flag = torch.empty((batch_size, boxes_num), dtype=torch.int32, device=pts.device)
+    roipool3d_cuda.forward_canonical_head(pts.contiguous(), boxes3d.contiguous(), pts_feature.contiguous(),
+                                          pool_extra_width, lead, pooled_features, pooled_empty_flag)
+    return pooled_features, pooled_empty_flag

@@ -161,3 +161,22 @@ def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, 
                                 out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel",
         desc=f"sa_fused C={C} C3={l3.M} G={G} npoint={npoint} ns={nsample}")
     return out
+
+
+def rcnn_input_fused(w1: PackedLayer, w2: PackedLayer, w3: PackedLayer, rows_in: torch.Tensor) -> torch.Tensor:
+    """xyz_up_layer (2 layers) + concat + merge_down_layer of the per-proposal network (rcnn.py:172-186) in one
+    kernel: rows_in (..., 136) in the head layout [128 channels | x, y, z, mask, depth | 0, 0, 0] ->
+    (..., 128) point-major merged features.  w1 is the first xyz_up layer packed as 128 x 8."""
+    assert rows_in.is_contiguous() and rows_in.dtype == torch.float32 and rows_in.shape[-1] == 136
+    assert (w1.M, w1.K) == (128, 8) and (w2.M, w2.K) == (128, 128) and (w3.M, w3.K) == (128, 256)
+    assert w1.relu and w2.relu and w3.relu
+    rows = rows_in.numel() // 136
+    out = torch.empty(rows_in.shape[:-1] + (128,), dtype=torch.float32, device=rows_in.device)
+    st = _lib.stream_and_device(rows_in)
+    flops = 2.0 * rows * (128 * 5 + 128 * 128 + 128 * 256)
+    profiler.launch(flops, lambda: _lib.check(
+        _lib.lib().jmb_rcnn_input_fused(w1.wpack.data_ptr(), w1.bias.data_ptr(), w2.wpack.data_ptr(),
+                                        w2.bias.data_ptr(), w3.wpack.data_ptr(), w3.bias.data_ptr(), rows, 136,
+                                        rows_in.data_ptr(), out.data_ptr(), st), "rcnn_input_fused"),
+        kind="rcnn_input_kernel", desc=f"rcnn_input_fused rows={rows}")
+    return out

@@ -19,8 +19,14 @@ t0 = time.perf_counter(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.
 e0.record(); suite.step(d); e1.record(); t_enq = time.perf_counter() - t0
 torch.cuda.synchronize()
 print(f"# host enqueue {t_enq*1e3:.2f} ms, device {e0.elapsed_time(e1):.2f} ms")
+GRAPH = len(sys.argv) > 2 and sys.argv[2] == 'graph'
+if GRAPH:
+    from jmodt_b200.runtime import CapturedPath
+    cap = CapturedPath(suite.step, d, warmup=1)
+    for _ in range(2): cap.replay()
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    suite.step(d)
+    cap.replay() if GRAPH else suite.step(d)
     torch.cuda.synchronize()
 path = 'gpurun_out/trace.json'
 prof.export_chrome_trace(path)

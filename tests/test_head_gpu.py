@@ -41,18 +41,53 @@ def test_rcnn_head_matches_torch_reference(cuda):
                 p.normal_(0, 0.1)
     rcnn.pack()
     inp = _frame_inputs(cuda, 1, 3)
-    inp["roi_boxes3d"] = inp["roi_boxes3d"][:, :24].contiguous()
-    pts_input, empty = rcnn.pool_rois(inp)
+    rois = inp["roi_boxes3d"]
+    inp["roi_boxes3d"] = torch.cat((rois[:, :20], rois[:, -4:]), dim=1).contiguous()     # the last rois are empty
+    rcnn.fuse_input = False
+    pts_input, empty = rcnn.pool_rois(inp)               # the reference's pts_input layout
     assert pts_input.shape == (24, 512, 133)
-    cls, reg, feat = rcnn.forward_points(pts_input)
+    assert 0 < int(empty.sum()) < 24
+    rcnn.fuse_input = True
+    pts_head, empty_h = rcnn.pool_rois(inp)              # head layout: [128 channels | xyz, mask, depth | 0 0 0]
+    assert pts_head.shape == (24, 512, 136) and torch.equal(empty, empty_h)
+    assert torch.equal(pts_head[..., :128], pts_input[..., 5:]) and torch.equal(pts_head[..., 128:133], pts_input[..., :5])
+    assert not pts_head[..., 133:].any()
     with torch.no_grad():
         wcls, wreg, wfeat = modules_ref.rcnn_forward_points(rcnn, pts_input, pu.farthest_point_sample, pu.ball_query)
-    assert cls.shape == (24, 1) and reg.shape == (24, 46) and feat.shape == (24, 512, 1)
-    assert _rel(feat, wfeat) < 1e-4, _rel(feat, wfeat)
-    assert _rel(cls, wcls) < 1e-4, _rel(cls, wcls)
-    assert _rel(reg, wreg) < 1e-4, _rel(reg, wreg)
+    for x in (pts_head, pts_input):                      # single-kernel input stage, and the layer-by-layer one
+        cls, reg, feat = rcnn.forward_points(x)
+        assert cls.shape == (24, 1) and reg.shape == (24, 46) and feat.shape == (24, 512, 1)
+        assert _rel(feat, wfeat) < 1e-4, _rel(feat, wfeat)
+        assert _rel(cls, wcls) < 1e-4, _rel(cls, wcls)
+        assert _rel(reg, wreg) < 1e-4, _rel(reg, wreg)
+    cls, reg, feat = rcnn.forward_points(pts_head)
     out = rcnn(inp)
     assert torch.equal(out["rcnn_feat"], feat) and out["pooled_empty_flag"].shape == (1, 24)
+
+
+def test_rcnn_input_stage_single_kernel_vs_layers(cuda):
+    """xyz_up_layer + cat + merge_down_layer (rcnn.py:172-186) as ONE kernel vs torch fp32 on random rows."""
+    from jmodt_b200 import tc
+    from jmodt_b200.head import RCNN
+    torch.manual_seed(2)
+    rcnn = RCNN().to(cuda).eval()
+    with torch.no_grad():
+        for p in rcnn.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    P = rcnn.pack()
+    g = torch.Generator().manual_seed(11)
+    rows = torch.zeros(5, 512, 136)
+    rows[..., :133] = torch.randn(5, 512, 133, generator=g)
+    rows = rows.to(cuda)
+    got = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], rows)
+    with torch.no_grad():
+        xyz_in = rows[..., 128:133].transpose(1, 2).unsqueeze(3)                         # (G, 5, 512, 1)
+        up = rcnn.xyz_up_layer(xyz_in)
+        want = rcnn.merge_down_layer(torch.cat((up, rows[..., :128].transpose(1, 2).unsqueeze(3)), dim=1))
+    want = want.squeeze(3).transpose(1, 2)
+    assert got.shape == (5, 512, 128)
+    assert _rel(got, want) < 1e-4, _rel(got, want)
 
 
 def test_affinity_matches_torch_reference(cuda):
