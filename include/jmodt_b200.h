@@ -192,10 +192,11 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
                                float *out, void *stream);
 
 /* One whole single-scale set-abstraction layer (reference pointnet2_modules.py:20-63 with QueryAndGroup and a
- * 3-layer SharedMLP of widths 128, 128, C3 in {128,256}) in ONE kernel: grouped gather -> MLP -> max over nsample.
- * w2/w3 are packed layers (jmodt_b200/tc.py); w1 is packed with its input columns reordered to [channels, xyz]
- * (tc.PackedLayer(..., xyz_last=True)).  C_in % 8 == 0, C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample a
- * multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
+ * 3-layer SharedMLP) in ONE kernel: grouped gather -> MLP -> max over nsample.  Layer widths C1, C2 <= 128 and
+ * C3 <= 256; w1/w2/w3 are packed layers (jmodt_b200/tc.py) ZERO-PADDED to 128 x K1, 128 x 128 and
+ * (128 or 256) x 128, w1 with its input columns reordered to [channels, xyz] (tc.PackedLayer(..., xyz_last=True)).
+ * C_in % 8 == 0 (0 = coordinates only, feats may be NULL), C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample
+ * a multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
  * centres (G, npoint, 3) -> out (G, C3, npoint), or point-major (G, npoint, C3) if out_point_major != 0. */
 JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
                          const float *b3, int C_in, int C3, int G, int npoint, int nsample, int n_pts,

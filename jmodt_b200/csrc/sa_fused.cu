@@ -29,28 +29,34 @@ namespace jmb {
 // warp roles: 0-15 epilogue (half h = (w>>2)&1, TMEM lane quadrant w&3, 32-column sub-block w>>3),
 //             16-19 gather (64 threads per half: one neighbour each), 20-21 MMA issuers (one per half)
 constexpr int SF_EPI_WARPS = 16;
-constexpr int SF_EPI_PER_HALF = 256;          // epilogue threads per half
 constexpr int SF_GATHER_WARP0 = 16;
-constexpr int SF_GATHER_PER_HALF = 64;
 constexpr int SF_ISSUER_WARP = 20;
-constexpr int SF_THREADS = 22 * 32;          // warps 20, 21: one MMA issuer per half
+// A tile of 128 columns is processed as NP independent PARTS (NP = 2 halves of 64 columns, or 4 quarters of 32): each
+// part has its own accumulator columns, operand-image slice, barriers, gather threads and MMA-issuer warp, so the
+// dependent chain  gather -> L1 -> epilogue -> L2 -> epilogue -> L3 -> epilogue  of one part overlaps the chains of the
+// others.  The chain is latency-bound (three TMEM->register->shared hand-offs per tile); more, narrower parts keep the
+// tensor pipe busier at the price of more MMA instructions.
+template <int NP> struct SfCfg {
+    static constexpr int PART = TC_BN / NP;                          // columns per part
+    static constexpr int THREADS = (SF_ISSUER_WARP + NP) * 32;      // warps 20 .. 20+NP-1: one MMA issuer per part
+    static constexpr int EPI_PER_PART = SF_EPI_WARPS * 32 / NP;
+    static constexpr uint32_t PART_OFF = (PART / 8) * TC_SBO;        // byte offset of the next part inside an image
+    // kind::f16, BF16 x BF16 -> F32, M=128, N=PART, A K-major, B MN-major / B K-major (layer 1)
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                                      ((uint32_t)(PART >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    static constexpr uint32_t IDESC_L1 = IDESC & ~(1u << 16);
+};
 constexpr int SF_MAXKC1 = 5;
 constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chunk: 16 KB
 constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
-constexpr int SF_HALF = 64;
-constexpr uint32_t SF_HALF_OFF = (SF_HALF / 8) * TC_SBO;           // byte offset of the second half inside an image
-// kind::f16, BF16 x BF16 -> F32, M=128, N=64, A K-major, B MN-major
-constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                              ((uint32_t)(SF_HALF >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-// layer 1: same but B K-major (bit 16 = 0)
-constexpr uint32_t SF_IDESC_L1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
-                                 ((uint32_t)(SF_HALF >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+constexpr int SF_MAXPARTS = 4;
 constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bases (hi at +0, lo at +64 of each block)
 
 struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
     const float *b1, *b2, *b3;
     int K1, Kc1, Mt3;      // K1 = Cp + 3 with Cp = C_in rounded up to 8 (channels first, xyz last)
+    int C3;                // real width of the last layer (<= 128 * Mt3; rows beyond it are zero padding)
     int C;                 // feature channels
     int G, npoint, nsample, n_pts;
     const float *feats;    // (G, n_pts, C) POINT-MAJOR
@@ -65,25 +71,20 @@ struct SaFusedParams {
     long long *dbg;        // optional timeline buffer (profiling aid): CTA 0 writes clock64() stamps
 };
 
-__device__ __forceinline__ void umma_ss64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+template <uint32_t IDESC>
+__device__ __forceinline__ void umma_ss_part(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(SF_IDESC_L1), "r"(accumulate)
+        "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_ts64(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+template <uint32_t IDESC>
+__device__ __forceinline__ void umma_ts_part(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(SF_IDESC), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_ts64_kmajor(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(SF_IDESC_L1), "r"(accumulate)
+        "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -125,24 +126,28 @@ __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_b
 //   W3[:, 0:128] . act2 + W3[:, 128:256] . channels (both A blocks in tensor memory, the second with the K-major row
 //   image as B), and every column is written point-major (rows, 128) — no pooling.  The (G, 256, 512) concat, both
 //   transposes of the pooled tensor and two activation round trips of the unfused path disappear.
-template <bool ROWS>
-__global__ void __launch_bounds__(SF_THREADS, 1)
+template <bool ROWS, int NP>
+__global__ void __launch_bounds__(SfCfg<NP>::THREADS, 1)
 sa_fused_kernel(const SaFusedParams p) {
+    using Cfg = SfCfg<NP>;
+    constexpr int PART = Cfg::PART;
+    constexpr int SF_THREADS = Cfg::THREADS;
     extern __shared__ __align__(1024) uint8_t sf_smem[];
     uint8_t *s_w1 = sf_smem;
     uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[2], s_x1_free[2], s_acc_full[2], s_epi_done[2], s_w1_full;
+    __shared__ __align__(8) uint64_t s_x1_full[SF_MAXPARTS], s_x1_free[SF_MAXPARTS], s_acc_full[SF_MAXPARTS],
+        s_epi_done[SF_MAXPARTS], s_w1_full;
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int h = 0; h < 2; ++h) {
-            mbar_init(&s_x1_full[h], SF_GATHER_PER_HALF);
+        for (int h = 0; h < NP; ++h) {
+            mbar_init(&s_x1_full[h], PART);
             mbar_init(&s_x1_free[h], 1);
             mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], SF_EPI_PER_HALF);
+            mbar_init(&s_epi_done[h], Cfg::EPI_PER_PART);
         }
         mbar_init(&s_w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -193,10 +198,10 @@ sa_fused_kernel(const SaFusedParams p) {
 
     if (warp < SF_EPI_WARPS) {
         // ====================================== epilogue warps ======================================
-        // warp w: columns [64h + 32s, +32) of accumulator rows [32*quad, +32)
-        const int quad = warp & 3, h = (warp >> 2) & 1, sblk = warp >> 3;
+        // warp w: columns [PART*h + 32*sblk, +32) of accumulator rows [32*quad, +32)
+        const int quad = warp & 3, h = (warp >> 2) % NP, sblk = (warp >> 2) / NP;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * SF_HALF;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * PART;
         uint32_t acc_phase = 0;
 
         // accumulator half -> next layer's operand image (row m of the accumulator is row k = m of the operand)
@@ -218,7 +223,7 @@ sa_fused_kernel(const SaFusedParams p) {
                     split2(w[2], w[3], hh.y, ll.y);
                     split2(w[4], w[5], hh.z, ll.z);
                     split2(w[6], w[7], hh.w, ll.w);
-                    const uint32_t off = (uint32_t)(h * 8 + (c0 >> 3) + q) * TC_SBO + rowoff;
+                    const uint32_t off = (uint32_t)(h * (PART / 8) + (c0 >> 3) + q) * TC_SBO + rowoff;
                     *reinterpret_cast<uint4 *>(ahi + off) = hh;
                     *reinterpret_cast<uint4 *>(alo + off) = ll;
                 }
@@ -229,7 +234,9 @@ sa_fused_kernel(const SaFusedParams p) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
-            const int c3 = TC_BM * p.Mt3, ch = mt * TC_BM + m, ctr0 = (nt * TC_BN + h * SF_HALF) / p.nsample;
+            const int c3 = p.C3, ch = mt * TC_BM + m, ctr0 = (nt * TC_BN + h * PART) / p.nsample;
+            const bool live = ch < c3;     // zero-padded rows of a layer narrower than the 128-row MMA tile are not stored
+                                           // (no early return: tcgen05.ld below is warp-collective)
             // element (centre w) of this channel: channel-first out[g][ch][ctr0 + w]  or  point-major out[g][ctr0 + w][ch]
             float *orow = p.out_point_major ? p.out + ((size_t)g * p.npoint + ctr0) * c3 + ch
                                             : p.out + ((size_t)g * c3 + ch) * p.npoint + ctr0;
@@ -237,7 +244,7 @@ sa_fused_kernel(const SaFusedParams p) {
             const int sub = p.nsample < 32 ? p.nsample : 32;
             float run = -INFINITY;
 #pragma unroll 1
-            for (int c0 = 0; c0 < SF_HALF; c0 += 32) {
+            for (int c0 = 0; c0 < PART; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -248,8 +255,13 @@ sa_fused_kernel(const SaFusedParams p) {
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
                     run = fmaxf(run, mx);
                     if ((c0 + 32) % p.nsample == 0) {
-                        orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = run;
+                        if (live) orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = run;
                         run = -INFINITY;
+                    } else if (c0 + 32 == PART && live) {
+                        // the pooling window (nsample columns) is wider than this part: the parts that share it combine
+                        // through an integer max on the zero-initialised output (post-ReLU values are >= 0, and
+                        // non-negative floats order like their bit patterns)
+                        atomicMax(reinterpret_cast<int *>(orow), __float_as_int(run));
                     }
                 } else {
                     for (int w0 = 0; w0 < 32; w0 += sub) {
@@ -257,7 +269,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j >= w0 && j < w0 + sub) mx = fmaxf(mx, v[j]);
-                        orow[(size_t)((c0 + w0) / p.nsample) * ostride] = mx;
+                        if (live) orow[(size_t)((c0 + w0) / p.nsample) * ostride] = mx;
                     }
                 }
             }
@@ -269,7 +281,7 @@ sa_fused_kernel(const SaFusedParams p) {
             const int c0 = sblk * 32;
             float v[32];
             tmem_ld32(taddr + c0, v);
-            float *dst = p.out + ((size_t)tile * TC_BN + h * SF_HALF + c0) * TC_BM + m;
+            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + c0) * TC_BM + m;
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
         };
@@ -294,7 +306,7 @@ sa_fused_kernel(const SaFusedParams p) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
                 if (ROWS) epilogue_rows(tile);
-                else if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools the whole 64-column half
+                else if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools all columns of the part
                 tc_fence_before();
                 mbar_arrive(&s_epi_done[h]);
             }
@@ -302,7 +314,7 @@ sa_fused_kernel(const SaFusedParams p) {
     } else if (warp < SF_ISSUER_WARP) {
         // ====================================== gather warps ======================================
         const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
-        const int h = tg >> 6, nl = tg & 63;
+        const int h = tg / PART, nl = tg % PART;
         const int n_groups = ROWS ? p.row_pitch / 8 : p.C / 8;   // feature k-groups; SA: group n_groups holds (dx, dy, dz, 0...)
         // One thread = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
         // channels in flight), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
@@ -310,11 +322,11 @@ sa_fused_kernel(const SaFusedParams p) {
         auto produce_x1 = [&](long long tile) {
             const int nt = (int)(tile % Nt);
             const int g = (int)(tile / Nt);
-            const int n = nt * TC_BN + h * SF_HALF + nl;
+            const int n = nt * TC_BN + h * PART + nl;
             const int pi = ROWS ? 0 : __ldg(p.idx + (size_t)g * N + n);
-            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + h * SF_HALF + nl) * p.row_pitch
+            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + h * PART + nl) * p.row_pitch
                                      : p.feats + ((size_t)g * p.n_pts + pi) * p.C;
-            const uint32_t noff = (uint32_t)(h * 8 + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
+            const uint32_t noff = (uint32_t)(h * (PART / 8) + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
             auto put = [&](int kg, const float (&v)[8]) {
                 uint4 hh, ll;
                 split2(v[0], v[1], hh.x, ll.x);
@@ -356,12 +368,12 @@ sa_fused_kernel(const SaFusedParams p) {
             if (ROWS && nl == 0) {
                 // the rows of this CTA's next two tiles are contiguous: pull this half's share into L2 ahead of the
                 // gather, whose 64 threads alone cannot keep enough HBM requests in flight
-                const uint32_t bytes = (uint32_t)(SF_HALF * p.row_pitch * 4);
+                const uint32_t bytes = (uint32_t)(PART * p.row_pitch * 4);
                 for (int a = (tile_ctr == 0 ? 1 : 2); a <= 2; ++a) {
                     const long long t2 = tile + (long long)a * gridDim.x;
                     if (t2 < total_tiles)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                                         p.feats + ((size_t)t2 * TC_BN + h * SF_HALF) * p.row_pitch), "r"(bytes) : "memory");
+                                         p.feats + ((size_t)t2 * TC_BN + h * PART) * p.row_pitch), "r"(bytes) : "memory");
                 }
             }
             if (tile_ctr > 0) mbar_wait(&s_x1_free[h], (tile_ctr - 1) & 1);   // the MMAs that read this half of the previous tile are done
@@ -369,7 +381,7 @@ sa_fused_kernel(const SaFusedParams p) {
         }
     } else {
         if (lane == 0) {
-            // ====================================== MMA issuers: one thread per half ======================================
+            // ====================================== MMA issuers: one thread per part ======================================
             // A single thread's instruction stream (descriptor arithmetic + 3 MMAs per K step) was the bottleneck of the
             // tensor pipe, so each half has its own issuer, and descriptors are formed by adding constants to a base
             // descriptor (the start-address field is the low 14 bits; images never cross it).
@@ -383,10 +395,10 @@ sa_fused_kernel(const SaFusedParams p) {
                 mbar_wait(&s_epi_done[h], epi_phase); epi_phase ^= 1;
                 tc_fence_after();
             };
-            const uint32_t acc = tmem_base + (uint32_t)h * SF_HALF;
+            const uint32_t acc = tmem_base + (uint32_t)h * PART;
             const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
-            const uint64_t x1_desc = make_smem_desc(smem_u32(s_x1) + h * SF_HALF_OFF);
-            const uint64_t act_desc = make_smem_desc(smem_u32(s_act) + h * SF_HALF_OFF);
+            const uint64_t x1_desc = make_smem_desc(smem_u32(s_x1) + h * Cfg::PART_OFF);
+            const uint64_t act_desc = make_smem_desc(smem_u32(s_act) + h * Cfg::PART_OFF);
             constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4;
             const int last_steps = (kmax16 - (p.Kc1 - 1) * TC_BK) >= 32 ? 2 : 1;
             long long *dbg = (p.dbg && blockIdx.x == 0 && h == 0) ? p.dbg : nullptr;
@@ -402,20 +414,20 @@ sa_fused_kernel(const SaFusedParams p) {
                 SF_STAMP(3);
                 if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
                     const uint64_t xd = x1_desc + 4 * D_CHUNK;
-                    umma_ss64(acc, w1_desc, xd, 0);
-                    umma_ss64(acc, w1_desc + D_IMG, xd, 1);
-                    umma_ss64(acc, w1_desc, xd + D_IMG, 1);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc, xd, 0);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc + D_IMG, xd, 1);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc, xd + D_IMG, 1);
                 }
                 for (int c = 0; !ROWS && c < p.Kc1; ++c) {
                     const int steps = c == p.Kc1 - 1 ? last_steps : 2;
                     const uint64_t wd = w1_desc + (uint64_t)c * D_CHUNK, xd = x1_desc + (uint64_t)c * D_CHUNK;
-                    umma_ss64(acc, wd, xd, c != 0);
-                    umma_ss64(acc, wd + D_IMG, xd, 1);
-                    umma_ss64(acc, wd, xd + D_IMG, 1);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd, c != 0);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_IMG, xd, 1);
+                    umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd + D_IMG, 1);
                     if (steps == 2) {
-                        umma_ss64(acc, wd + D_K16, xd + D_K16, 1);
-                        umma_ss64(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
-                        umma_ss64(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
+                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16, xd + D_K16, 1);
+                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
+                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
                     }
                 }
                 if (!ROWS) umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
@@ -430,18 +442,18 @@ sa_fused_kernel(const SaFusedParams p) {
                     for (int k16 = 0; k16 < 8; ++k16) {
                         const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
                         const uint32_t ahi = wcol + (uint32_t)k16 * 8;
-                        umma_ts64(acc, ahi, xd, k16 != 0);
-                        umma_ts64(acc, ahi + 64, xd, 1);
-                        umma_ts64(acc, ahi, xd + D_IMG, 1);
+                        umma_ts_part<Cfg::IDESC>(acc, ahi, xd, k16 != 0);
+                        umma_ts_part<Cfg::IDESC>(acc, ahi + 64, xd, 1);
+                        umma_ts_part<Cfg::IDESC>(acc, ahi, xd + D_IMG, 1);
                     }
                     if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
 #pragma unroll
                         for (int k16 = 0; k16 < 8; ++k16) {
                             const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
                             const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
-                            umma_ts64_kmajor(acc, ahi, xd, 1);
-                            umma_ts64_kmajor(acc, ahi + 64, xd, 1);
-                            umma_ts64_kmajor(acc, ahi, xd + D_IMG, 1);
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd, 1);
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi + 64, xd, 1);
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd + D_IMG, 1);
                         }
                         umma_commit(&s_x1_free[h]);
                     }
@@ -460,6 +472,19 @@ sa_fused_kernel(const SaFusedParams p) {
     }
 }
 
+// Parts per tile (see SfCfg): 2 unless JMB_SA_PARTS=4.  Measured on B200 (profiles/r01/sa_fused_parts.txt): quarters are
+// 2 % faster on the RCNN SA0 shape and 20-30 % slower on the narrow RPN levels — the in-kernel timeline shows the chain
+// is bound by MMA issue (two issuers share the pipe; the layer-1 SS MMAs re-read their A operand from shared memory for
+// every 64 columns), not by the epilogue hand-offs, so narrower parts do not pay.
+static int sf_parts() {
+    static int parts = 0;
+    if (parts == 0) {
+        const char *e = getenv("JMB_SA_PARTS");
+        parts = (e && e[0] == '4') ? 4 : 2;
+    }
+    return parts;
+}
+
 }  // namespace jmb
 
 extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
@@ -476,17 +501,17 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     }
     JMB_REQUIRE(G >= 0 && npoint > 0 && nsample > 0 && n_pts > 0, "sa_fused: bad sizes");
     if (G == 0) return JMB_OK;
-    JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && feats && idx && xyz && centres && out, "sa_fused: null pointer");
-    JMB_REQUIRE(C > 0 && C % 8 == 0 && C + 3 <= SF_MAXKC1 * TC_BK, "sa_fused: C_in = %d must be a multiple of 8 and <= 152", C);
+    JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && (feats || C == 0) && idx && xyz && centres && out, "sa_fused: null pointer");
+    JMB_REQUIRE(C >= 0 && C % 8 == 0 && C + 3 <= SF_MAXKC1 * TC_BK, "sa_fused: C_in = %d must be a multiple of 8 and <= 152", C);
     const int K1 = C + 3;   // C is a multiple of 8, so the xyz group starts right after the channels
     JMB_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15u) == 0, "sa_fused: feats must be 16-byte aligned");
-    JMB_REQUIRE(C3 == 128 || C3 == 256, "sa_fused: last layer width must be 128 or 256");
+    JMB_REQUIRE(C3 >= 1 && C3 <= 256, "sa_fused: last layer width %d must be in 1..256", C3);
     JMB_REQUIRE(nsample % 8 == 0 && 64 % nsample == 0, "sa_fused: nsample must be 8, 16, 32 or 64");
     JMB_REQUIRE(((long long)npoint * nsample) % TC_BN == 0, "sa_fused: npoint*nsample must be a multiple of 128");
     SaFusedParams p;
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = C3 / TC_BM; p.C = C;
+    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = div_up(C3, TC_BM); p.C3 = C3; p.C = C;
     p.w3_blocks = p.Mt3; p.rows = 0; p.row_pitch = 0;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
     p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
@@ -495,11 +520,18 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         int dev = 0;
         JMB_CUDA(cudaGetDevice(&dev));
         JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     }
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    sa_fused_kernel<false><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    if (sf_parts() == 4) {
+        if (nsample > SfCfg<4>::PART)     // pooling windows span two parts: they combine with atomicMax on a zeroed output
+            JMB_CUDA(cudaMemsetAsync(out, 0, (size_t)G * C3 * npoint * sizeof(float), (cudaStream_t)stream));
+        sa_fused_kernel<false, 4><<<grid, SfCfg<4>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    } else {
+        sa_fused_kernel<false, 2><<<grid, SfCfg<2>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    }
     if (dbg_on) {
         long long hbuf[1024];
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -532,7 +564,7 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
     SaFusedParams p = {};
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C = 128; p.w3_blocks = 2;
+    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C = 128; p.w3_blocks = 2;
     p.G = 1; p.npoint = 1; p.nsample = TC_BN; p.n_pts = 0;
     p.feats = in; p.out = out; p.out_point_major = 1; p.rows = rows; p.row_pitch = row_pitch;
     static int sms = 0;
@@ -540,10 +572,12 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
         int dev = 0;
         JMB_CUDA(cudaGetDevice(&dev));
         JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     }
     const long long tiles = rows / TC_BN;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    sa_fused_kernel<true><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    if (sf_parts() == 4) sa_fused_kernel<true, 4><<<grid, SfCfg<4>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    else sa_fused_kernel<true, 2><<<grid, SfCfg<2>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("rcnn_input_fused");
 }

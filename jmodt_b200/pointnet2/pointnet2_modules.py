@@ -121,14 +121,19 @@ class _PointnetSAModuleBase(nn.Module):
         outs = []
         if features is not None:
             features = features.contiguous()
+        feats_pm = None      # point-major copy of the features, shared by the scales that run as one kernel
         for gi, (grouper, layers) in enumerate(zip(self.groupers, packed)):
             if isinstance(grouper, pointnet2_utils.QueryAndGroup):
                 assert grouper.use_xyz, "the fused path groups xyz with the features"
                 idx = nbr[gi]
                 pool = grouper.nsample
-                if getattr(self, "fuse_chain", True) and features is not None and \
-                        tc.sa_fused_supported(layers, features.shape[1], new_xyz.shape[1], grouper.nsample):
-                    outs.append(tc.sa_fused(layers, xyz, features, idx, new_xyz))   # whole layer in one kernel
+                c_in = 0 if features is None else features.shape[1]
+                if getattr(self, "fuse_chain", True) and \
+                        tc.sa_fused_supported(layers, c_in, new_xyz.shape[1], grouper.nsample):
+                    if features is not None and feats_pm is None:
+                        feats_pm = features.transpose(1, 2).contiguous()
+                    outs.append(tc.sa_fused(layers, xyz, feats_pm, idx, new_xyz,
+                                            feats_point_major=True))                 # whole layer in one kernel
                     continue
                 h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
                                            pool=pool if len(layers) == 1 else 0)

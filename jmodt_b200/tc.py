@@ -128,38 +128,55 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
 
 
 def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) -> bool:
-    """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu)."""
-    return (len(layers) == 3 and layers[0].M == 128 and layers[1].M == 128 and layers[1].K == 128
-            and layers[2].K == 128 and layers[2].M in (128, 256) and all(l.relu for l in layers)
-            and n_feat_channels % 8 == 0 and 0 < n_feat_channels <= 152
+    """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu): three ReLU layers of widths
+    C1, C2 <= 128 and C3 <= 256 (narrower layers run zero-padded to the 128-row MMA tile), 0 <= C_in <= 152."""
+    return (len(layers) == 3 and layers[0].M <= 128 and layers[1].M <= 128 and layers[1].K == layers[0].M
+            and layers[2].K == layers[1].M and layers[2].M <= 256 and all(l.relu for l in layers)
+            and all(l._w32 is not None for l in layers)
+            and n_feat_channels % 8 == 0 and 0 <= n_feat_channels <= 152 and layers[0].K == n_feat_channels + 3
             and nsample in (8, 16, 32, 64) and (npoint * nsample) % 128 == 0)
 
 
-def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor, centres: torch.Tensor,
-             w1_xyz_last: PackedLayer | None = None, feats_point_major: bool = False,
-             out_point_major: bool = False) -> torch.Tensor:
-    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first (transposed
-    here to the point-major layout the gather wants), idx (G, npoint, nsample) int32, centres (G, npoint, 3)
-    -> (G, C3, npoint).  `w1_xyz_last` is layers[0] packed with xyz_last=True (built on the fly if omitted)."""
-    G, n_pts, _ = xyz.shape
-    C = feats.shape[2] if feats_point_major else feats.shape[1]
-    npoint, nsample = idx.shape[1], idx.shape[2]
+def _sa_fused_packs(layers):
+    """The three layers as the images sa_fused_kernel keeps resident: W1 (128 x K1, columns [channels, xyz]),
+    W2 (128 x 128), W3 (128|256 x 128), zero-padded; cached on the first layer."""
     l1, l2, l3 = layers
-    assert l1.K == 3 + C and idx.is_contiguous() and xyz.is_contiguous()
-    l1 = w1_xyz_last if w1_xyz_last is not None else l1.repacked_xyz_last()
-    if not feats_point_major:
-        feats = feats.transpose(1, 2)                   # (G, n_pts, C): one neighbour = one contiguous row
-    feats = feats.contiguous()
-    oshape = (G, npoint, l3.M) if out_point_major else (G, l3.M, npoint)
+    cache = getattr(l1, "_sa_packs", None)
+    if cache is None:
+        def padded(layer, K):
+            w = torch.zeros(layer.M, K, dtype=torch.float32, device=layer.bias.device)
+            w[:, : layer.K] = layer._w32
+            return PackedLayer(w, layer.bias[: layer.M], layer.relu)
+        cache = l1._sa_packs = (l1.repacked_xyz_last(), l2 if l2.K == 128 else padded(l2, 128),
+                                l3 if l3.K == 128 else padded(l3, 128))
+    return cache
+
+
+def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor | None, idx: torch.Tensor, centres: torch.Tensor,
+             feats_point_major: bool = False, out_point_major: bool = False) -> torch.Tensor:
+    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first (transposed
+    here to the point-major layout the gather wants), (G, n_pts, C) with feats_point_major, or None (coordinates
+    only), idx (G, npoint, nsample) int32, centres (G, npoint, 3) -> (G, C3, npoint) or point-major (G, npoint, C3)."""
+    G, n_pts, _ = xyz.shape
+    C = 0 if feats is None else (feats.shape[2] if feats_point_major else feats.shape[1])
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    assert layers[0].K == 3 + C and idx.is_contiguous() and xyz.is_contiguous()
+    l1, l2, l3 = _sa_fused_packs(layers)
+    C3 = layers[2].M
+    if feats is not None:
+        if not feats_point_major:
+            feats = feats.transpose(1, 2)               # (G, n_pts, C): one neighbour = one contiguous row
+        feats = feats.contiguous()
+    oshape = (G, npoint, C3) if out_point_major else (G, C3, npoint)
     out = torch.empty(oshape, dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)
-    flops = 2.0 * G * npoint * nsample * (l1.M * l1.K + l2.M * l2.K + l3.M * l3.K)
+    flops = 2.0 * G * npoint * nsample * sum(l.M * l.K for l in layers)
     profiler.launch(flops, lambda: _lib.check(
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
-                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, l3.M, G, npoint, nsample, n_pts,
-                                feats.data_ptr(), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
+                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, C3, G, npoint, nsample, n_pts,
+                                _lib.ptr(feats), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
                                 out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel",
-        desc=f"sa_fused C={C} C3={l3.M} G={G} npoint={npoint} ns={nsample}")
+        desc=f"sa_fused C={C} widths={layers[0].M},{layers[1].M},{C3} G={G} npoint={npoint} ns={nsample}")
     return out
 
 

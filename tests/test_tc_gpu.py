@@ -119,16 +119,20 @@ def test_many_launches_reuse_the_scheduler_slots(cuda):
             _check(got.cpu().double(), wants[i % 3])
 
 
-@pytest.mark.parametrize("C,npoint,ns,C3", [(128, 128, 64, 128), (128, 32, 64, 256), (64, 64, 16, 128), (128, 16, 8, 256)])
-def test_sa_fused_single_kernel_matches_layerwise_and_torch(cuda, C, npoint, ns, C3):
+@pytest.mark.parametrize("C,npoint,ns,C3,C1,C2", [(128, 128, 64, 128, 128, 128), (128, 32, 64, 256, 128, 128),
+                                                  (64, 64, 16, 128, 128, 128), (128, 16, 8, 256, 128, 128),
+                                                  (0, 128, 16, 32, 16, 16), (0, 64, 32, 64, 32, 32),       # RPN level 0
+                                                  (96, 64, 16, 128, 64, 64), (96, 32, 32, 128, 64, 96),    # RPN level 1
+                                                  (8, 16, 8, 200, 24, 40)])
+def test_sa_fused_single_kernel_matches_layerwise_and_torch(cuda, C, npoint, ns, C3, C1, C2):
     """The one-kernel set-abstraction layer vs (a) the layer-by-layer tcgen05 path and (b) torch fp32."""
     from jmodt_b200 import tc
     from jmodt_b200.pointnet2 import pointnet2_utils as pu
     g = torch.Generator(device="cpu").manual_seed(C + npoint)
     G, n_pts = 37, 512
     xyz = (torch.rand(G, n_pts, 3, generator=g) * 2).to(cuda)
-    feats = torch.randn(G, C, n_pts, generator=g).to(cuda)
-    dims = [3 + C, 128, 128, C3]
+    feats = torch.randn(G, C, n_pts, generator=g).to(cuda) if C else None
+    dims = [3 + C, C1, C2, C3]
     layers, ws = [], []
     for i in range(3):
         w = (torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).to(cuda)
