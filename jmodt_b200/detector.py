@@ -14,6 +14,7 @@ row (f)1 of SURVEY §8 ("next"), outside the hot-path scope of this round.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List
 
@@ -22,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, box_utils, tc
+from . import _lib, box_utils, runtime, tc
 from .head import RCNN, HeadConfig, affinity, affinity_batched
 from .iou3d import iou3d_cuda
 from .pointnet2 import pytorch_utils as pt_utils
@@ -121,10 +122,12 @@ class IALayer(nn.Module):
     def forward(self, img_feas, point_feas):
         P = self._packed or self.pack()
         img_feas, point_feas = img_feas.contiguous(), point_feas.contiguous()
-        ri = tc.mlp_layer(P["fc1"], img_feas)                       # (B, rc, N)
-        rp = tc.mlp_layer(P["fc2"], point_feas)
+        # three independent projections of the inputs: forked streams (runtime.parallel)
+        ri, rp, conv = runtime.parallel(lambda: tc.mlp_layer(P["fc1"], img_feas),      # (B, rc, N)
+                                        lambda: tc.mlp_layer(P["fc2"], point_feas),
+                                        lambda: tc.mlp_layer(P["conv1"], img_feas))
         att = torch.sigmoid(tc.mlp_layer(P["fc3"], torch.tanh(ri + rp)))   # (B, 1, N)
-        return tc.mlp_layer(P["conv1"], img_feas) * att
+        return conv * att
 
 
 class AttentionFusion(nn.Module):
@@ -206,7 +209,7 @@ class PointNet2MSG(nn.Module):
         return maps, fused
 
     overlap_geometry = True
-    l0_chunks = 4
+    l0_chunks = int(os.environ.get("JMB_L0_CHUNKS", "8"))     # prefixes of the level-0 FPS output consumed while it runs
 
     def _geometry(self, xyz):
         """FPS, ball query and three_nn depend on coordinates only, the MLP stacks on features only.  In eval mode the
@@ -345,8 +348,9 @@ class RPN(nn.Module):
             self._packed = (_pack_stack(self.rpn_cls_layer), _pack_stack(self.rpn_reg_layer))
         xyz, feats = self.backbone_net(input_data["pts_input"], input_data.get("img"), input_data.get("pts_xy"),
                                        image_maps=image_maps)
-        rpn_cls = run_stack(self._packed[0], feats).transpose(1, 2).contiguous()     # (B, N, 1)
-        rpn_reg = run_stack(self._packed[1], feats).transpose(1, 2).contiguous()     # (B, N, 76)
+        rpn_cls, rpn_reg = runtime.parallel(
+            lambda: run_stack(self._packed[0], feats).transpose(1, 2).contiguous(),      # (B, N, 1)
+            lambda: run_stack(self._packed[1], feats).transpose(1, 2).contiguous())      # (B, N, 76)
         return {"rpn_cls": rpn_cls, "rpn_reg": rpn_reg, "backbone_xyz": xyz, "backbone_features": feats}
 
 

@@ -15,7 +15,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from . import tc
+from . import runtime, tc
 from .pointnet2 import pointnet2_utils as pu
 from .pointnet2 import pytorch_utils as pt_utils
 from .pointnet2.pointnet2_modules import PointnetSAModule
@@ -234,8 +234,8 @@ class RCNN(nn.Module):
             l_xyz, l_feat = new_xyz, h
         # heads: one column per proposal
         feat_t = l_feat.squeeze(-1).t().contiguous().unsqueeze(0)                         # (1, 512, G)
-        rcnn_cls = run_stack(P["cls"], feat_t)[0].t().contiguous()                        # (G, 1)
-        rcnn_reg = run_stack(P["reg"], feat_t)[0].t().contiguous()                        # (G, 46)
+        rcnn_cls, rcnn_reg = runtime.parallel(lambda: run_stack(P["cls"], feat_t)[0].t().contiguous(),   # (G, 1)
+                                              lambda: run_stack(P["reg"], feat_t)[0].t().contiguous())   # (G, 46)
         return rcnn_cls, rcnn_reg, l_feat
 
     @torch.no_grad()
@@ -257,11 +257,15 @@ def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torc
     pt = pred_features.transpose(1, 2).contiguous()                                       # (G, 512, P)
     dt = det_features.transpose(1, 2).contiguous()                                        # (G, 512, D)
     cor = (pt.unsqueeze(3) - dt.unsqueeze(2)).abs().contiguous()                          # (G, 512, P, D)
-    logits = run_stack(packed["link"], cor.view(G, -1, P * D)).view(G, P, D)
-    col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)       # softmax over predecessors
-    link = (torch.softmax(logits, dim=2) + col) / 2
-    start = torch.sigmoid(run_stack(packed["se"], cor.mean(dim=2).contiguous())).view(G, D)
-    end = torch.sigmoid(run_stack(packed["se"], cor.mean(dim=3).contiguous())).view(G, P)
+    def link_branch():
+        logits = run_stack(packed["link"], cor.view(G, -1, P * D)).view(G, P, D)
+        col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)   # softmax over predecessors
+        return (torch.softmax(logits, dim=2) + col) / 2, logits
+
+    (link, logits), start, end = runtime.parallel(
+        link_branch,
+        lambda: torch.sigmoid(run_stack(packed["se"], cor.mean(dim=2).contiguous())).view(G, D),
+        lambda: torch.sigmoid(run_stack(packed["se"], cor.mean(dim=3).contiguous())).view(G, P))
     return link, start, end, logits
 
 

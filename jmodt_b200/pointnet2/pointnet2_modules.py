@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
-from .. import tc
+from .. import runtime, tc
 
 
 def _use_fused(module: nn.Module) -> bool:
@@ -118,23 +118,24 @@ class _PointnetSAModuleBase(nn.Module):
 
     def _forward_fused(self, xyz, features, new_xyz, nbr):
         packed = getattr(self, "_packed", None) or self.pack()
-        outs = []
         if features is not None:
             features = features.contiguous()
-        feats_pm = None      # point-major copy of the features, shared by the scales that run as one kernel
-        for gi, (grouper, layers) in enumerate(zip(self.groupers, packed)):
+        fuse = getattr(self, "fuse_chain", True)
+        c_in = 0 if features is None else features.shape[1]
+        one_kernel = [isinstance(g, pointnet2_utils.QueryAndGroup) and fuse and
+                      tc.sa_fused_supported(layers, c_in, new_xyz.shape[1], g.nsample)
+                      for g, layers in zip(self.groupers, packed)]
+        # point-major copy of the features, shared by the scales that run as one kernel
+        feats_pm = features.transpose(1, 2).contiguous() if (features is not None and any(one_kernel)) else None
+
+        def scale(gi):
+            grouper, layers = self.groupers[gi], packed[gi]
             if isinstance(grouper, pointnet2_utils.QueryAndGroup):
                 assert grouper.use_xyz, "the fused path groups xyz with the features"
                 idx = nbr[gi]
                 pool = grouper.nsample
-                c_in = 0 if features is None else features.shape[1]
-                if getattr(self, "fuse_chain", True) and \
-                        tc.sa_fused_supported(layers, c_in, new_xyz.shape[1], grouper.nsample):
-                    if features is not None and feats_pm is None:
-                        feats_pm = features.transpose(1, 2).contiguous()
-                    outs.append(tc.sa_fused(layers, xyz, feats_pm, idx, new_xyz,
-                                            feats_point_major=True))                 # whole layer in one kernel
-                    continue
+                if one_kernel[gi]:
+                    return tc.sa_fused(layers, xyz, feats_pm, idx, new_xyz, feats_point_major=True)   # whole layer in one kernel
                 h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
                                            pool=pool if len(layers) == 1 else 0)
             else:  # GroupAll
@@ -144,7 +145,10 @@ class _PointnetSAModuleBase(nn.Module):
                                            pool=pool if len(layers) == 1 else 0)
             for i, layer in enumerate(layers[1:]):
                 h = tc.mlp_layer(layer, h, pool=pool if i == len(layers) - 2 else 0)
-            outs.append(h)
+            return h
+
+        # the scales of a level are independent chains of small launches: run them on forked streams
+        outs = runtime.parallel(*[(lambda gi=gi: scale(gi)) for gi in range(len(self.groupers))])
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
 

@@ -11,6 +11,7 @@ captured graph the events are *external* event-record nodes, so they are re-reco
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict
 
 import torch
@@ -104,3 +105,49 @@ class CapturedPath:
     def replay(self):
         self.graph.replay()
         return self.outputs
+
+
+# ---- independent branches on forked streams -------------------------------------------------------------------------
+branch_parallel = os.environ.get("JMB_BRANCH_PARALLEL", "1") != "0"      # False: branches run one after the other on the caller's stream
+_branch_streams: dict = {}
+
+
+def parallel(*fns):
+    """Run independent closures concurrently: fns[0] on the caller's stream, the others on forked side streams that
+    join before returning (inside a CUDA-graph capture the fork/join becomes graph edges).  The hot path is a chain
+    of small launches that each leave most of the 148 SMs idle or sit in their prologue / tail for a third of their
+    run time — the two scales of a multi-scale set-abstraction level, the three input projections of the LI-Fusion
+    attention, the cls / reg heads — so sibling launches overlap.  Tensors produced on a side stream are handed to
+    the caller's stream with record_stream()."""
+    if len(fns) == 1 or not branch_parallel:
+        return [f() for f in fns]
+    main = torch.cuda.current_stream()
+    dev = main.device
+    pool = _branch_streams.setdefault(dev, [])
+    while len(pool) < len(fns) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    outs = [None] * len(fns)
+    joins = []
+    for i, f in enumerate(fns[1:], 1):
+        s = pool[i - 1]
+        s.wait_event(fork)
+        with torch.cuda.stream(s):
+            outs[i] = f()
+            ev = torch.cuda.Event()
+            ev.record(s)
+        joins.append(ev)
+    outs[0] = fns[0]()
+    for ev in joins:
+        main.wait_event(ev)
+
+    def hand_over(o):
+        if isinstance(o, torch.Tensor):
+            o.record_stream(main)
+        elif isinstance(o, (list, tuple)):
+            for x in o:
+                hand_over(x)
+    for o in outs[1:]:
+        hand_over(o)
+    return outs
