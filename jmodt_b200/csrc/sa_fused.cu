@@ -144,10 +144,10 @@ sa_fused_kernel(const SaFusedParams p) {
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int h = 0; h < NP; ++h) {
-            mbar_init(&s_x1_full[h], PART);
+            mbar_init(&s_x1_full[h], PART / 32);              // one arrival per warp (elected lane after __syncwarp)
             mbar_init(&s_x1_free[h], 1);
             mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], Cfg::EPI_PER_PART);
+            mbar_init(&s_epi_done[h], Cfg::EPI_PER_PART / 32);
         }
         mbar_init(&s_w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,7 +299,8 @@ sa_fused_kernel(const SaFusedParams p) {
                 SF_ESTAMP(40 + layer);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&s_epi_done[h]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_epi_done[h]);
                 SF_ESTAMP(50 + layer);
             }
             for (int mt = 0; mt < p.Mt3; ++mt) {
@@ -308,7 +309,8 @@ sa_fused_kernel(const SaFusedParams p) {
                 if (ROWS) epilogue_rows(tile);
                 else if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools all columns of the part
                 tc_fence_before();
-                mbar_arrive(&s_epi_done[h]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_epi_done[h]);
             }
         }
     } else if (warp < SF_ISSUER_WARP) {
@@ -360,7 +362,8 @@ sa_fused_kernel(const SaFusedParams p) {
                     }
             }
             fence_proxy_async();
-            mbar_arrive(&s_x1_full[h]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_x1_full[h]);
         };
 
         uint32_t tile_ctr = 0;

@@ -19,20 +19,26 @@
 // feats[k-3][idx[n]] otherwise — the grouped tensor is never materialised.
 //
 // Structure (v3): one persistent CTA per SM, 18 warps, every hand-off through mbarriers.
-//   warp 17      loader: claims tiles from a global atomic counter (dynamic scheduling: a CTA that shares its SM
-//                with another stream's kernel simply claims fewer tiles), publishes them in a shared-memory tile
-//                ring, and issues all bulk async copies: one 16 KB weight chunk image per K chunk and — for dense
-//                X — the raw fp32 rows of the chunk (32 rows x 512 B, one cp.async.bulk per row) into a 4-stage
-//                ring, so ~64 KB of loads are in flight per SM without holding registers.
-//   warps 0-7    converters: raw fp32 chunk (shared memory) -> bf16 hi/lo split -> MN-major core-matrix images;
-//                in gather mode they load through the neighbour index themselves (register double-buffer).
+//   warp 17      scheduler: claims tiles from a global atomic counter (dynamic scheduling: a CTA that shares its SM
+//                with another stream's kernel simply claims fewer tiles) and publishes them in a shared-memory tile
+//                ring;  warp 18 streams the weights: one 16 KB cp.async.bulk chunk image per K chunk.
+//   warps 0-7    converters: raw fp32 chunk (shared memory) -> bf16 hi/lo split -> MN-major core-matrix images.
+//                Dense X is staged by the converters themselves with 16-byte cp.async (LDGSTS) three chunks ahead into
+//                a 4-stage raw ring whose mbarrier counts the copies (cp.async.mbarrier.arrive.noinc): 48 KB of loads
+//                in flight per SM, no registers held.  (v3 staged each 512-byte row with its own cp.async.bulk and
+//                wrote each output row with another: ~780 bulk requests per tile at ~30 ns each through the SM's one
+//                TMA unit — 23 us per 128x128x512 tile, ncu tensor pipe 15 %.  Bulk copies are now only used where one
+//                request moves 16 KB.)  In gather mode they load through the neighbour index (register double-buffer).
 //   warp 16      MMA issuer: six tcgen05.mma (128x128x16) per 32-deep K chunk into a double-buffered accumulator.
-//   warps 8-15   epilogue: tcgen05.ld -> bias -> ReLU -> (a) staged in shared memory, written back with one
-//                cp.async.bulk per (row, 64-column half): 256 B contiguous bursts instead of 32 scattered 16 B
-//                stores per instruction; (b) max-pool over nsample in registers; (c) point-major rows.
+//   warps 8-15   epilogue: tcgen05.ld -> bias -> ReLU -> (a) staged in shared memory and written back by the same warp
+//                as 256-byte row segments (16 lanes x 16 B per row, two rows per store instruction);
+//                (b) max-pool over nsample in registers; (c) point-major rows.
 // Tiles narrower than 128 columns (N = 8..64 per group, e.g. GroupAll over 32 points) pack 128/N groups into one
 // tile, so the tensor cores and the converters never work on padding columns.
 #include "tc_common.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace jmb {
 
@@ -62,7 +68,7 @@ struct TcGemmParams {
     long long col_tiles;          // G * Nt (P == 1) or ceil(G / P)
     int mode;                     // 0 dense, 1 grouped gather
     int use_raw;                  // dense X staged by bulk copies (needs 16-byte aligned rows)
-    int bulk_out;                 // dense Y written by bulk copies (needs 16-byte aligned rows)
+    int bulk_out;                 // dense Y staged in shared memory and written as 16-byte pieces (needs 16-byte aligned rows)
     const float *x;               // dense: (G, K, N)   gather: feats (G, K-3, n_pts)
     long long x_group_stride;     // elements
     int x_row_stride;             // elements between consecutive k rows
@@ -76,20 +82,19 @@ struct TcGemmParams {
     float *y;
     long long y_group_stride;     // elements between consecutive groups of y
     int *counter, *done;          // dynamic tile scheduler (reset by the last CTA to leave)
+    long long *dbg;               // optional clock64 timeline of CTA 0 (JMB_TC_DEBUG=1): [0..511] MMA issuer, [512..] converter warp 0
 };
 
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
-                 : "memory");
-}
+#define TC_STAMP(buf, idx, tag) do { if ((buf) && (idx) < 500) { (buf)[(idx)++] = (tag); (buf)[(idx)++] = clock64(); } } while (0)
 
 // column c (0..127) of column tile ct -> group g and column n inside the group
-__device__ __forceinline__ void tc_col(const TcGemmParams &p, long long ct, int c, int &g, int &n) {
+__device__ __forceinline__ void tc_col(const TcGemmParams &p, long long ct64, int c, int &g, int &n) {
+    const int ct = (int)ct64;               // col_tiles * Mt < 2^30 (checked by the launcher): 32-bit division
     if (p.P == 1) {
-        g = (int)(ct / p.Nt);
-        n = (int)(ct % p.Nt) * TC_BN + c;
+        g = ct / p.Nt;
+        n = (ct - g * p.Nt) * TC_BN + c;
     } else {
-        g = (int)ct * p.P + (c >> p.Nshift);
+        g = ct * p.P + (c >> p.Nshift);
         n = c & (p.N - 1);
     }
 }
@@ -109,10 +114,12 @@ tc_gemm_kernel(const TcGemmParams p) {
     constexpr int N_CONSUMER_WARPS = TC_CONV_WARPS + TC_EPI_WARPS + 2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], TC_CONV_WARPS * 32); mbar_init(&s_xempty[s], 1); }
+        // one arrival per WARP (elected lane after __syncwarp): 256 per-thread arrivals on one shared-memory barrier per
+        // K chunk serialise and were the bottleneck of the whole pipeline (~2 900 cycles per chunk, ncu: tensor pipe 15 %)
+        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], TC_CONV_WARPS); mbar_init(&s_xempty[s], 1); }
         for (int s = 0; s < TC_WSTAGES; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_wempty[s], 1); }
-        for (int s = 0; s < TC_RSTAGES; ++s) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], TC_CONV_WARPS * 32); }
-        for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], TC_EPI_WARPS * 32); }
+        for (int s = 0; s < TC_RSTAGES; ++s) { mbar_init(&s_rfull[s], TC_CONV_WARPS * 32); mbar_init(&s_rempty[s], TC_CONV_WARPS); }
+        for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], TC_EPI_WARPS); }
         for (int s = 0; s < TC_TSLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], N_CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -143,7 +150,6 @@ tc_gemm_kernel(const TcGemmParams p) {
 
     if (warp == W_LOAD) {
         // =============================== loader: tile scheduler + all bulk copies ===============================
-        uint32_t rctr = 0;
         auto fetch = [&]() -> int {
             int t = -1;
             if (lane == 0) {
@@ -166,29 +172,6 @@ tc_gemm_kernel(const TcGemmParams p) {
         while (cur >= 0) {
             const int nxt = fetch();     // published one tile ahead: the converters prefetch across tile boundaries
             publish(nxt);
-            const long long ct = cur / p.Mt;
-            int g0, n0;
-            tc_col(p, ct, 0, g0, n0);
-            const int gv = p.P == 1 ? 1 : min(p.P, p.G - g0);                // valid groups in the tile
-            const int cols = p.P == 1 ? min(TC_BN, p.N - n0) : p.N;          // valid columns per group piece
-            if (p.use_raw) {
-                for (int kc = 0; kc < p.Kc; ++kc) {
-                    const int s = rctr % TC_RSTAGES;
-                    const int rows = min(TC_BK, p.K - kc * TC_BK);
-                    if (lane == 0) {
-                        mbar_wait(&s_rempty[s], ((rctr / TC_RSTAGES) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&s_rfull[s], (uint32_t)(rows * gv * cols * 4));
-                    }
-                    __syncwarp();
-                    if (lane < rows) {
-                        uint8_t *dst = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)lane * TC_RAW_ROW;
-                        const float *src = p.x + (size_t)g0 * p.x_group_stride + (size_t)(kc * TC_BK + lane) * p.x_row_stride + n0;
-                        for (int gi = 0; gi < gv; ++gi)
-                            bulk_g2s(dst + (size_t)gi * cols * 4, src + (size_t)gi * p.x_group_stride, (uint32_t)cols * 4, &s_rfull[s]);
-                    }
-                    ++rctr;
-                }
-            }
             cur = nxt;
         }
     } else if (warp == W_WLOAD) {
@@ -218,10 +201,13 @@ tc_gemm_kernel(const TcGemmParams p) {
         const int ng = (t >> 3) & 15;        // group of 8 columns inside the tile
         const int kh = t >> 7;               // this thread converts k blocks kh and kh + 2 of the chunk
         uint32_t xctr = 0, rctr = 0;
+        long long *cdbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
+        int cdi = 0;
 
-        auto store_images = [&](const float (&v)[2][8]) {
+        auto store_images = [&](const float (&v)[2][8], uint64_t *release = nullptr) {
             const int s = xctr % TC_XSTAGES;
             mbar_wait(&s_xempty[s], ((xctr / TC_XSTAGES) & 1) ^ 1);
+            TC_STAMP(cdbg, cdi, 12);
             uint8_t *xhi = tc_smem + TC_OFF_X + (size_t)s * TC_CHUNK, *xlo = xhi + TC_IMG;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -234,35 +220,75 @@ tc_gemm_kernel(const TcGemmParams p) {
                 *reinterpret_cast<uint4 *>(xhi + off) = h;
                 *reinterpret_cast<uint4 *>(xlo + off) = l;
             }
-            fence_proxy_async();
-            mbar_arrive(&s_xfull[s]);
+            fence_proxy_async();        // this thread's image rows -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&s_xfull[s]);
+                if (release) mbar_arrive(release);     // the raw stage the values came from is free again
+            }
             ++xctr;
         };
 
         if (p.use_raw) {
+            // ---- producer side: this thread's four 16-byte pieces of raw chunk (tile, kc) -> stage ictr % RSTAGES ----
+            int ig0 = 0, in0 = 0;        // group / first column of the tile being staged (64-bit divisions: once per tile)
+            auto issue_raw = [&](int kc, uint32_t ictr) {
+                const int s = ictr % TC_RSTAGES;
+                mbar_wait(&s_rempty[s], ((ictr / TC_RSTAGES) & 1) ^ 1);     // every converter warp has read the stage
+                TC_STAMP(cdbg, cdi, 15);
+                uint8_t *stage = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int piece = t + j * (TC_CONV_WARPS * 32);
+                    const int r = piece >> 5, c4 = (piece & 31) * 4;           // row of the chunk, first of 4 columns
+                    const int g = p.P == 1 ? ig0 : ig0 + (c4 >> p.Nshift);
+                    const int n = p.P == 1 ? in0 + c4 : (c4 & (p.N - 1));
+                    const int k = kc * TC_BK + r;
+                    const bool ok = k < p.K && g < p.G && n < p.N;             // N % 4 == 0: a piece is all in or all out
+                    const float *src = ok ? p.x + (size_t)g * p.x_group_stride + (size_t)k * p.x_row_stride + n : p.x;
+                    const uint32_t dst = smem_u32(stage + (size_t)r * TC_RAW_ROW + (size_t)c4 * 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                }
+                TC_STAMP(cdbg, cdi, 16);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_rfull[s])) : "memory");
+            };
+            constexpr int LOOKAHEAD = TC_RSTAGES - 1;
+            uint32_t ictr = 0, itile = tctr;
+            int icur = ring_read(itile), ikc = 0;
+            if (icur >= 0) tc_col(p, icur / p.Mt, 0, ig0, in0);
+            auto advance_issue = [&]() {
+                if (icur < 0) return;
+                issue_raw(ikc, ictr++);
+                if (++ikc == p.Kc) {
+                    ikc = 0;
+                    icur = ring_read(++itile);
+                    if (icur >= 0) tc_col(p, icur / p.Mt, 0, ig0, in0);
+                }
+            };
+            for (int i = 0; i < LOOKAHEAD; ++i) advance_issue();
+
             int cur = ring_read(tctr);
             while (cur >= 0) {
                 for (int kc = 0; kc < p.Kc; ++kc) {
                     const int s = rctr % TC_RSTAGES;
+                    TC_STAMP(cdbg, cdi, 10);
                     mbar_wait(&s_rfull[s], (rctr / TC_RSTAGES) & 1);
+                    TC_STAMP(cdbg, cdi, 11);
                     float v[2][8];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int row = (kh + 2 * q) * 8 + kk;
-                        if (kc * TC_BK + row < p.K) {
-                            const float4 *src = reinterpret_cast<const float4 *>(
-                                tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)row * TC_RAW_ROW + ng * 32);
-                            const float4 a4 = src[0], b4 = src[1];
-                            v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
-                            v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
-                        }
+                        const float4 *src = reinterpret_cast<const float4 *>(
+                            tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)row * TC_RAW_ROW + ng * 32);
+                        const float4 a4 = src[0], b4 = src[1];      // rows >= K and columns >= N were zero-filled by the copy
+                        v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                        v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
                     }
-                    store_images(v);                 // consumes v, so the raw stage can be handed back afterwards
-                    mbar_arrive(&s_rempty[s]);
+                    store_images(v, &s_rempty[s]);   // consumes v, so the raw stage is handed back with the same arrival
+                    TC_STAMP(cdbg, cdi, 13);
                     ++rctr;
+                    advance_issue();
+                    TC_STAMP(cdbg, cdi, 14);
                 }
                 ring_release(tctr);
                 ++tctr;
@@ -375,8 +401,7 @@ tc_gemm_kernel(const TcGemmParams p) {
             const bool whole = (p.out_mode == 1 && p.pool > 64);
             const int c_begin = whole ? 0 : half * 64;
             const int c_end = whole ? (half == 0 ? TC_BN : 0) : c_begin + 64;
-            if (p.out_mode == 0 && p.bulk_out)
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging rows of the previous tile are free again
+            if (p.out_mode == 0 && p.bulk_out) __syncwarp();     // this warp's staging rows of the previous tile have been read
             mbar_wait(&s_acc_full[buf], (tile_ctr / TC_ACC_BUFS) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TC_BN;
@@ -385,9 +410,10 @@ tc_gemm_kernel(const TcGemmParams p) {
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
-                if (c0 + 32 >= c_end) {     // last read of this accumulator by this thread: hand it back to the MMA warp early
+                if (c0 + 32 >= c_end) {     // last read of this accumulator by this warp: hand it back to the MMA warp early
                     tc_fence_before();
-                    mbar_arrive(&s_acc_empty[buf]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_acc_empty[buf]);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -471,30 +497,25 @@ tc_gemm_kernel(const TcGemmParams p) {
             }
             if (whole && half != 0) {       // nothing read: still hand the accumulator back
                 tc_fence_before();
-                mbar_arrive(&s_acc_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_acc_empty[buf]);
             }
             if (p.out_mode == 0 && p.bulk_out) {
-                fence_proxy_async();        // this thread's staged row -> visible to the bulk-copy engine
-                if (m < p.M) {
-                    if (p.P == 1) {
-                        int g, n;
-                        tc_col(p, ct, c_begin, g, n);
-                        const int cnt = min(64, p.N - n);
-                        if (cnt > 0)
-                            bulk_s2g(p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + n, stage_row + (size_t)c_begin * 4,
-                                     (uint32_t)cnt * 4);
-                    } else {
-                        const int piece = min(p.N, 64);
-                        for (int c = c_begin; c < c_end; c += piece) {
-                            int g, n;
-                            tc_col(p, ct, c, g, n);
-                            if (g < p.G)
-                                bulk_s2g(p.y + (size_t)g * p.y_group_stride + (size_t)m * p.N + n, stage_row + (size_t)c * 4,
-                                         (uint32_t)piece * 4);
-                        }
+                // the warp's 32 staged rows x 64 columns go out as 256-byte row segments: lanes 0-15 one row, 16-31 the next
+                __syncwarp();
+                const int sub = lane >> 4, c4 = c_begin + (lane & 15) * 4;
+                int g, n;
+                tc_col(p, ct, c4, g, n);
+                if (g < p.G && n < p.N) {
+                    float *ybase = p.y + (size_t)g * p.y_group_stride + n;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; rr += 2) {
+                        const int row = quad * 32 + rr + sub, mm = mt * TC_BM + row;
+                        if (mm < p.M)
+                            *reinterpret_cast<float4 *>(ybase + (size_t)mm * p.N) = *reinterpret_cast<const float4 *>(
+                                tc_smem + TC_OFF_OUT + (size_t)row * TC_RAW_ROW + (size_t)c4 * 4);
                     }
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             ++tile_ctr;
             ring_release(tctr);
@@ -502,22 +523,27 @@ tc_gemm_kernel(const TcGemmParams p) {
             cur = ring_read(tctr);
         }
         ring_release(tctr);
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (warp == W_MMA) {
         // =============================== MMA issuer ===============================
         constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4;
         uint32_t xctr = 0, wctr = 0, tile_ctr = 0;
+        long long *mdbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+        int mdi = 0;
         int cur = ring_read(tctr);
         while (cur >= 0) {
             if (lane == 0) {
                 const int buf = tile_ctr % TC_ACC_BUFS;
+                TC_STAMP(mdbg, mdi, 0);
                 mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
                 for (int kc = 0; kc < p.Kc; ++kc, ++xctr, ++wctr) {
                     const int sx = xctr % TC_XSTAGES, sw = wctr % TC_WSTAGES;
+                    TC_STAMP(mdbg, mdi, 1);
                     mbar_wait(&s_wfull[sw], (wctr / TC_WSTAGES) & 1);
+                    TC_STAMP(mdbg, mdi, 2);
                     mbar_wait(&s_xfull[sx], (xctr / TC_XSTAGES) & 1);
+                    TC_STAMP(mdbg, mdi, 3);
                     tc_fence_after();
                     const uint64_t xd = make_smem_desc(smem_u32(tc_smem + TC_OFF_X + (size_t)sx * TC_CHUNK));
                     const uint64_t wd = make_smem_desc(smem_u32(tc_smem + TC_OFF_W + (size_t)sw * TC_CHUNK));
@@ -529,6 +555,7 @@ tc_gemm_kernel(const TcGemmParams p) {
                     umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
                     umma_commit(&s_xempty[sx]);
                     umma_commit(&s_wempty[sw]);
+                    TC_STAMP(mdbg, mdi, 4);
                 }
                 umma_commit(&s_acc_full[buf]);
             }
@@ -622,6 +649,14 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.counter = sched + 2 * slot;
     p.done = sched + 2 * slot + 1;
 
+    static long long *dbg_buf = nullptr;          // JMB_TC_DEBUG=1: CTA 0 records a clock64() timeline (profiling aid)
+    static int dbg_on = -1;
+    if (dbg_on < 0) {
+        const char *e = getenv("JMB_TC_DEBUG");
+        dbg_on = (e && e[0] == '1') ? 1 : 0;
+        if (dbg_on) { cudaMalloc(&dbg_buf, 1024 * sizeof(long long)); cudaMemset(dbg_buf, 0, 1024 * sizeof(long long)); }
+    }
+    p.dbg = dbg_buf;
     const size_t smem = (size_t)TC_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
@@ -630,5 +665,17 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     }
     const int grid = (int)(tiles < (long long)sms[dev] ? tiles : (long long)sms[dev]);
     tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (dbg_on) {
+        long long hbuf[1024];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        for (int part = 0; part < 2; ++part) {
+            const long long *b = hbuf + part * 512;
+            fprintf(stderr, "[tc_gemm timeline %s M=%d K=%d N=%d] ", part ? "converter warp 0" : "mma issuer", M, K, N);
+            for (int i = 0; i + 1 < 500 && (b[i] || b[i + 1]); i += 2) fprintf(stderr, "%lld:%lld ", b[i], b[i + 1] - hbuf[1]);
+            fprintf(stderr, "\n");
+        }
+        cudaMemset(dbg_buf, 0, 1024 * sizeof(long long));
+    }
     return check_launch("tc_mlp_layer");
 }
