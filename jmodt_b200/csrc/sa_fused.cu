@@ -231,8 +231,8 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         auto epilogue_pool = [&](long long tile, int mt) {
-            const int nt = (int)(tile % Nt);
-            const int g = (int)(tile / Nt);
+            const int g = (int)tile / Nt;              // total_tiles < 2^31 (checked by the launcher): 32-bit division
+            const int nt = (int)tile - g * Nt;
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
             const int c3 = p.C3, ch = mt * TC_BM + m, ctr0 = (nt * TC_BN + h * PART) / p.nsample;
             const bool live = ch < c3;     // zero-padded rows of a layer narrower than the 128-row MMA tile are not stored
@@ -322,8 +322,8 @@ sa_fused_kernel(const SaFusedParams p) {
         // channels in flight), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
         // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots: conflict-free).
         auto produce_x1 = [&](long long tile) {
-            const int nt = (int)(tile % Nt);
-            const int g = (int)(tile / Nt);
+            const int g = (int)tile / Nt;              // total_tiles < 2^31 (checked by the launcher): 32-bit division
+            const int nt = (int)tile - g * Nt;
             const int n = nt * TC_BN + h * PART + nl;
             const int pi = ROWS ? 0 : __ldg(p.idx + (size_t)g * N + n);
             const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + h * PART + nl) * p.row_pitch
@@ -527,6 +527,7 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     }
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
+    JMB_REQUIRE(tiles < (1LL << 31), "sa_fused: too many tiles");
     const int grid = (int)(tiles < sms ? tiles : sms);
     if (sf_parts() == 4) {
         if (nsample > SfCfg<4>::PART)     // pooling windows span two parts: they combine with atomicMax on a zeroed output
@@ -579,6 +580,7 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
         JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
     }
     const long long tiles = rows / TC_BN;
+    JMB_REQUIRE(tiles < (1LL << 31), "rcnn_input_fused: too many rows");
     const int grid = (int)(tiles < sms ? tiles : sms);
     if (sf_parts() == 4) sa_fused_kernel<true, 4><<<grid, SfCfg<4>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
     else sa_fused_kernel<true, 2><<<grid, SfCfg<2>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
