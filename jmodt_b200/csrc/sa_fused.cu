@@ -100,7 +100,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 
 // Row m of a packed 128 x 128 weight block (4 chunk images of 128 x 32) -> 64 TMEM columns (bf16 pairs) of lane m.
 __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_block, int part /*0 hi, 1 lo*/, int m,
-                                                    uint32_t taddr) {
+                                                    uint32_t taddr, int nchunks = 4 /* chunks present; the rest is zero */) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {        // 32 columns (two K chunks) per tcgen05.st
         uint32_t r[32];
@@ -110,7 +110,9 @@ __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_b
             const uint8_t *img = reinterpret_cast<const uint8_t *>(wpack_block) + (size_t)kc * SF_CHUNK + (size_t)part * TC_IMG;
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + k8 * TC_LBO + (m >> 3) * TC_SBO + (m & 7) * 16));
+                const uint4 v = kc < nchunks
+                                    ? __ldg(reinterpret_cast<const uint4 *>(img + k8 * TC_LBO + (m >> 3) * TC_SBO + (m & 7) * 16))
+                                    : make_uint4(0u, 0u, 0u, 0u);
                 r[cc * 16 + k8 * 4 + 0] = v.x; r[cc * 16 + k8 * 4 + 1] = v.y;
                 r[cc * 16 + k8 * 4 + 2] = v.z; r[cc * 16 + k8 * 4 + 3] = v.w;
             }
@@ -184,6 +186,14 @@ sa_fused_kernel(const SaFusedParams p) {
             const __nv_bfloat16 *blk = p.w3 + (size_t)mt * 4 * (SF_CHUNK / 2);
             weight_rows_to_tmem(blk, 0, m, lane_base + SF_TMEM_W3 + mt * 128);
             weight_rows_to_tmem(blk, 1, m, lane_base + SF_TMEM_W3 + mt * 128 + 64);
+        }
+        if (!ROWS && p.w3_blocks == 1) {
+            // one W3 block leaves 128 tensor-memory columns free: the first 128 input columns of W1 go there too, so
+            // layer 1 runs in TS mode like layers 2 and 3 (an SS MMA re-reads its 4 KB A operand from shared memory for
+            // every 64 columns, which made layer 1 — a third of the MMAs — half of the MMA issue time)
+            const int n1 = p.Kc1 < 4 ? p.Kc1 : 4;
+            weight_rows_to_tmem(p.w1, 0, m, lane_base + SF_TMEM_W3 + 128, n1);
+            weight_rows_to_tmem(p.w1, 1, m, lane_base + SF_TMEM_W3 + 128 + 64, n1);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -403,7 +413,6 @@ sa_fused_kernel(const SaFusedParams p) {
             const uint64_t x1_desc = make_smem_desc(smem_u32(s_x1) + h * Cfg::PART_OFF);
             const uint64_t act_desc = make_smem_desc(smem_u32(s_act) + h * Cfg::PART_OFF);
             constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4;
-            const int last_steps = (kmax16 - (p.Kc1 - 1) * TC_BK) >= 32 ? 2 : 1;
             long long *dbg = (p.dbg && blockIdx.x == 0 && h == 0) ? p.dbg : nullptr;
             int di = 0;
 #define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
@@ -421,16 +430,23 @@ sa_fused_kernel(const SaFusedParams p) {
                     umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc + D_IMG, xd, 1);
                     umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc, xd + D_IMG, 1);
                 }
-                for (int c = 0; !ROWS && c < p.Kc1; ++c) {
-                    const int steps = c == p.Kc1 - 1 ? last_steps : 2;
-                    const uint64_t wd = w1_desc + (uint64_t)c * D_CHUNK, xd = x1_desc + (uint64_t)c * D_CHUNK;
-                    umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd, c != 0);
-                    umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_IMG, xd, 1);
-                    umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd + D_IMG, 1);
-                    if (steps == 2) {
-                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16, xd + D_K16, 1);
-                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
-                        umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
+                if (!ROWS) {
+                    const int steps_total = kmax16 / 16;
+                    const int ts_steps = p.w3_blocks == 1 ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
+                    for (int st = 0; st < steps_total; ++st) {
+                        const uint64_t off = (uint64_t)(st >> 1) * D_CHUNK + (uint64_t)(st & 1) * D_K16;
+                        const uint64_t xd = x1_desc + off;
+                        if (st < ts_steps) {
+                            const uint32_t ahi = tmem_base + SF_TMEM_W3 + 128 + (uint32_t)st * 8;
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd, st != 0);
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi + 64, xd, 1);
+                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+                        } else {
+                            const uint64_t wd = w1_desc + off;
+                            umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd, st != 0);
+                            umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_IMG, xd, 1);
+                            umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd + D_IMG, 1);
+                        }
                     }
                 }
                 if (!ROWS) umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile

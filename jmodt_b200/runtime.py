@@ -119,7 +119,7 @@ def parallel(*fns):
     run time — the two scales of a multi-scale set-abstraction level, the three input projections of the LI-Fusion
     attention, the cls / reg heads — so sibling launches overlap.  Tensors produced on a side stream are handed to
     the caller's stream with record_stream()."""
-    if len(fns) == 1 or not branch_parallel:
+    if len(fns) == 1 or not branch_parallel or not torch.cuda.is_available():
         return [f() for f in fns]
     main = torch.cuda.current_stream()
     dev = main.device
