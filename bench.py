@@ -270,6 +270,11 @@ def run_b200(args):
 
     from jmodt_b200 import _lib, tc
     _lib.lib()  # fail loudly if the CUDA library is missing: there is no fallback
+    # stdout carries exactly ONE JSON line: anything libraries print while the run is in progress (NCCL's version banner
+    # goes to stdout) is sent to stderr instead, and the descriptor is restored just before the result is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -481,8 +486,11 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    os.close(stdout_fd)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
