@@ -96,7 +96,7 @@ launch_count = 0  # kernels enqueued through the C ABI (bench.py reports it as g
 
 def check(rc: int, what: str) -> None:
     global launch_count
-    launch_count += {"nms": 2, "proposal_layer": 4}.get(what, 1)   # nms = mask + sweep kernels, proposal = 4
+    launch_count += {"nms": 2, "proposal_layer": 3}.get(what, 1)   # nms = mask + sweep kernels, proposal = 3
     if rc != 0:
         msg = lib().jmb_last_error().decode(errors="replace")
         raise JmodtB200Error(f"{what} failed (code {rc}): {msg}")

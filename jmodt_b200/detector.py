@@ -423,7 +423,7 @@ class ProposalLayer(nn.Module):
         return ret_bbox3d, ret_scores
 
     def _forward_batched(self, scores, proposals, order):
-        """Whole batch in four kernels, no host synchronisation (csrc/proposal.cu)."""
+        """Whole batch in three kernels, no host synchronisation (csrc/proposal.cu)."""
         cfg = self.cfg
         B, N = scores.shape
         L = _lib.lib()

@@ -172,20 +172,27 @@ def test_rpn_backbone_vs_cpu_oracle(cuda, cref):
 
 @pytest.mark.gpu
 def test_batched_proposal_layer_equals_reference_loop(cuda):
-    """csrc/proposal.cu (4 kernels, no host sync) vs the reference's per-frame / per-bin procedure
-    (proposal_layer.py:36-121) executed with this package's single-set NMS: identical boxes and scores."""
+    """csrc/proposal.cu (3 kernels, no host sync, quota-bounded greedy NMS) vs the reference's per-frame / per-bin
+    procedure (proposal_layer.py:36-121) executed with this package's single-set mask + sweep NMS: identical boxes and
+    scores — including heavily overlapping proposals (deep scans, quota not reached) and rotated NMS."""
     from jmodt_b200.detector import ProposalLayer, RpnConfig
     from jmodt_b200.synth import make_batch
     g = torch.Generator().manual_seed(9)
-    for case, post in [("both bins", 128), ("far bin empty", 100), ("near bin empty", 64)]:
+    for case, post in [("both bins", 128), ("far bin empty", 100), ("near bin empty", 64), ("dense overlaps", 128),
+                       ("dense overlaps rotated", 128), ("everything suppressed", 512)]:
         cfg = RpnConfig(post_nms_top_n=post)
+        if case.startswith("dense"):
+            cfg.nms_thresh = 0.3
+            cfg.nms_type = "rotate" if "rotated" in case else "normal"
+        if case == "everything suppressed":
+            cfg.nms_thresh = 0.01
         B, N = 3, 16384
         xyz = torch.from_numpy(make_batch(70, B, with_image=False)["pts"]).to(cuda)
         if case == "far bin empty":
             xyz[..., 2] = xyz[..., 2].clamp(max=35.0)
         if case == "near bin empty":
             xyz[..., 2] = xyz[..., 2] * 0.3 + 45.0
-        reg = (torch.randn(B, N, 76, generator=g) * 0.5).to(cuda)
+        reg = (torch.randn(B, N, 76, generator=g) * (0.02 if ("dense" in case or "suppressed" in case) else 0.5)).to(cuda)
         scores = torch.randn(B, N, generator=g).to(cuda)
         layer = ProposalLayer(cfg=cfg)
         boxes_b, scores_b = layer(scores, reg, xyz)
