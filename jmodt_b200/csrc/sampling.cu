@@ -484,6 +484,8 @@ extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dat
                 case 5: return launch_fps_cluster<2, 256, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 6: return launch_fps_cluster<16, 64, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 7: return launch_fps_cluster<2, 128, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 8: return launch_fps<512, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 9: return launch_fps<256, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 default: break;
             }
         }

@@ -18,8 +18,8 @@ if len(sys.argv) > 1:
     e1.record(); torch.cuda.synchronize()
     print(f"cfg={os.environ.get('JMB_FPS_CFG','0')} b={b} n={n} m={m}: {e0.elapsed_time(e1)/5:.3f} ms  exact={ok}")
 else:
-    for (b, n, m) in [(8, 16384, 4096), (8, 4096, 1024), (1, 16384, 4096)]:
-        for cfg in range(0, 8):
+    for (b, n, m) in ([(8, 4096, 1024)] if os.environ.get('FPS_TUNE_L1') else [(8, 16384, 4096), (8, 4096, 1024), (1, 16384, 4096)]):
+        for cfg in (range(0, 10) if n == 4096 else range(0, 8)):
             env = dict(os.environ, JMB_FPS_CFG=str(cfg))
             r = subprocess.run([sys.executable, __file__, str(b), str(n), str(m)], env=env, capture_output=True, text=True)
             print(r.stdout.strip() or r.stderr.strip()[-300:])
