@@ -116,9 +116,10 @@ tc_gemm_kernel(const TcGemmParams p) {
     if (threadIdx.x == 0) {
         // one arrival per WARP (elected lane after __syncwarp): 256 per-thread arrivals on one shared-memory barrier per
         // K chunk serialise and were the bottleneck of the whole pipeline (~2 900 cycles per chunk, ncu: tensor pipe 15 %)
-        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], TC_CONV_WARPS); mbar_init(&s_xempty[s], 1); }
+        const int conv_arrivals = p.use_raw ? TC_CONV_WARPS / 2 : TC_CONV_WARPS;    // dense: one group of four warps per stage
+        for (int s = 0; s < TC_XSTAGES; ++s) { mbar_init(&s_xfull[s], conv_arrivals); mbar_init(&s_xempty[s], 1); }
         for (int s = 0; s < TC_WSTAGES; ++s) { mbar_init(&s_wfull[s], 1); mbar_init(&s_wempty[s], 1); }
-        for (int s = 0; s < TC_RSTAGES; ++s) { mbar_init(&s_rfull[s], TC_CONV_WARPS * 32); mbar_init(&s_rempty[s], TC_CONV_WARPS); }
+        for (int s = 0; s < TC_RSTAGES; ++s) { mbar_init(&s_rfull[s], TC_CONV_WARPS * 16); mbar_init(&s_rempty[s], TC_CONV_WARPS / 2); }
         for (int b = 0; b < TC_ACC_BUFS; ++b) { mbar_init(&s_acc_full[b], 1); mbar_init(&s_acc_empty[b], TC_EPI_WARPS); }
         for (int s = 0; s < TC_TSLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], N_CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -230,20 +231,42 @@ tc_gemm_kernel(const TcGemmParams p) {
         };
 
         if (p.use_raw) {
-            // ---- producer side: this thread's four 16-byte pieces of raw chunk (tile, kc) -> stage ictr % RSTAGES ----
-            int ig0 = 0, in0 = 0;        // group / first column of the tile being staged (64-bit divisions: once per tile)
-            auto issue_raw = [&](int kc, uint32_t ictr) {
-                const int s = ictr % TC_RSTAGES;
-                mbar_wait(&s_rempty[s], ((ictr / TC_RSTAGES) & 1) ^ 1);     // every converter warp has read the stage
+            // Dense X: the eight converter warps work as TWO independent groups of four; group g stages, converts and
+            // publishes the K chunks c = g, g+2, g+4, ... of the flattened (tile, chunk) sequence.  A chunk costs one
+            // warp ~1 250 cycles of mostly latency (five barrier round trips, the copy issue, the image stores); with
+            // the groups on alternate chunks those latencies overlap.  Raw stage c % 4 and image stage c % 2 belong to
+            // group c % 2 alone, so the groups never wait for each other.
+            const int grp = t >> 7, tl = t & 127;
+            const int rk = tl & 7, rg = tl >> 3;          // k row inside a block of 8, group of 8 columns inside the tile
+            struct Cur { uint32_t ring; int tile, kc, g0, n0; };
+            auto norm = [&](Cur &c, bool release) {       // move to the tile that holds chunk index c.kc
+                bool moved = false;
+                while (c.tile >= 0 && c.kc >= p.Kc) {
+                    c.kc -= p.Kc;
+                    if (release) ring_release(c.ring);
+                    c.tile = ring_read(++c.ring);
+                    moved = true;
+                }
+                if (moved && c.tile >= 0) tc_col(p, c.tile / p.Mt, 0, c.g0, c.n0);
+            };
+            auto open_cur = [&](Cur &c, bool release) {
+                c.ring = tctr; c.tile = ring_read(c.ring); c.kc = grp; c.g0 = c.n0 = 0;
+                if (c.tile >= 0) tc_col(p, c.tile / p.Mt, 0, c.g0, c.n0);
+                norm(c, release);
+            };
+            // this thread's eight 16-byte pieces of raw chunk number ci -> stage ci % RSTAGES
+            auto issue_raw = [&](const Cur &c, uint32_t ci) {
+                const int s = ci % TC_RSTAGES;
+                mbar_wait(&s_rempty[s], ((ci / TC_RSTAGES) & 1) ^ 1);       // the group's four warps have read the stage
                 TC_STAMP(cdbg, cdi, 15);
                 uint8_t *stage = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int piece = t + j * (TC_CONV_WARPS * 32);
+                for (int j = 0; j < 8; ++j) {
+                    const int piece = tl + j * 128;
                     const int r = piece >> 5, c4 = (piece & 31) * 4;           // row of the chunk, first of 4 columns
-                    const int g = p.P == 1 ? ig0 : ig0 + (c4 >> p.Nshift);
-                    const int n = p.P == 1 ? in0 + c4 : (c4 & (p.N - 1));
-                    const int k = kc * TC_BK + r;
+                    const int g = p.P == 1 ? c.g0 : c.g0 + (c4 >> p.Nshift);
+                    const int n = p.P == 1 ? c.n0 + c4 : (c4 & (p.N - 1));
+                    const int k = c.kc * TC_BK + r;
                     const bool ok = k < p.K && g < p.G && n < p.N;             // N % 4 == 0: a piece is all in or all out
                     const float *src = ok ? p.x + (size_t)g * p.x_group_stride + (size_t)k * p.x_row_stride + n : p.x;
                     const uint32_t dst = smem_u32(stage + (size_t)r * TC_RAW_ROW + (size_t)c4 * 4);
@@ -252,49 +275,63 @@ tc_gemm_kernel(const TcGemmParams p) {
                 TC_STAMP(cdbg, cdi, 16);
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_rfull[s])) : "memory");
             };
-            constexpr int LOOKAHEAD = TC_RSTAGES - 1;
-            uint32_t ictr = 0, itile = tctr;
-            int icur = ring_read(itile), ikc = 0;
-            if (icur >= 0) tc_col(p, icur / p.Mt, 0, ig0, in0);
-            auto advance_issue = [&]() {
-                if (icur < 0) return;
-                issue_raw(ikc, ictr++);
-                if (++ikc == p.Kc) {
-                    ikc = 0;
-                    icur = ring_read(++itile);
-                    if (icur >= 0) tc_col(p, icur / p.Mt, 0, ig0, in0);
-                }
-            };
-            for (int i = 0; i < LOOKAHEAD; ++i) advance_issue();
-
-            int cur = ring_read(tctr);
-            while (cur >= 0) {
-                for (int kc = 0; kc < p.Kc; ++kc) {
-                    const int s = rctr % TC_RSTAGES;
-                    TC_STAMP(cdbg, cdi, 10);
-                    mbar_wait(&s_rfull[s], (rctr / TC_RSTAGES) & 1);
-                    TC_STAMP(cdbg, cdi, 11);
-                    float v[2][8];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int row = (kh + 2 * q) * 8 + kk;
-                        const float4 *src = reinterpret_cast<const float4 *>(
-                            tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)row * TC_RAW_ROW + ng * 32);
-                        const float4 a4 = src[0], b4 = src[1];      // rows >= K and columns >= N were zero-filled by the copy
-                        v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
-                        v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
-                    }
-                    store_images(v, &s_rempty[s]);   // consumes v, so the raw stage is handed back with the same arrival
-                    TC_STAMP(cdbg, cdi, 13);
-                    ++rctr;
-                    advance_issue();
-                    TC_STAMP(cdbg, cdi, 14);
-                }
-                ring_release(tctr);
-                ++tctr;
-                cur = ring_read(tctr);
+            Cur ic, cc;
+            open_cur(ic, false);
+            open_cur(cc, true);
+            uint32_t ci = grp, c = grp;                    // chunk numbers of the next chunk to stage / to convert
+            for (int i = 0; i < 2 && ic.tile >= 0; ++i) {  // two chunks of the group in flight
+                issue_raw(ic, ci);
+                ci += 2; ic.kc += 2;
+                norm(ic, false);
             }
-            ring_release(tctr);
+            while (cc.tile >= 0) {
+                const int s = c % TC_RSTAGES;
+                TC_STAMP(cdbg, cdi, 10);
+                mbar_wait(&s_rfull[s], (c / TC_RSTAGES) & 1);
+                TC_STAMP(cdbg, cdi, 11);
+                float v[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 *src = reinterpret_cast<const float4 *>(
+                        tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)(q * 8 + rk) * TC_RAW_ROW + rg * 32);
+                    const float4 a4 = src[0], b4 = src[1];      // rows >= K and columns >= N were zero-filled by the copy
+                    v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                    v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
+                }
+                {   // image stage c % 2 (this group's own): wait until the MMAs of chunk c - 2 have read it
+                    const int sx = c % TC_XSTAGES;
+                    mbar_wait(&s_xempty[sx], ((c / TC_XSTAGES) & 1) ^ 1);
+                    TC_STAMP(cdbg, cdi, 12);
+                    uint8_t *xhi = tc_smem + TC_OFF_X + (size_t)sx * TC_CHUNK, *xlo = xhi + TC_IMG;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 h, l;
+                        split2(v[q][0], v[q][1], h.x, l.x);
+                        split2(v[q][2], v[q][3], h.y, l.y);
+                        split2(v[q][4], v[q][5], h.z, l.z);
+                        split2(v[q][6], v[q][7], h.w, l.w);
+                        const uint32_t off = (uint32_t)rg * TC_SBO + (uint32_t)q * TC_LBO + (uint32_t)rk * 16;
+                        *reinterpret_cast<uint4 *>(xhi + off) = h;
+                        *reinterpret_cast<uint4 *>(xlo + off) = l;
+                    }
+                    fence_proxy_async();        // this thread's image rows -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&s_xfull[sx]);
+                        mbar_arrive(&s_rempty[s]);             // the raw stage the values came from is free again
+                    }
+                }
+                TC_STAMP(cdbg, cdi, 13);
+                c += 2; cc.kc += 2;
+                norm(cc, true);
+                if (ic.tile >= 0) {
+                    issue_raw(ic, ci);
+                    ci += 2; ic.kc += 2;
+                    norm(ic, false);
+                }
+                TC_STAMP(cdbg, cdi, 14);
+            }
+            ring_release(cc.ring);
         } else {
             // register path: gather mode, or dense rows that are not 16-byte aligned.  Software-pipelined: the global
             // loads of the next chunk (possibly of the next tile) are issued before the current one is converted.
