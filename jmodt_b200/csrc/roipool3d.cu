@@ -43,8 +43,10 @@ struct BoxTest {
 //   [feature lead .. feat_len-1 | x, y, z | feature 0 .. lead-1 | zero padding]  with pitch round_up(3 + feat_len, 8)
 // i.e. the 128 RPN channels first (one 16-byte aligned block) and the 5 inputs of xyz_up_layer (rcnn.py:172-180:
 // xyz, seg mask, depth) behind them.  lead == 0 is the reference layout [x, y, z | features], pitch 3 + feat_len.
-template <bool CANON>
-__global__ void __launch_bounds__(RP_THREADS)
+// RP_UNROLL = 4 (head layout): four rows / four scan steps in flight per warp, 4 CTAs per SM; RP_UNROLL = 1 (reference
+// layout, rows only 4-byte aligned): one row per warp iteration at full occupancy — measured faster there.
+template <bool CANON, int RP_UNROLL>
+__global__ void __launch_bounds__(RP_THREADS, RP_UNROLL == 1 ? 6 : 4)
 roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float extra, int lead,
                  const float *__restrict__ xyz, const float *__restrict__ boxes3d,
                  const float *__restrict__ pts_feature, float *__restrict__ pooled,
@@ -80,17 +82,26 @@ roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float ex
     const int beg = warp * seg, end = min(pts_num, beg + seg);
     int *mine = s_warp + (size_t)warp * sampled;
     int cnt = 0;
-    for (int p0 = beg; p0 < end && cnt < sampled; p0 += 32) {
-        const int p = p0 + (int)lane;
-        bool hit = false;
-        if (p < end) {
-            const float *q = pts + (size_t)p * 3;
-            hit = T.inside(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+    for (int p0 = beg; p0 < end && cnt < sampled; p0 += 32 * RP_UNROLL) {   // RP_UNROLL 32-point steps per trip: their loads overlap
+        float px[RP_UNROLL], py[RP_UNROLL], pz[RP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RP_UNROLL; ++u) {
+            const int p = p0 + u * 32 + (int)lane;
+            px[u] = py[u] = pz[u] = 0.f;
+            if (p < end) {
+                const float *q = pts + (size_t)p * 3;
+                px[u] = __ldg(q); py[u] = __ldg(q + 1); pz[u] = __ldg(q + 2);
+            }
         }
-        const unsigned mk = __ballot_sync(0xffffffffu, hit);
-        const int pos = cnt + __popc(mk & lt_mask);
-        if (hit && pos < sampled) mine[pos] = p;
-        cnt += __popc(mk);
+#pragma unroll
+        for (int u = 0; u < RP_UNROLL; ++u) {
+            const int p = p0 + u * 32 + (int)lane;
+            const bool hit = p < end && T.inside(px[u], py[u], pz[u]);
+            const unsigned mk = __ballot_sync(0xffffffffu, hit);
+            const int pos = cnt + __popc(mk & lt_mask);
+            if (hit && pos < sampled) mine[pos] = p;
+            cnt += __popc(mk);
+        }
     }
     cnt = min(cnt, sampled);
     if (lane == 0) s_cnt[warp] = cnt;
@@ -134,29 +145,96 @@ roipool3d_kernel(int pts_num, int boxes_num, int feat_len, int sampled, float ex
         return;
     }
 
-    // ---- phase 2: row copies, one warp per row, wrap-around duplicates (:152-158) ---------
+    // ---- phase 2: row copies, wrap-around duplicates (:152-158) --------------------------------
+    // One warp per row, RP_UNROLL rows per iteration: the loads of all rows are issued before the first store, so a
+    // warp keeps ~2 KB in flight instead of one 0.5 KB row (the copy is latency-bound: 64 warps per SM, ~1.5 us per
+    // L2-read / HBM-write round trip).  The head layout with 128 channels moves them as 8-byte pairs.
     const float *feat = pts_feature + (size_t)b * pts_num * feat_len;
-    for (int s = warp; s < sampled; s += RP_WARPS) {
-        const int src = s_final[s < have ? s : s % have];
-        float *dst = dst_box + (size_t)s * row;
-        const float *f = feat + (size_t)src * feat_len;
-        if (lane < 3) {
-            const float *q = pts + (size_t)src * 3;
-            float v = __ldg(q + lane);
-            if (CANON) {
-                const float tx = __ldg(q) - ox, tz = __ldg(q + 2) - oz;
-                // rotate_pc_along_y_torch: x' = x*cos - z*sin ; z' = x*sin + z*cos
-                if (lane == 0) v = __fmaf_rn(tz, -rs, __fmul_rn(tx, rc));
-                else if (lane == 1) v = v - oy;
-                else v = __fmaf_rn(tz, rc, __fmul_rn(tx, rs));
+    const bool vec = lead > 0 && xoff == 128 && row == 136 && (feat_len & 1) == 0 && (lead & 1) == 0 &&
+                     (reinterpret_cast<uintptr_t>(feat) & 7u) == 0 && (reinterpret_cast<uintptr_t>(dst_box) & 7u) == 0;
+    for (int s0 = warp; s0 < sampled; s0 += RP_WARPS * RP_UNROLL) {
+        int src[RP_UNROLL];
+        float xv[RP_UNROLL];                 // lanes 0..2: transformed coordinate `lane` of the row
+#pragma unroll
+        for (int u = 0; u < RP_UNROLL; ++u) {
+            const int sidx = s0 + u * RP_WARPS;
+            src[u] = sidx < sampled ? s_final[sidx < have ? sidx : sidx % have] : -1;
+            xv[u] = 0.f;
+            if (src[u] >= 0 && lane < 3) {
+                const float *q = pts + (size_t)src[u] * 3;
+                float v = __ldg(q + lane);
+                if (CANON) {
+                    const float tx = __ldg(q) - ox, tz = __ldg(q + 2) - oz;
+                    // rotate_pc_along_y_torch: x' = x*cos - z*sin ; z' = x*sin + z*cos
+                    if (lane == 0) v = __fmaf_rn(tz, -rs, __fmul_rn(tx, rc));
+                    else if (lane == 1) v = v - oy;
+                    else v = __fmaf_rn(tz, rc, __fmul_rn(tx, rs));
+                }
+                xv[u] = v;
             }
-            dst[xoff + lane] = v;
         }
-        if (lead > 0) {
-            for (int j = lane; j < xoff; j += 32) dst[j] = __ldg(f + lead + j);
-            for (int j = lane; j < row - xoff - 3; j += 32) dst[xoff + 3 + j] = j < lead ? __ldg(f + j) : 0.f;
+        if (vec) {
+            float2 a[RP_UNROLL], c[RP_UNROLL];
+            float tl[RP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < RP_UNROLL; ++u) {
+                if (src[u] < 0) continue;
+                const float *f = feat + (size_t)src[u] * feat_len;
+                const float2 *f2 = reinterpret_cast<const float2 *>(f + lead);
+                a[u] = __ldg(f2 + lane);
+                c[u] = __ldg(f2 + 32 + lane);
+                tl[u] = (lane >= 3 && (int)lane < 3 + lead) ? __ldg(f + lane - 3) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RP_UNROLL; ++u) {
+                if (src[u] < 0) continue;
+                float *dst = dst_box + (size_t)(s0 + u * RP_WARPS) * row;
+                float2 *d2 = reinterpret_cast<float2 *>(dst);
+                d2[lane] = a[u];
+                d2[32 + lane] = c[u];
+                if (lane < 8) dst[128 + lane] = lane < 3 ? xv[u] : tl[u];
+            }
+        } else if (lead == 0 && RP_UNROLL == 1) {
+            if (src[0] >= 0) {
+                float *dst = dst_box + (size_t)s0 * row;
+                const float *f = feat + (size_t)src[0] * feat_len;
+                if (lane < 3) dst[lane] = xv[0];
+                for (int j = lane; j < feat_len; j += 32) dst[3 + j] = __ldg(f + j);
+            }
+        } else if (lead == 0) {
+            // reference layout [x, y, z | features]: rows are only 4-byte aligned; the same 64 columns of all rows are
+            // loaded before any is stored
+            if (lane < 3) {
+#pragma unroll
+                for (int u = 0; u < RP_UNROLL; ++u)
+                    if (src[u] >= 0) dst_box[(size_t)(s0 + u * RP_WARPS) * row + lane] = xv[u];
+            }
+            for (int j0 = 0; j0 < feat_len; j0 += 64) {
+                const int ja = j0 + (int)lane, jb = ja + 32;
+                float va[RP_UNROLL], vb[RP_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RP_UNROLL; ++u) {
+                    const float *f = feat + (size_t)(src[u] >= 0 ? src[u] : 0) * feat_len;
+                    va[u] = (src[u] >= 0 && ja < feat_len) ? __ldg(f + ja) : 0.f;
+                    vb[u] = (src[u] >= 0 && jb < feat_len) ? __ldg(f + jb) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < RP_UNROLL; ++u) {
+                    float *dst = dst_box + (size_t)(s0 + u * RP_WARPS) * row + 3;
+                    if (src[u] >= 0 && ja < feat_len) dst[ja] = va[u];
+                    if (src[u] >= 0 && jb < feat_len) dst[jb] = vb[u];
+                }
+            }
         } else {
-            for (int j = lane; j < feat_len; j += 32) dst[3 + j] = __ldg(f + j);
+#pragma unroll
+            for (int u = 0; u < RP_UNROLL; ++u) {
+                if (src[u] < 0) continue;
+                float *dst = dst_box + (size_t)(s0 + u * RP_WARPS) * row;
+                const float *f = feat + (size_t)src[u] * feat_len;
+                if (lane < 3) dst[xoff + lane] = xv[u];
+                for (int j = lane; j < xoff; j += 32) dst[j] = __ldg(f + lead + j);
+                for (int j = lane; j < row - xoff - 3; j += 32) dst[xoff + 3 + j] = j < lead ? __ldg(f + j) : 0.f;
+            }
         }
     }
 }
@@ -174,7 +252,8 @@ static int launch_roipool(bool canon, int lead, int batch, int pts_num, int boxe
     JMB_REQUIRE(batch <= 65535, "roipool3d: batch %d exceeds grid.y limit", batch);
     const size_t smem = (size_t)(RP_WARPS + 1) * sampled * sizeof(int);
     JMB_REQUIRE(smem <= 200 * 1024, "roipool3d: sampled_pt_num %d too large", sampled);
-    auto kern = canon ? roipool3d_kernel<true> : roipool3d_kernel<false>;
+    auto kern = lead > 0 ? (canon ? roipool3d_kernel<true, 4> : roipool3d_kernel<false, 4>)
+                         : (canon ? roipool3d_kernel<true, 1> : roipool3d_kernel<false, 1>);
     if (smem > 48 * 1024)
         JMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(boxes_num, batch);
