@@ -211,6 +211,13 @@ JMB_API int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2
                                  const float *b3, long long rows, int row_pitch, const float *in, float *out,
                                  void *stream);
 
+/* Pair correlation features of the link / start-end heads (reference jmodt/tracking/tracker.py:81-112,
+ * rcnn.py:239-258): pt (G, K, P) predecessor and dt (G, K, D) successor features, channel-first ->
+ * cor (G, K, P*D) = |pt[.., i] - dt[.., j]| at column i*D + j, mean_over_p (G, K, D) = mean_i cor and
+ * mean_over_d (G, K, P) = mean_j cor.  Any of the three outputs may be NULL. */
+JMB_API int jmb_pair_corr(int G, int K, int P, int D, const float *pt, const float *dt, float *cor,
+                          float *mean_over_p, float *mean_over_d, void *stream);
+
 /* ---- proposal layer ---------------------------------------------------------------------- */
 
 /* Scratch bytes for jmb_proposal_layer. */

@@ -15,7 +15,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from . import runtime, tc
+from . import _lib, runtime, tc
 from .pointnet2 import pointnet2_utils as pu
 from .pointnet2 import pytorch_utils as pt_utils
 from .pointnet2.pointnet2_modules import PointnetSAModule
@@ -247,6 +247,21 @@ class RCNN(nn.Module):
         return {"rcnn_cls": rcnn_cls, "rcnn_reg": rcnn_reg, "rcnn_feat": feat, "pooled_empty_flag": empty}
 
 
+def pair_corr(pt: torch.Tensor, dt: torch.Tensor):
+    """|p_i - d_j| features of G frame pairs and their two means in one kernel (csrc/pair_corr.cu):
+    pt (G, K, P), dt (G, K, D) channel-first -> cor (G, K, P*D), mean over i (G, K, D), mean over j (G, K, P)."""
+    G, K, P = pt.shape
+    D = dt.shape[2]
+    assert dt.shape[:2] == (G, K) and pt.is_contiguous() and dt.is_contiguous() and pt.dtype == dt.dtype == torch.float32
+    cor = torch.empty((G, K, P * D), dtype=torch.float32, device=pt.device)
+    mean_p = torch.empty((G, K, D), dtype=torch.float32, device=pt.device)
+    mean_d = torch.empty((G, K, P), dtype=torch.float32, device=pt.device)
+    st = _lib.stream_and_device(pt)
+    _lib.check(_lib.lib().jmb_pair_corr(G, K, P, D, pt.data_ptr(), dt.data_ptr(), cor.data_ptr(), mean_p.data_ptr(),
+                                        mean_d.data_ptr(), st), "pair_corr")
+    return cor, mean_p, mean_d
+
+
 @torch.no_grad()
 def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
     """`affinity` for G frame pairs at once: pred_features (G, P, 512), det_features (G, D, 512) ->
@@ -256,16 +271,17 @@ def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torc
     packed = rcnn.packed
     pt = pred_features.transpose(1, 2).contiguous()                                       # (G, 512, P)
     dt = det_features.transpose(1, 2).contiguous()                                        # (G, 512, D)
-    cor = (pt.unsqueeze(3) - dt.unsqueeze(2)).abs().contiguous()                          # (G, 512, P, D)
+    cor, mean_p, mean_d = pair_corr(pt, dt)          # (G, 512, P*D), mean over predecessors (G, 512, D), over successors (G, 512, P)
+
     def link_branch():
-        logits = run_stack(packed["link"], cor.view(G, -1, P * D)).view(G, P, D)
+        logits = run_stack(packed["link"], cor).view(G, P, D)
         col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)   # softmax over predecessors
         return (torch.softmax(logits, dim=2) + col) / 2, logits
 
     (link, logits), start, end = runtime.parallel(
         link_branch,
-        lambda: torch.sigmoid(run_stack(packed["se"], cor.mean(dim=2).contiguous())).view(G, D),
-        lambda: torch.sigmoid(run_stack(packed["se"], cor.mean(dim=3).contiguous())).view(G, P))
+        lambda: torch.sigmoid(run_stack(packed["se"], mean_p)).view(G, D),
+        lambda: torch.sigmoid(run_stack(packed["se"], mean_d)).view(G, P))
     return link, start, end, logits
 
 

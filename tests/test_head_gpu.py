@@ -112,6 +112,37 @@ def test_affinity_matches_torch_reference(cuda):
         assert _rel(link, wl) < 1e-4 and _rel(start, ws) < 1e-4 and _rel(end, we) < 1e-4
 
 
+def test_batched_affinity_and_pair_corr_match_torch_reference(cuda):
+    """affinity_batched (one pair_corr launch + one launch per layer for all frame pairs) vs the torch fp32
+    restatement pair by pair; the pair-correlation kernel alone vs torch (|p - d| exact, means to fp32 rounding)."""
+    from jmodt_b200.head import RCNN, affinity_batched, pair_corr
+    from oracle import modules_ref
+    torch.manual_seed(4)
+    rcnn = RCNN().to(cuda).eval()
+    with torch.no_grad():
+        for p in rcnn.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    rcnn.pack()
+    g = torch.Generator().manual_seed(8)
+    for G, P, D in [(4, 128, 128), (3, 37, 50), (1, 1, 3), (2, 200, 9)]:
+        pf = torch.randn(G, P, 512, generator=g).abs().to(cuda)
+        df = torch.randn(G, D, 512, generator=g).abs().to(cuda)
+        pt, dt = pf.transpose(1, 2).contiguous(), df.transpose(1, 2).contiguous()
+        cor, mean_p, mean_d = pair_corr(pt, dt)
+        want = (pt.unsqueeze(3) - dt.unsqueeze(2)).abs()                                   # (G, 512, P, D)
+        assert torch.equal(cor.view(G, 512, P, D), want)
+        assert torch.allclose(mean_p, want.mean(dim=2), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(mean_d, want.mean(dim=3), rtol=1e-5, atol=1e-6)
+        link, start, end, logits = affinity_batched(rcnn, pf, df)
+        assert link.shape == (G, P, D) and start.shape == (G, D) and end.shape == (G, P)
+        for k in range(G):
+            with torch.no_grad():
+                wl, ws, we, wlog = modules_ref.affinity(rcnn.link_layer, rcnn.se_layer, pf[k], df[k])
+            assert _rel(logits[k], wlog) < 1e-4, (G, P, D, _rel(logits[k], wlog))
+            assert _rel(link[k], wl) < 1e-4 and _rel(start[k], ws) < 1e-4 and _rel(end[k], we) < 1e-4
+
+
 def test_state_dict_keys_match_reference_layout(cuda):
     from jmodt_b200.head import RCNN
     keys = set(RCNN().state_dict())
