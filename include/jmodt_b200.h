@@ -218,6 +218,12 @@ JMB_API int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2
 JMB_API int jmb_pair_corr(int G, int K, int P, int D, const float *pt, const float *dt, float *cor,
                           float *mean_over_p, float *mean_over_d, void *stream);
 
+/* Per-point feature vector of the RoI-pooling stage (reference proposal_target_layer.py:17-34, point_rcnn.py:47):
+ * feat (B, C, N) channel-first and E <= 2 per-point scalars extra0/extra1 (B, N) -> out (B, N, E + C) =
+ * [extra0, extra1, feat[:, :, n]] — torch.cat((mask, depth, features.permute(0, 2, 1)), dim=2) as one tiled transpose. */
+JMB_API int jmb_pack_point_features(int B, int C, int N, int E, const float *feat, const float *extra0,
+                                    const float *extra1, float *out, void *stream);
+
 /* ---- proposal layer ---------------------------------------------------------------------- */
 
 /* Scratch bytes for jmb_proposal_layer. */

@@ -68,3 +68,48 @@ extern "C" int jmb_pair_corr(int G, int K, int P, int D, const float *pt, const 
     pair_corr_kernel<<<dim3(K, G), 256, smem, (cudaStream_t)stream>>>(K, P, D, pt, dt, cor, mean_over_p, mean_over_d);
     return check_launch("pair_corr");
 }
+
+// ---- point-feature packing for RoI pooling ---------------------------------------------------------------------
+// The reference builds the per-point feature vector of the RoI-pooling stage with
+//     pts_feature = torch.cat((seg_mask.unsqueeze(2), depth.unsqueeze(2), rpn_features), dim=2)
+// (proposal_target_layer.py:17-34) where rpn_features is backbone_features.permute(0, 2, 1) (point_rcnn.py:47): a
+// strided gather of the channel-first (B, C, N) tensor, 32 bytes fetched per 4 bytes used.  Here a CTA transposes a
+// 32-point x C-channel tile through shared memory: coalesced reads along the points, coalesced row writes.
+namespace jmb {
+
+__global__ void __launch_bounds__(256)
+pack_point_features_kernel(int C, int N, int E, const float *__restrict__ feat, const float *__restrict__ e0,
+                           const float *__restrict__ e1, float *__restrict__ out) {
+    extern __shared__ float pk_tile[];                 // [32][C + 1]
+    const int b = blockIdx.y, n0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *src = feat + (size_t)b * C * N;
+    const int pitch = C + 1;
+    const int n = n0 + lane;
+    for (int c = warp; c < C; c += 8) pk_tile[lane * pitch + c] = n < N ? __ldg(src + (size_t)c * N + n) : 0.f;
+    __syncthreads();
+    const int row = E + C;
+    for (int r = warp; r < 32; r += 8) {
+        const int p = n0 + r;
+        if (p >= N) break;
+        float *dst = out + ((size_t)b * N + p) * row;
+        if (lane == 0 && E > 0) dst[0] = __ldg(e0 + (size_t)b * N + p);
+        if (lane == 1 && E > 1) dst[1] = __ldg(e1 + (size_t)b * N + p);
+        for (int c = lane; c < C; c += 32) dst[E + c] = pk_tile[r * pitch + c];
+    }
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_pack_point_features(int B, int C, int N, int E, const float *feat, const float *extra0,
+                                       const float *extra1, float *out, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(B >= 0 && C >= 0 && N >= 0 && E >= 0 && E <= 2, "pack_point_features: bad sizes");
+    if (B == 0 || N == 0) return JMB_OK;
+    JMB_REQUIRE((feat || C == 0) && out && (E < 1 || extra0) && (E < 2 || extra1), "pack_point_features: null pointer");
+    JMB_REQUIRE(B <= 65535, "pack_point_features: batch too large");
+    const size_t smem = (size_t)32 * (C + 1) * sizeof(float);
+    JMB_REQUIRE(smem <= 48 * 1024, "pack_point_features: %d channels exceed the shared-memory tile", C);
+    pack_point_features_kernel<<<dim3(div_up(N, 32), B), 256, smem, (cudaStream_t)stream>>>(C, N, E, feat, extra0, extra1, out);
+    return check_launch("pack_point_features");
+}

@@ -349,8 +349,8 @@ class RPN(nn.Module):
         xyz, feats = self.backbone_net(input_data["pts_input"], input_data.get("img"), input_data.get("pts_xy"),
                                        image_maps=image_maps)
         rpn_cls, rpn_reg = runtime.parallel(
-            lambda: run_stack(self._packed[0], feats).transpose(1, 2).contiguous(),      # (B, N, 1)
-            lambda: run_stack(self._packed[1], feats).transpose(1, 2).contiguous())      # (B, N, 76)
+            lambda: run_stack(self._packed[0], feats, point_major_out=True),      # (B, N, 1): transposed by the epilogue
+            lambda: run_stack(self._packed[1], feats, point_major_out=True))      # (B, N, 76)
         return {"rpn_cls": rpn_cls, "rpn_reg": rpn_reg, "backbone_xyz": xyz, "backbone_features": feats}
 
 

@@ -76,9 +76,12 @@ def _pack_stack(seq) -> List[tc.PackedLayer]:
     return packed
 
 
-def run_stack(packed: List[tc.PackedLayer], x: torch.Tensor, pool: int = 0) -> torch.Tensor:
+def run_stack(packed: List[tc.PackedLayer], x: torch.Tensor, pool: int = 0, point_major_out: bool = False) -> torch.Tensor:
+    """x (G, K, N) through the layers; the last one max-pools over `pool` columns, or (point_major_out) writes
+    (G, N, M) directly — the `.transpose(1, 2).contiguous()` of the reference heads (rpn.py:76-77) for free."""
     for i, layer in enumerate(packed):
-        x = tc.mlp_layer(layer, x, pool=pool if i == len(packed) - 1 else 0)
+        last = i == len(packed) - 1
+        x = tc.mlp_layer(layer, x, pool=pool if last else 0, point_major_out=point_major_out and last)
     return x
 
 
@@ -165,7 +168,7 @@ class RCNN(nn.Module):
         extra = [input_data["seg_mask"].unsqueeze(2)]
         if cfg.use_depth:
             extra.append((input_data["pts_depth"] / 70.0 - 0.5).unsqueeze(2))
-        pts_feature = torch.cat(extra + [input_data["rpn_features"]], dim=2)
+        pts_feature = pack_point_features(extra, input_data["rpn_features"])
         if self._input_fusable(len(extra), input_data["rpn_features"].shape[2]):
             pooled, empty = roipool3d_utils.roipool3d_gpu_canonical_head(
                 input_data["rpn_xyz"], pts_feature, input_data["roi_boxes3d"], cfg.pool_extra_width, len(extra),
@@ -245,6 +248,24 @@ class RCNN(nn.Module):
         pts_input, empty = self.pool_rois(input_data)
         rcnn_cls, rcnn_reg, feat = self.forward_points(pts_input)
         return {"rcnn_cls": rcnn_cls, "rcnn_reg": rcnn_reg, "rcnn_feat": feat, "pooled_empty_flag": empty}
+
+
+def pack_point_features(extra, rpn_features: torch.Tensor) -> torch.Tensor:
+    """torch.cat(extra + [rpn_features], dim=2) (proposal_target_layer.py:17-34).  rpn_features (B, N, C) is normally the
+    permuted view of the channel-first backbone output (point_rcnn.py:47): then the concat is one tiled transpose
+    (csrc/pair_corr.cu: jmb_pack_point_features) instead of a strided gather; otherwise plain torch.cat."""
+    B, N, C = rpn_features.shape
+    cf = rpn_features.permute(0, 2, 1)
+    if not (rpn_features.is_cuda and rpn_features.dtype == torch.float32 and cf.is_contiguous() and len(extra) <= 2
+            and C <= 256 and all(e.shape == (B, N, 1) and e.dtype == torch.float32 for e in extra)):
+        return torch.cat(list(extra) + [rpn_features], dim=2)
+    ex = [e.reshape(B, N).contiguous() for e in extra]
+    out = torch.empty((B, N, len(ex) + C), dtype=torch.float32, device=rpn_features.device)
+    st = _lib.stream_and_device(rpn_features)
+    _lib.check(_lib.lib().jmb_pack_point_features(B, C, N, len(ex), cf.data_ptr(), ex[0].data_ptr() if ex else None,
+                                                  ex[1].data_ptr() if len(ex) > 1 else None, out.data_ptr(), st),
+               "pack_point_features")
+    return out
 
 
 def pair_corr(pt: torch.Tensor, dt: torch.Tensor):

@@ -143,6 +143,19 @@ def test_batched_affinity_and_pair_corr_match_torch_reference(cuda):
             assert _rel(link[k], wl) < 1e-4 and _rel(start[k], ws) < 1e-4 and _rel(end[k], we) < 1e-4
 
 
+def test_pack_point_features_equals_torch_cat(cuda):
+    """torch.cat((mask, depth, features.permute(0, 2, 1)), dim=2) as one tiled transpose: bit-identical."""
+    from jmodt_b200.head import pack_point_features
+    g = torch.Generator().manual_seed(3)
+    for B, C, N, E in [(2, 128, 16384, 2), (1, 96, 1000, 2), (3, 7, 33, 1), (1, 128, 64, 0)]:
+        feat = torch.randn(B, C, N, generator=g).to(cuda)
+        extra = [torch.randn(B, N, 1, generator=g).to(cuda) for _ in range(E)]
+        rf = feat.permute(0, 2, 1)                       # what point_rcnn.py:47 hands to the pooling stage
+        got = pack_point_features(extra, rf)
+        assert got.is_contiguous() and torch.equal(got, torch.cat(extra + [rf], dim=2))
+        assert torch.equal(pack_point_features(extra, rf.contiguous()), torch.cat(extra + [rf], dim=2))   # fallback path
+
+
 def test_state_dict_keys_match_reference_layout(cuda):
     from jmodt_b200.head import RCNN
     keys = set(RCNN().state_dict())
