@@ -81,7 +81,10 @@ def run_stack(packed: List[tc.PackedLayer], x: torch.Tensor, pool: int = 0, poin
     (G, N, M) directly — the `.transpose(1, 2).contiguous()` of the reference heads (rpn.py:76-77) for free."""
     for i, layer in enumerate(packed):
         last = i == len(packed) - 1
-        x = tc.mlp_layer(layer, x, pool=pool if last else 0, point_major_out=point_major_out and last)
+        pm = point_major_out and last and layer.M > 1
+        x = tc.mlp_layer(layer, x, pool=pool if last else 0, point_major_out=pm)
+    if point_major_out and packed[-1].M == 1:
+        x = x.transpose(1, 2)            # (G, 1, N) and (G, N, 1) are the same memory
     return x
 
 
