@@ -187,8 +187,11 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn, activation=activation)
 
+    interp_after_first_layer = True      # fused path without skip features: see forward()
+
     def train(self, mode: bool = True):
         self._packed = None
+        self._first_linear = None
         return super().train(mode)
 
     @staticmethod
@@ -206,16 +209,33 @@ class PointnetFPModule(nn.Module):
         :param unknown: (B, n, 3), known: (B, m, 3), unknow_feats: (B, C1, n), known_feats: (B, C2, m)
         :return: (B, mlp[-1], n)
         """
+        fused = _use_fused(self)
+        packed = None
+        if fused:
+            packed = getattr(self, "_packed", None)
+            if packed is None:
+                packed = self._packed = pack_shared_mlp(self.mlp)
         if known is not None:
             idx, weight = plan if plan is not None else self.plan(unknown, known)
+            if fused and unknow_feats is None and self.interp_after_first_layer and packed[0].relu and \
+                    packed[0]._w32 is not None and known_feats.shape[2] < unknown.shape[1]:
+                # No skip features: the first layer is linear up to its ReLU and the interpolation weights sum to one,
+                # so  relu(W . interp(f) + b) = relu(interp(W . f + b)).  Running the layer on the m KNOWN points and
+                # interpolating its (usually narrower) output does n/m times fewer FLOPs and gathers fewer channels
+                # (level 0: 16 384 -> 4 096 columns, 256 -> 128 channels).  Same result to fp32 rounding.
+                lin = getattr(self, "_first_linear", None)
+                if lin is None:
+                    lin = self._first_linear = tc.PackedLayer(packed[0]._w32, packed[0].bias[: packed[0].M], relu=False)
+                h = tc.mlp_layer(lin, known_feats.contiguous())
+                h = torch.relu_(pointnet2_utils.three_interpolate(h, idx, weight))
+                for layer in packed[1:]:
+                    h = tc.mlp_layer(layer, h)
+                return h
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
-        if _use_fused(self):
-            packed = getattr(self, "_packed", None)
-            if packed is None:
-                packed = self._packed = pack_shared_mlp(self.mlp)
+        if fused:
             h = new_features.contiguous()
             for layer in packed:
                 h = tc.mlp_layer(layer, h)

@@ -247,3 +247,26 @@ def test_wait_indices_gate_orders_a_consumer_behind_a_running_sampler(cuda):
             seen = idx[:, :k1].clone()
         torch.cuda.synchronize()
         assert torch.equal(seen, want[:, :k1]), k1
+
+
+@pytest.mark.gpu
+def test_fp_module_interpolating_after_the_first_layer_is_equivalent(cuda):
+    """Without skip features relu(W . interp(f) + b) = relu(interp(W . f + b)) (the weights sum to one): the fused FP
+    path that runs the first layer on the known points must match the reference order to fp32 rounding."""
+    from jmodt_b200.pointnet2.pointnet2_modules import PointnetFPModule
+    from jmodt_b200.synth import fill_deterministic
+    g = torch.Generator().manual_seed(21)
+    fp = fill_deterministic(PointnetFPModule(mlp=[256, 128, 128])).to(cuda).eval()
+    unknown = torch.rand(2, 4096, 3, generator=g).to(cuda)
+    known = unknown[:, :1024].contiguous()
+    feats = torch.randn(2, 256, 1024, generator=g).to(cuda)
+    with torch.no_grad():
+        fp.interp_after_first_layer = True
+        a = fp(unknown, known, None, feats)
+        fp.interp_after_first_layer = False
+        b = fp(unknown, known, None, feats)
+        fp.fused = False
+        want = fp(unknown, known, None, feats)          # torch layers (cuDNN fp32), reference op order
+    assert a.shape == b.shape == want.shape == (2, 128, 4096)
+    assert _rel(a.cpu().numpy(), want.cpu().numpy()) < 1e-4 and _rel(b.cpu().numpy(), want.cpu().numpy()) < 1e-4
+    assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
