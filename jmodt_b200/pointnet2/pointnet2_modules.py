@@ -217,17 +217,30 @@ class PointnetFPModule(nn.Module):
                 packed = self._packed = pack_shared_mlp(self.mlp)
         if known is not None:
             idx, weight = plan if plan is not None else self.plan(unknown, known)
-            if fused and unknow_feats is None and self.interp_after_first_layer and packed[0].relu and \
-                    packed[0]._w32 is not None and known_feats.shape[2] < unknown.shape[1]:
-                # No skip features: the first layer is linear up to its ReLU and the interpolation weights sum to one,
-                # so  relu(W . interp(f) + b) = relu(interp(W . f + b)).  Running the layer on the m KNOWN points and
-                # interpolating its (usually narrower) output does n/m times fewer FLOPs and gathers fewer channels
-                # (level 0: 16 384 -> 4 096 columns, 256 -> 128 channels).  Same result to fp32 rounding.
+            if fused and self.interp_after_first_layer and packed[0].relu and packed[0]._w32 is not None and \
+                    known_feats.shape[2] < unknown.shape[1]:
+                # The first layer is linear up to its ReLU, and so is the interpolation (weights sum to one):
+                #     relu(W . [interp(f); skip] + b) = relu(interp(W_a . f) + (W_b . skip + b)).
+                # Running W_a on the m KNOWN points and interpolating its (narrower) output does n/m times fewer
+                # FLOPs, gathers fewer channels and needs no concat (level 0, no skip features: 16 384 -> 4 096
+                # columns, 256 -> 128 channels).  Same result to fp32 rounding.
+                c2 = known_feats.shape[1]
                 lin = getattr(self, "_first_linear", None)
-                if lin is None:
-                    lin = self._first_linear = tc.PackedLayer(packed[0]._w32, packed[0].bias[: packed[0].M], relu=False)
-                h = tc.mlp_layer(lin, known_feats.contiguous())
-                h = torch.relu_(pointnet2_utils.three_interpolate(h, idx, weight))
+                if lin is None or lin[0].K != c2:
+                    w, b = packed[0]._w32, packed[0].bias[: packed[0].M]
+                    if unknow_feats is None:
+                        lin = (tc.PackedLayer(w, b, relu=False), None)
+                    else:
+                        lin = (tc.PackedLayer(w[:, :c2].contiguous(), None, relu=False),
+                               tc.PackedLayer(w[:, c2:].contiguous(), b, relu=False))
+                    self._first_linear = lin
+                if unknow_feats is None:
+                    h = tc.mlp_layer(lin[0], known_feats.contiguous())
+                    h = torch.relu_(pointnet2_utils.three_interpolate(h, idx, weight))
+                else:
+                    ha, hb = runtime.parallel(lambda: tc.mlp_layer(lin[0], known_feats.contiguous()),
+                                              lambda: tc.mlp_layer(lin[1], unknow_feats.contiguous()))
+                    h = torch.relu_(pointnet2_utils.three_interpolate(ha, idx, weight).add_(hb))
                 for layer in packed[1:]:
                     h = tc.mlp_layer(layer, h)
                 return h

@@ -1,5 +1,5 @@
 """Runs ONE stage of the e2e step between cudaProfilerStart/Stop so `ncu --profile-from-start off` captures just it.
-usage: python profiles/stage_profile.py {rpn|rcnn|affinity|proposal} [frames]"""
+usage: python profiles/stage_profile.py {step|rpn|rcnn|affinity|proposal} [frames]"""
 import sys, torch
 sys.path.insert(0, '.')
 import bench
@@ -21,7 +21,8 @@ pts_input, _ = m.rcnn_net.pool_rois(rc_in)
 feat = m.rcnn_net.forward_points(pts_input)[2]
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-if stage == 'rpn': m.rpn(inp, image_maps=suite.image_maps)
+if stage == 'step': suite.step(d)
+elif stage == 'rpn': m.rpn(inp, image_maps=suite.image_maps)
 elif stage == 'rcnn': m.rcnn_net.forward_points(pts_input)
 elif stage == 'affinity': m.pair_affinity(feat, 128)
 elif stage == 'proposal': m.rpn.proposal_layer(scores, rpn["rpn_reg"], rpn["backbone_xyz"])

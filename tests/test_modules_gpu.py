@@ -270,3 +270,15 @@ def test_fp_module_interpolating_after_the_first_layer_is_equivalent(cuda):
     assert a.shape == b.shape == want.shape == (2, 128, 4096)
     assert _rel(a.cpu().numpy(), want.cpu().numpy()) < 1e-4 and _rel(b.cpu().numpy(), want.cpu().numpy()) < 1e-4
     assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+    # with skip features: relu(interp(W_a . f) + W_b . skip + b)
+    fp2 = fill_deterministic(PointnetFPModule(mlp=[256 + 96, 256, 256])).to(cuda).eval()
+    skip = torch.randn(2, 96, 4096, generator=g).to(cuda)
+    with torch.no_grad():
+        a2 = fp2(unknown, known, skip, feats)
+        fp2.interp_after_first_layer = False
+        b2 = fp2(unknown, known, skip, feats)
+        fp2.fused = False
+        want2 = fp2(unknown, known, skip, feats)
+    assert a2.shape == want2.shape == (2, 256, 4096)
+    assert _rel(a2.cpu().numpy(), want2.cpu().numpy()) < 1e-4 and _rel(b2.cpu().numpy(), want2.cpu().numpy()) < 1e-4
+    assert _rel(a2.cpu().numpy(), b2.cpu().numpy()) < 2e-5
