@@ -224,6 +224,13 @@ JMB_API int jmb_pair_corr(int G, int K, int P, int D, const float *pt, const flo
 JMB_API int jmb_pack_point_features(int B, int C, int N, int E, const float *feat, const float *extra0,
                                     const float *extra1, float *out, void *stream);
 
+/* Tracker association inputs (reference jmodt/tracking/data_association.py:10-28,42-45): boxes (n, 7)
+ * [x, y, z, h, w, l, ry] -> dist (na, nb) = 1 - |centre_a - centre_b| / max corner-to-corner distance, and, when
+ * link / iou (na, nb) are given, score = link * w_app + iou * w_iou + dist * w_dis.  dist or score may be NULL. */
+JMB_API int jmb_boxes_dist(int na, const float *boxes_a, int nb, const float *boxes_b, float *dist,
+                           const float *link, const float *iou, float w_app, float w_iou, float w_dis,
+                           float *score, void *stream);
+
 /* ---- proposal layer ---------------------------------------------------------------------- */
 
 /* Scratch bytes for jmb_proposal_layer. */

@@ -40,6 +40,7 @@ SIGNATURES = {
     "jmb_rcnn_input_fused": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, _vp, _vp, _vp],
     "jmb_pair_corr": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_pack_point_features": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "jmb_boxes_dist": [_i, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp],
     "jmb_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "jmb_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "jmb_boxes_iou3d": [_i, _vp, _i, _vp, _vp, _vp],

@@ -31,6 +31,14 @@ _MAP = {
 }
 
 
+def boxes_dist_gpu(boxes_a, boxes_b):
+    """Drop-in for `jmodt.tracking.data_association.boxes_dist_gpu` (data_association.py:10-28): assign it over the
+    reference function (`data_association.boxes_dist_gpu = dropin.boxes_dist_gpu`) — that module also imports ortools,
+    so it is patched rather than aliased."""
+    from .association import boxes_dist_gpu as f
+    return f(boxes_a, boxes_b)
+
+
 def install() -> None:
     """Alias the reference's operator module paths to this package (idempotent)."""
     for parent in ("jmodt", "jmodt.ops"):
