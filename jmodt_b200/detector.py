@@ -354,9 +354,10 @@ class RPN(nn.Module):
         return {"rpn_cls": rpn_cls, "rpn_reg": rpn_reg, "backbone_xyz": xyz, "backbone_features": feats}
 
 
-def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size):
+def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bin, anchor_size, get_ry_fine=False):
     """bbox_transform.py:27-260 for the configuration the detector runs with: BBOX_AVG_BY_BIN=True,
-    get_xz_fine=True, get_y_by_bin=False, RY_WITH_BIN=False, get_ry_fine=False (config.py:193-208).
+    get_xz_fine=True, get_y_by_bin=False, RY_WITH_BIN=False (config.py:193-208); get_ry_fine=False for the RPN
+    (proposal_layer.py:24-32), True for the RCNN head (tools/eval.py:109-116: heading bins over [-pi/4, pi/4]).
     roi_box3d (N, 3|7), pred_reg (N, C) -> (N, 7) [x, y, z, h, w, l, ry]."""
     per_loc_bin_num = int(loc_scope / loc_bin_size) * 2
     nb = per_loc_bin_num
@@ -373,9 +374,13 @@ def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bi
     ry_bin = torch.argmax(pred_reg[:, start:start + num_head_bin], dim=1)
     ry_res_norm = torch.gather(pred_reg[:, start + num_head_bin:start + 2 * num_head_bin], 1,
                                ry_bin.unsqueeze(1)).squeeze(1)
-    angle_per_class = (2 * np.pi) / num_head_bin
-    ry = (ry_bin.float() * angle_per_class + ry_res_norm * (angle_per_class / 2)) % (2 * np.pi)
-    ry = torch.where(ry > np.pi, ry - 2 * np.pi, ry)       # `ry[ry > pi] -= 2*pi` without the nonzero() host sync
+    if get_ry_fine:          # bbox_transform.py:137-141
+        angle_per_class = (np.pi / 2) / num_head_bin
+        ry = (ry_bin.float() * angle_per_class + angle_per_class / 2) + ry_res_norm * (angle_per_class / 2) - np.pi / 4
+    else:                    # :142-148
+        angle_per_class = (2 * np.pi) / num_head_bin
+        ry = (ry_bin.float() * angle_per_class + ry_res_norm * (angle_per_class / 2)) % (2 * np.pi)
+        ry = torch.where(ry > np.pi, ry - 2 * np.pi, ry)   # `ry[ry > pi] -= 2*pi` without the nonzero() host sync
     size_l = start + 2 * num_head_bin
     size_res_norm = pred_reg[:, size_l:size_l + 3]
     hwl = size_res_norm * anchor_size + anchor_size
@@ -389,6 +394,38 @@ def decode_bbox_target(roi_box3d, pred_reg, loc_scope, loc_bin_size, num_head_bi
     ret[:, 0] += roi_center[:, 0]          # `ret[:, [0, 2]] += roi_center[:, [0, 2]]` without host-built index tensors
     ret[:, 2] += roi_center[:, 2]
     return ret
+
+
+@torch.no_grad()
+def postprocess_detections(roi_boxes3d, rcnn_cls, rcnn_reg, rcnn_feat=None, head_cfg: HeadConfig | None = None,
+                           mean_size=(1.52563191462, 1.62856739989, 3.88311640418), score_thresh: float = 0.2,
+                           nms_thresh: float = 0.1):
+    """Detection post-processing of the evaluation loop (tools/eval.py:96-193): decode the RCNN
+    regression against its RoIs, sigmoid scores, score threshold (cfg.RCNN.SCORE_THRESH), rotated BEV NMS ordered by
+    the raw scores (cfg.RCNN.NMS_THRESH) — per frame, everything on the device (the reference copies each frame's
+    suppression mask to the host).  roi_boxes3d (B, M, 7), rcnn_cls (B*M, 1), rcnn_reg (B*M, C), rcnn_feat (B*M, F, 1)
+    -> list of B dicts {boxes3d (k, 7), scores (k,), raw_scores (k,), feat (k, F) | None, roi_index (k,)}."""
+    from .iou3d import iou3d_utils
+    cfg = head_cfg or HeadConfig()
+    B, M = roi_boxes3d.shape[:2]
+    anchor = torch.tensor(mean_size, dtype=torch.float32, device=roi_boxes3d.device)
+    boxes = decode_bbox_target(roi_boxes3d.reshape(-1, 7), rcnn_reg.reshape(B * M, -1), cfg.loc_scope, cfg.loc_bin_size,
+                               cfg.num_head_bin, anchor, get_ry_fine=True).view(B, M, 7)
+    raw = rcnn_cls.reshape(B, M)
+    norm = torch.sigmoid(raw)
+    feat = None if rcnn_feat is None else rcnn_feat.reshape(B, M, -1)
+    out = []
+    for k in range(B):
+        sel = torch.nonzero(norm[k] > score_thresh).flatten()
+        if sel.numel() == 0:
+            out.append({"boxes3d": boxes.new_zeros(0, 7), "scores": raw.new_zeros(0), "raw_scores": raw.new_zeros(0),
+                        "feat": None if feat is None else feat.new_zeros(0, feat.shape[2]), "roi_index": sel})
+            continue
+        b_sel, r_sel = boxes[k, sel], raw[k, sel]
+        keep = iou3d_utils.nms_gpu(box_utils.boxes3d_to_bev_torch(b_sel).contiguous(), r_sel.contiguous(), nms_thresh).view(-1)
+        out.append({"boxes3d": b_sel[keep], "scores": norm[k, sel][keep], "raw_scores": r_sel[keep],
+                    "feat": None if feat is None else feat[k, sel][keep], "roi_index": sel[keep]})
+    return out
 
 
 class ProposalLayer(nn.Module):

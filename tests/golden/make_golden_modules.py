@@ -130,6 +130,23 @@ def main(out_path):
     with torch.no_grad():
         g["fp_in"], g["fp_out"] = x.numpy(), fp.mlp(x.unsqueeze(-1)).squeeze(-1).numpy()
 
+    # ---- decode_bbox_target as the evaluation loop calls it on the RCNN head (tools/eval.py:109-116): 7-column RoIs
+    # (rotated back by the RoI heading) and the fine heading bins.  Drawn LAST so the arrays above keep their values.
+    rois7 = torch.cat([torch.rand(200, 3, generator=gen) * torch.tensor([80.0, 4.0, 70.0]) - torch.tensor([40.0, 1.0, 0.0]),
+                       torch.tensor([1.5256, 1.6286, 3.8831]) * (0.8 + 0.4 * torch.rand(200, 3, generator=gen)),
+                       (torch.rand(200, 1, generator=gen) * 2 - 1) * np.pi], dim=1)
+    reg46 = torch.randn(200, 46, generator=gen)
+    torch.Tensor.get_device = lambda self: "cpu"
+    try:
+        dec7 = rbt.decode_bbox_target(rois7.clone(), reg46, anchor_size=mean_size, loc_scope=cfg.RCNN.LOC_SCOPE,
+                                      loc_bin_size=cfg.RCNN.LOC_BIN_SIZE, num_head_bin=cfg.RCNN.NUM_HEAD_BIN,
+                                      get_xz_fine=True, get_y_by_bin=cfg.RCNN.LOC_Y_BY_BIN,
+                                      loc_y_scope=cfg.RCNN.LOC_Y_SCOPE, loc_y_bin_size=cfg.RCNN.LOC_Y_BIN_SIZE,
+                                      get_ry_fine=True)
+    finally:
+        torch.Tensor.get_device = orig
+    g["dec7_rois"], g["dec7_reg"], g["dec7_out"] = rois7.numpy(), reg46.numpy(), dec7.numpy()
+
     np.savez_compressed(out_path, **g)
     print("wrote", out_path, sorted(g))
 

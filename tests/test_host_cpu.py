@@ -77,6 +77,20 @@ def test_decode_bbox_target_matches_the_reference_golden_on_cpu():
     assert float(out[:, 6].max()) <= np.pi + 1e-6 and float(out[:, 6].min()) >= -np.pi - 1e-6
 
 
+def test_rcnn_decode_with_rotated_rois_and_fine_heading_matches_the_reference_golden():
+    """decode_bbox_target as the evaluation loop calls it on the RCNN head (tools/eval.py:109-116): 7-column RoIs,
+    get_ry_fine=True — against outputs of the reference function on the same inputs."""
+    from jmodt_b200.detector import decode_bbox_target
+    from jmodt_b200.head import HeadConfig
+    G = np.load(os.path.join(HERE, "golden", "ref_modules.npz"))
+    cfg = HeadConfig()
+    out = decode_bbox_target(torch.from_numpy(G["dec7_rois"]).clone(), torch.from_numpy(G["dec7_reg"]), cfg.loc_scope,
+                             cfg.loc_bin_size, cfg.num_head_bin,
+                             torch.tensor((1.52563191462, 1.62856739989, 3.88311640418), dtype=torch.float32),
+                             get_ry_fine=True)
+    np.testing.assert_allclose(out.numpy(), G["dec7_out"], atol=2e-5, rtol=1e-5)
+
+
 def test_sa_fused_supported_shapes():
     from jmodt_b200 import tc
     mk = lambda dims: [tc.PackedLayer(torch.zeros(dims[i + 1], dims[i]), None, True) for i in range(3)]
