@@ -201,7 +201,7 @@ tc_gemm_kernel(const TcGemmParams p) {
         const int kk = t & 7;                // k row inside a group of 8
         const int ng = (t >> 3) & 15;        // group of 8 columns inside the tile
         const int kh = t >> 7;               // this thread converts k blocks kh and kh + 2 of the chunk
-        uint32_t xctr = 0, rctr = 0;
+        uint32_t xctr = 0;
         long long *cdbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
         int cdi = 0;
 
