@@ -6,7 +6,8 @@
 
 A "step" is one pass of the hot path over one batch of `--frames` synthetic KITTI-shaped frames per GPU
 (16 384 points, 128 proposals per frame).  The workload names which part of the path is measured; see
-DESIGN.md for the exact op list and shapes of each workload.
+DESIGN.md §6 for the exact op list, shapes and how each JSON key is measured.  The default e2e workload replays the
+whole step as one CUDA graph (`--no-graph`: every kernel enqueued from Python); stdout carries exactly one JSON line.
 
 The CPU arm and the cpu_baseline leg are the only places that execute oracle/ (as the reported baseline).
 """
