@@ -18,14 +18,14 @@
 // (pointnet2_utils.py:241-290): X[k][n] = xyz[idx[n]][k] - centre[n / nsample][k] for k < 3 and
 // feats[k-3][idx[n]] otherwise — the grouped tensor is never materialised.
 //
-// Structure (v3): one persistent CTA per SM, 18 warps, every hand-off through mbarriers.
+// Structure (v4): one persistent CTA per SM, 19 warps, every hand-off through mbarriers (one arrival per warp).
 //   warp 17      scheduler: claims tiles from a global atomic counter (dynamic scheduling: a CTA that shares its SM
 //                with another stream's kernel simply claims fewer tiles) and publishes them in a shared-memory tile
 //                ring;  warp 18 streams the weights: one 16 KB cp.async.bulk chunk image per K chunk.
 //   warps 0-7    converters: raw fp32 chunk (shared memory) -> bf16 hi/lo split -> MN-major core-matrix images.
-//                Dense X is staged by the converters themselves with 16-byte cp.async (LDGSTS) three chunks ahead into
-//                a 4-stage raw ring whose mbarrier counts the copies (cp.async.mbarrier.arrive.noinc): 48 KB of loads
-//                in flight per SM, no registers held.  (v3 staged each 512-byte row with its own cp.async.bulk and
+//                Dense X is staged by the converters themselves with 16-byte cp.async (LDGSTS) into a 4-stage raw ring
+//                whose mbarrier counts the copies (cp.async.mbarrier.arrive.noinc), as two independent groups of
+//                four warps on alternate K chunks, each with two chunks in flight; no registers held.  (v3 staged each 512-byte row with its own cp.async.bulk and
 //                wrote each output row with another: ~780 bulk requests per tile at ~30 ns each through the SM's one
 //                TMA unit — 23 us per 128x128x512 tile, ncu tensor pipe 15 %.  Bulk copies are now only used where one
 //                request moves 16 KB.)  In gather mode they load through the neighbour index (register double-buffer).
