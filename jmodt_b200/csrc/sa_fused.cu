@@ -6,9 +6,11 @@
 // round-trips a 549 MB/frame grouped tensor and two 537 MB/frame activations through HBM; here a tile of 128
 // (centre, sample) columns never leaves the SM, and NO weight is re-read after the prologue:
 //
-//   * layer-1 weights (K1 <= 160) stay in shared memory for the lifetime of the persistent CTA (A operand, SS MMA);
 //   * layer-2 / layer-3 weights (bf16 hi and lo parts) stay in TENSOR MEMORY and are the A operand of TS-mode MMAs
 //     (TMEM map: 128 accumulator columns, 128 for W2, 128 per 128-row block of W3 -> at most 512);
+//   * layer-1 weights (K1 <= 160) stay in shared memory for the lifetime of the persistent CTA (SS MMA); when W3 is
+//     a single block (C3 <= 128) the 128 tensor-memory columns left over hold W1[:, :128] and layer 1 runs in TS mode
+//     as well (an SS MMA re-reads its 4 KB A operand from shared memory for every 64 columns);
 //   * a tile is processed as two 64-column halves with separate accumulators, operand images and worker groups
 //     (4 warps each), so one half's epilogue (TMEM -> bias/ReLU -> bf16 split -> next operand image, or max-pool)
 //     and its gather of the NEXT tile run while the tensor core works on the other half;
