@@ -21,7 +21,9 @@
 //     first version of this kernel).  The layer-1 operand is therefore staged K-major (B operand, b_major = K) with
 //     the channels first and the three relative coordinates last; W1's columns are permuted to match at pack time.
 //
-// Shapes: layer widths C1 = C2 = 128, C3 in {128, 256}; C_in % 8 == 0, C_in + 3 <= 160; nsample in {8,...,64} | 64.
+// Shapes: layer widths C1, C2 <= 128 and C3 <= 256 (weights zero-padded to the 128-row tile); C_in % 8 == 0 (0 = coordinates
+// only), C_in + 3 <= 160; nsample in {8, 16, 32, 64}; npoint * nsample a multiple of 128.  The ROWS instantiation of the same
+// kernel is the input stage of the per-proposal network (see the comment above sa_fused_kernel).
 #include "tc_common.cuh"
 
 #include <stdlib.h>
