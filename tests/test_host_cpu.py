@@ -101,3 +101,24 @@ def test_sa_fused_supported_shapes():
     assert not tc.sa_fused_supported(mk([259, 128, 196, 256]), 256, 256, 16)      # RPN level 2: too wide
     assert not tc.sa_fused_supported(mk([131, 128, 128, 128]), 128, 3, 8)         # npoint * nsample not a multiple of 128
     assert not tc.sa_fused_supported(mk([131, 128, 128, 128])[:2], 128, 128, 64)
+
+
+def test_tracking_oracle_corners_and_distance_properties():
+    """oracle/tracking_ref.py (restatement of kitti_utils.py:107-133 and data_association.py:10-28): corners against an
+    independent numpy construction; the distance score is 1 on the diagonal, symmetric, and < 1 elsewhere."""
+    from oracle import tracking_ref
+    g = torch.Generator().manual_seed(0)
+    n = 9
+    boxes = torch.cat([torch.rand(n, 3, generator=g) * 20, 1 + torch.rand(n, 3, generator=g) * 3,
+                       (torch.rand(n, 1, generator=g) * 2 - 1) * np.pi], dim=1)
+    corners = tracking_ref.boxes3d_to_corners3d(boxes).numpy()
+    for i in range(n):
+        x, y, z, h, w, l, ry = boxes[i].double().numpy()
+        xs = np.array([l, l, -l, -l, l, l, -l, -l]) / 2
+        ys = np.array([0, 0, 0, 0, -h, -h, -h, -h])
+        zs = np.array([w, -w, -w, w, w, -w, -w, w]) / 2
+        want = np.stack([np.cos(ry) * xs + np.sin(ry) * zs + x, ys + y, -np.sin(ry) * xs + np.cos(ry) * zs + z], axis=1)
+        np.testing.assert_allclose(corners[i], want, atol=1e-5)
+    d = tracking_ref.boxes_dist(boxes, boxes)
+    assert torch.allclose(torch.diagonal(d), torch.ones(n)) and torch.allclose(d, d.t(), atol=1e-6)
+    assert float((d - torch.eye(n)).max()) < 1.0
