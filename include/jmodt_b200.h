@@ -12,7 +12,13 @@
  *     iou3d.cpp:87-96); scratch memory is passed in by the caller, sized by the
  *     matching *_workspace_bytes() query;
  *   - outputs are fully written by the kernels, so callers need not zero-initialise them
- *     (the reference requires it for ball_query idx and roipool3d outputs).
+ *     (the reference requires it for ball_query idx and roipool3d outputs);
+ *   - re-entrant: entry points may be called from several host threads and for several
+ *     devices of one process (the reference's multi-GPU mode is single-process
+ *     nn.DataParallel, tools/train.py:86-87).  Whatever is cached (SM counts, the opt-in
+ *     shared-memory attribute of a kernel, the address of the tile-scheduler counters — a
+ *     __device__ array, so every device has its own copy without an allocation) is kept per
+ *     device, and the scheduler slot of a launch comes from an atomic sequence.
  *
  * Each declaration cites the reference interface it replaces (paths relative to the
  * reference repository root).

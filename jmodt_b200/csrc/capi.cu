@@ -15,6 +15,29 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int device_info(int *dev, int *sms) {
+    static int cache[JMB_MAX_DEVICES] = {0};      // written once per device with the same value: benign race
+    int d = 0;
+    JMB_CUDA(cudaGetDevice(&d));
+    JMB_REQUIRE(d >= 0 && d < JMB_MAX_DEVICES, "device index %d out of range", d);
+    int n = __atomic_load_n(&cache[d], __ATOMIC_RELAXED);
+    if (n == 0) {
+        JMB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d));
+        __atomic_store_n(&cache[d], n, __ATOMIC_RELAXED);
+    }
+    *dev = d;
+    *sms = n;
+    return JMB_OK;
+}
+
+int set_func_attr_once(const void *func, cudaFuncAttribute attr, int value, int dev, unsigned long long *mask) {
+    const unsigned long long bit = 1ULL << dev;
+    if (__atomic_load_n(mask, __ATOMIC_ACQUIRE) & bit) return JMB_OK;
+    JMB_CUDA(cudaFuncSetAttribute(func, attr, value));      // idempotent: two threads racing here both succeed
+    __atomic_fetch_or(mask, bit, __ATOMIC_RELEASE);
+    return JMB_OK;
+}
+
 }  // namespace jmb
 
 extern "C" int jmb_version(void) { return 1; }
@@ -29,7 +52,6 @@ extern "C" int jmb_set_device(int device) {
 
 extern "C" int jmb_sm_count(void) {
     int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return JMB_ERR_CUDA;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return JMB_ERR_CUDA;
-    return sms;
+    const int rc = jmb::device_info(&dev, &sms);
+    return rc == JMB_OK ? sms : rc;
 }

@@ -38,6 +38,21 @@ inline int check_launch(const char *what) {
         }                                                                     \
     } while (0)
 
+// ---- per-device state: the library may be driven on several GPUs from one process (the reference's only multi-GPU
+// mode is single-process nn.DataParallel, tools/train.py:86-87), so nothing device-dependent is cached process-wide.
+constexpr int JMB_MAX_DEVICES = 64;
+// current device and its SM count (cached per device, thread-safe); returns JMB_OK or an error code
+int device_info(int *dev, int *sms);
+// cudaFuncSetAttribute once per (kernel, device): `mask` is the call site's own per-device "already set" bit set
+int set_func_attr_once(const void *func, cudaFuncAttribute attr, int value, int dev, unsigned long long *mask);
+
+#define JMB_FUNC_ATTR_ONCE(kernel, attr, value, dev)                                                         \
+    do {                                                                                                     \
+        static unsigned long long mask__ = 0;                                                                \
+        int rc__ = ::jmb::set_func_attr_once(reinterpret_cast<const void *>(kernel), attr, value, dev, &mask__); \
+        if (rc__ != JMB_OK) return rc__;                                                                     \
+    } while (0)
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline long long div_up_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -232,11 +232,15 @@ extern "C" int jmb_proposal_layer(int B, int N, const float *proposals, const fl
         return JMB_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    proposal_select_kernel<<<dim3(2, B), 256, 0, st>>>(p, proposals, order, ws);
     const size_t smem = (size_t)p.max_post * 5 * sizeof(float);
     JMB_REQUIRE(smem <= 40 * 1024, "proposal_layer: post_nms_top_n too large");
+    proposal_select_kernel<<<dim3(2, B), 256, 0, st>>>(p, proposals, order, ws);
+    int rc = check_launch("proposal_layer(select)");
+    if (rc != JMB_OK) return rc;
     if (rotated) nms_greedy_batched_kernel<true><<<B * 2, 256, smem, st>>>(p, nms_thresh, ws);
     else nms_greedy_batched_kernel<false><<<B * 2, 256, smem, st>>>(p, nms_thresh, ws);
+    rc = check_launch("proposal_layer(nms)");
+    if (rc != JMB_OK) return rc;
     proposal_finalize_kernel<<<B, 128, 0, st>>>(p, proposals, scores, ws, ret_boxes, ret_scores);
-    return check_launch("proposal_layer");
+    return check_launch("proposal_layer(finalize)");
 }

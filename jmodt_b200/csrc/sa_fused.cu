@@ -538,14 +538,13 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     p.w3_blocks = p.Mt3; p.rows = 0; p.row_pitch = 0;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
     p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        JMB_CUDA(cudaGetDevice(&dev));
-        JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    int dev = 0, sms = 0;
+    {
+        const int rc = device_info(&dev, &sms);
+        if (rc != JMB_OK) return rc;
     }
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
     JMB_REQUIRE(tiles < (1LL << 31), "sa_fused: too many tiles");
     const int grid = (int)(tiles < sms ? tiles : sms);
@@ -591,14 +590,13 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
     p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C = 128; p.w3_blocks = 2;
     p.G = 1; p.npoint = 1; p.nsample = TC_BN; p.n_pts = 0;
     p.feats = in; p.out = out; p.out_point_major = 1; p.rows = rows; p.row_pitch = row_pitch;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        JMB_CUDA(cudaGetDevice(&dev));
-        JMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
-        JMB_CUDA(cudaFuncSetAttribute(sa_fused_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
+    int dev = 0, sms = 0;
+    {
+        const int rc = device_info(&dev, &sms);
+        if (rc != JMB_OK) return rc;
     }
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
     const long long tiles = rows / TC_BN;
     JMB_REQUIRE(tiles < (1LL << 31), "rcnn_input_fused: too many rows");
     const int grid = (int)(tiles < sms ? tiles : sms);

@@ -319,11 +319,10 @@ static int launch_fps_cluster(int b, int n, int m, int bs, int log2bs, int S, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (CL > 8) {
-        static bool allowed = false;
-        if (!allowed) {
-            cudaFuncSetAttribute(fps_cluster_kernel<CL, T, PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            allowed = true;
-        }
+        int dev = 0, sms = 0;
+        const int rc = device_info(&dev, &sms);
+        if (rc != JMB_OK) return rc;
+        JMB_FUNC_ATTR_ONCE((fps_cluster_kernel<CL, T, PPT>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1, dev);
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL, T, PPT>, n, m, bs, log2bs, S, dataset, temp, idxs);
     if (e != cudaSuccess) {
@@ -454,11 +453,10 @@ extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dat
     }
     // small batches: spread each frame over a thread-block cluster (latency); large batches: one CTA per frame
     // (throughput).  sms*2 is the point where single-CTA kernels already fill the machine.
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sms = 148;
+    int dev = 0, sms = 0;
+    {
+        const int rc = device_info(&dev, &sms);
+        if (rc != JMB_OK) return rc;
     }
     if (m > 1) {
         static int cfg_override = -1;   // JMB_FPS_CFG: tuning aid for profiles/fps_tune.py

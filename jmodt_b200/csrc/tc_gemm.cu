@@ -621,20 +621,24 @@ tc_gemm_kernel(const TcGemmParams p) {
     }
 }
 
-// Scheduler counters: 64 (counter, done) pairs per device, used round-robin so that launches which may overlap on
-// different streams never share a pair.  512 bytes, allocated once per device (the only allocation in the library).
-constexpr int TC_SCHED_SLOTS = 64;
+// Scheduler counters: TC_SCHED_SLOTS (counter, done) pairs in a __device__ array — every device the library runs on gets
+// its own zero-initialised copy with the module, so there is no allocation and no synchronisation on first use.  A launch
+// takes the next slot of a process-wide atomic sequence: two launches share a pair only if they are TC_SCHED_SLOTS
+// launches apart, i.e. never while both can be in flight (a captured graph bakes its slots in; graphs captured one
+// after the other hold disjoint slot ranges).  The last CTA of a launch re-arms its pair.
+constexpr int TC_SCHED_SLOTS = 4096;
+__device__ int g_tc_sched[2 * TC_SCHED_SLOTS];
+
 static int *tc_sched_buffer(int dev) {
-    static int *bufs[64] = {nullptr};
-    if (dev < 0 || dev >= 64) return nullptr;
-    if (!bufs[dev]) {
-        int *b = nullptr;
-        if (cudaMalloc(&b, 2 * TC_SCHED_SLOTS * sizeof(int)) != cudaSuccess) return nullptr;
-        if (cudaMemset(b, 0, 2 * TC_SCHED_SLOTS * sizeof(int)) != cudaSuccess) return nullptr;
-        cudaDeviceSynchronize();
-        bufs[dev] = b;
+    static int *bufs[JMB_MAX_DEVICES] = {nullptr};     // symbol address per device (same value written by every thread)
+    int *b = __atomic_load_n(&bufs[dev], __ATOMIC_ACQUIRE);
+    if (!b) {
+        void *sym = nullptr;
+        if (cudaGetSymbolAddress(&sym, g_tc_sched) != cudaSuccess) return nullptr;
+        b = static_cast<int *>(sym);
+        __atomic_store_n(&bufs[dev], b, __ATOMIC_RELEASE);
     }
-    return bufs[dev];
+    return b;
 }
 
 }  // namespace jmb
@@ -674,15 +678,15 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.use_raw = (mode == 0 && al16(x) && N % 4 == 0 && x_row_stride % 4 == 0 && x_group_stride % 4 == 0) ? 1 : 0;
     p.bulk_out = (out_mode == 0 && al16(y) && N % 4 == 0 && p.y_group_stride % 4 == 0) ? 1 : 0;
 
-    static int sms[64] = {0};
-    int dev = 0;
-    JMB_CUDA(cudaGetDevice(&dev));
-    JMB_REQUIRE(dev >= 0 && dev < 64, "tc_mlp_layer: device index %d", dev);
-    if (sms[dev] == 0) JMB_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    int dev = 0, sms = 0;
+    {
+        const int rc = device_info(&dev, &sms);
+        if (rc != JMB_OK) return rc;
+    }
     int *sched = tc_sched_buffer(dev);
-    JMB_REQUIRE(sched != nullptr, "tc_mlp_layer: cannot allocate the scheduler counters");
+    JMB_REQUIRE(sched != nullptr, "tc_mlp_layer: cannot resolve the scheduler counters");
     static unsigned launch_seq = 0;
-    const unsigned slot = (launch_seq++) % TC_SCHED_SLOTS;
+    const unsigned slot = __atomic_fetch_add(&launch_seq, 1u, __ATOMIC_RELAXED) % TC_SCHED_SLOTS;
     p.counter = sched + 2 * slot;
     p.done = sched + 2 * slot + 1;
 
@@ -695,12 +699,8 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     }
     p.dbg = dbg_buf;
     const size_t smem = (size_t)TC_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {
-        JMB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const int grid = (int)(tiles < (long long)sms[dev] ? tiles : (long long)sms[dev]);
+    JMB_FUNC_ATTR_ONCE(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, dev);
+    const int grid = (int)(tiles < (long long)sms ? tiles : (long long)sms);
     tc_gemm_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
     if (dbg_on) {
         long long hbuf[1024];
