@@ -591,8 +591,8 @@ def cpu_reference_e2e(threads, rcnn_sample=32, pair_sample=64):
         maps = model.rpn.backbone_net.image_features(torch.from_numpy(f["img"]))        # untimed, as on the GPU
         t0 = time.perf_counter()
         bxyz, feats = modules_ref.backbone_forward(model.rpn.backbone_net, xyz, xy, maps, cref)
-        rpn_cls = model.rpn.rpn_cls_layer(feats).transpose(1, 2)
-        rpn_reg = model.rpn.rpn_reg_layer(feats).transpose(1, 2)
+        rpn_cls = modules_ref.shared_mlp(model.rpn.rpn_cls_layer, feats).transpose(1, 2)
+        rpn_reg = modules_ref.shared_mlp(model.rpn.rpn_reg_layer, feats).transpose(1, 2)
         t_rpn = time.perf_counter() - t0
         t0 = time.perf_counter()
         cfg = model.rpn.cfg

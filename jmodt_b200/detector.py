@@ -112,15 +112,14 @@ class IALayer(nn.Module):
 
     def pack(self):
         w, b = tc.fold_conv_bn(self.conv1[0], self.conv1[1])
-        self._packed = {"conv1": tc.PackedLayer(w, b, True),
-                        "fc1": tc.PackedLayer(self.fc1.weight, self.fc1.bias, False),
-                        "fc2": tc.PackedLayer(self.fc2.weight, self.fc2.bias, False),
-                        "fc3": tc.PackedLayer(self.fc3.weight, self.fc3.bias, False)}
-        return self._packed
+        return {"conv1": tc.PackedLayer(w, b, True),
+                "fc1": tc.PackedLayer(self.fc1.weight, self.fc1.bias, False),
+                "fc2": tc.PackedLayer(self.fc2.weight, self.fc2.bias, False),
+                "fc3": tc.PackedLayer(self.fc3.weight, self.fc3.bias, False)}
 
     @torch.no_grad()
     def forward(self, img_feas, point_feas):
-        P = self._packed or self.pack()
+        P = tc.packed_for(self, self.pack)
         img_feas, point_feas = img_feas.contiguous(), point_feas.contiguous()
         # three independent projections of the inputs: forked streams (runtime.parallel)
         ri, rp, conv = runtime.parallel(lambda: tc.mlp_layer(P["fc1"], img_feas),      # (B, rc, N)
@@ -146,11 +145,9 @@ class AttentionFusion(nn.Module):
 
     @torch.no_grad()
     def forward(self, point_features, img_features):
-        if self._packed is None:
-            w, b = tc.fold_conv_bn(self.conv1, self.bn1)
-            self._packed = tc.PackedLayer(w, b, True)
+        packed = tc.packed_for(self, lambda: tc.PackedLayer(*tc.fold_conv_bn(self.conv1, self.bn1), True))
         img_features = self.IA_Layer(img_features, point_features)
-        return tc.mlp_layer(self._packed, torch.cat([point_features, img_features], dim=1).contiguous())
+        return tc.mlp_layer(packed, torch.cat([point_features, img_features], dim=1).contiguous())
 
 
 class PointNet2MSG(nn.Module):
@@ -209,7 +206,13 @@ class PointNet2MSG(nn.Module):
         return maps, fused
 
     overlap_geometry = True
-    l0_chunks = int(os.environ.get("JMB_L0_CHUNKS", "8"))     # prefixes of the level-0 FPS output consumed while it runs
+    # Opt-in (JMB_L0_CHUNKS=8): consume the level-0 FPS output in prefixes while the sampler is still running.  The
+    # gates (`wait_indices`) poll a buffer another stream's kernel fills, which needs that kernel to be making progress
+    # concurrently — true on an otherwise idle B200 (the sampler holds 64 of 148 SMs) but not something CUDA guarantees,
+    # so the default is 1: level 0 waits for the sampler's completion event like every other level.  The throughput path
+    # (`PointRCNN.geometry` + `forward(..., geometry=...)`, bench.py) takes the whole coordinate stage off the critical
+    # path instead by computing it one step ahead.
+    l0_chunks = int(os.environ.get("JMB_L0_CHUNKS", "1"))
 
     def _geometry(self, xyz):
         """FPS, ball query and three_nn depend on coordinates only, the MLP stacks on features only.  In eval mode the
@@ -344,13 +347,14 @@ class RPN(nn.Module):
     @torch.no_grad()
     def forward(self, input_data, image_maps=None):
         from .head import _pack_stack, run_stack
-        if self._packed is None:
-            self._packed = (_pack_stack(self.rpn_cls_layer), _pack_stack(self.rpn_reg_layer))
+        if self.training:
+            raise RuntimeError("jmodt_b200.detector.RPN is inference only: call .eval() first")
+        packed = tc.packed_for(self, lambda: (_pack_stack(self.rpn_cls_layer), _pack_stack(self.rpn_reg_layer)))
         xyz, feats = self.backbone_net(input_data["pts_input"], input_data.get("img"), input_data.get("pts_xy"),
                                        image_maps=image_maps)
         rpn_cls, rpn_reg = runtime.parallel(
-            lambda: run_stack(self._packed[0], feats, point_major_out=True),      # (B, N, 1): transposed by the epilogue
-            lambda: run_stack(self._packed[1], feats, point_major_out=True))      # (B, N, 76)
+            lambda: run_stack(packed[0], feats, point_major_out=True),      # (B, N, 1): transposed by the epilogue
+            lambda: run_stack(packed[1], feats, point_major_out=True))      # (B, N, 76)
         return {"rpn_cls": rpn_cls, "rpn_reg": rpn_reg, "backbone_xyz": xyz, "backbone_features": feats}
 
 
@@ -539,7 +543,8 @@ class PointRCNN(nn.Module):
 
     @torch.no_grad()
     def pair_affinity(self, rcnn_feat, rois_per_frame):
-        """Link / start-end scores between consecutive frames (t, t+1) of a batch: rcnn_feat (B*M, 512, 1)."""
+        """Link / start-end scores of the disjoint frame pairs (0, 1), (2, 3), ... of a batch (an odd last frame is
+        left out): rcnn_feat (B*M, 512, 1) -> one (link (M, M), start (M,), end (M,), logits (M, M)) per pair."""
         f = rcnn_feat.view(-1, rois_per_frame, rcnn_feat.shape[1])
         npairs = f.shape[0] // 2
         link, start, end, logits = affinity_batched(self.rcnn_net, f[0:2 * npairs:2], f[1:2 * npairs:2])

@@ -132,22 +132,25 @@ class RCNN(nn.Module):
     # ---- packing ----------------------------------------------------------------------------
     def pack(self):
         """(Re)build the tensor-core weight images from the current parameters (call after loading weights)."""
-        self._packed = {
+        if self.training:
+            raise RuntimeError("jmodt_b200.head.RCNN is inference only: call .eval() first")
+        P = {
             "xyz_up": _pack_stack(self.xyz_up_layer), "merge_down": _pack_stack(self.merge_down_layer),
             "sa": [_pack_stack(sa.mlps[0]) for sa in self.SA_modules],
             "cls": _pack_stack(self.cls_layer), "reg": _pack_stack(self.reg_layer),
             "link": _pack_stack(self.link_layer), "se": _pack_stack(self.se_layer),
         }
-        up = self._packed["xyz_up"]
+        up = P["xyz_up"]
         if len(up) == 2 and up[0].K <= 8 and up[0]._w32 is not None:
             w8 = torch.zeros(up[0].M, 8, dtype=torch.float32, device=up[0].bias.device)
             w8[:, : up[0].K] = up[0]._w32
-            self._packed["xyz_up_w8"] = tc.PackedLayer(w8, up[0].bias[: up[0].M], up[0].relu)
-        return self._packed
+            P["xyz_up_w8"] = tc.PackedLayer(w8, up[0].bias[: up[0].M], up[0].relu)
+        return P
 
     @property
     def packed(self):
-        return self._packed if self._packed is not None else self.pack()
+        """Packed weight images of the current parameters (re-packed after load_state_dict / .to() / in-place updates)."""
+        return tc.packed_for(self, self.pack)
 
     # ---- forward ----------------------------------------------------------------------------
     @torch.no_grad()
@@ -271,58 +274,63 @@ def pack_point_features(extra, rpn_features: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pair_corr(pt: torch.Tensor, dt: torch.Tensor):
+def pair_corr(pt: torch.Tensor, dt: torch.Tensor, want_cor: bool = True, want_mean_p: bool = True,
+              want_mean_d: bool = True):
     """|p_i - d_j| features of G frame pairs and their two means in one kernel (csrc/pair_corr.cu):
-    pt (G, K, P), dt (G, K, D) channel-first -> cor (G, K, P*D), mean over i (G, K, D), mean over j (G, K, P)."""
+    pt (G, K, P), dt (G, K, D) channel-first -> cor (G, K, P*D), mean over i (G, K, D), mean over j (G, K, P);
+    an output that is not wanted is not computed (None)."""
     G, K, P = pt.shape
     D = dt.shape[2]
     assert dt.shape[:2] == (G, K) and pt.is_contiguous() and dt.is_contiguous() and pt.dtype == dt.dtype == torch.float32
-    cor = torch.empty((G, K, P * D), dtype=torch.float32, device=pt.device)
-    mean_p = torch.empty((G, K, D), dtype=torch.float32, device=pt.device)
-    mean_d = torch.empty((G, K, P), dtype=torch.float32, device=pt.device)
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=pt.device)
+    cor = new(G, K, P * D) if want_cor else None
+    mean_p = new(G, K, D) if want_mean_p else None
+    mean_d = new(G, K, P) if want_mean_d else None
     st = _lib.stream_and_device(pt)
-    _lib.check(_lib.lib().jmb_pair_corr(G, K, P, D, pt.data_ptr(), dt.data_ptr(), cor.data_ptr(), mean_p.data_ptr(),
-                                        mean_d.data_ptr(), st), "pair_corr")
+    _lib.check(_lib.lib().jmb_pair_corr(G, K, P, D, pt.data_ptr(), dt.data_ptr(), _lib.ptr(cor), _lib.ptr(mean_p),
+                                        _lib.ptr(mean_d), st), "pair_corr")
     return cor, mean_p, mean_d
 
 
+def _stacks(link_model, se_model):
+    """Packed layer stacks of the link / start-end heads (any pt_utils.Conv1d nn.Sequential, e.g. the reference's
+    `rcnn_net.link_layer` / `se_layer` handed to the tracker at tools/eval.py:333-336); cached on the modules."""
+    return (tc.packed_for(link_model, lambda: _pack_stack(link_model)),
+            tc.packed_for(se_model, lambda: _pack_stack(se_model)))
+
+
 @torch.no_grad()
-def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
-    """`affinity` for G frame pairs at once: pred_features (G, P, 512), det_features (G, D, 512) ->
-    link (G, P, D), start (G, D), end (G, P), logits (G, P, D).  One launch per layer for all pairs."""
+def affinity_scores_batched(link_model, se_model, pred_features: torch.Tensor, det_features: torch.Tensor):
+    """Link and start / end scores of G frame pairs at once (reference tracker.py:81-112 per pair; the training
+    twin is rcnn.py:239-258): pred_features (G, P, 512), det_features (G, D, 512) ->
+    link (G, P, D) = (softmax over successors + softmax over predecessors) / 2, start (G, D), end (G, P) (after the
+    sigmoid), raw link logits (G, P, D).  One launch per layer for all pairs."""
     G, P, _ = pred_features.shape
     D = det_features.shape[1]
-    packed = rcnn.packed
+    link_stack, se_stack = _stacks(link_model, se_model)
     pt = pred_features.transpose(1, 2).contiguous()                                       # (G, 512, P)
     dt = det_features.transpose(1, 2).contiguous()                                        # (G, 512, D)
     cor, mean_p, mean_d = pair_corr(pt, dt)          # (G, 512, P*D), mean over predecessors (G, 512, D), over successors (G, 512, P)
 
     def link_branch():
-        logits = run_stack(packed["link"], cor).view(G, P, D)
+        logits = run_stack(link_stack, cor).view(G, P, D)
         col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)   # softmax over predecessors
         return (torch.softmax(logits, dim=2) + col) / 2, logits
 
     (link, logits), start, end = runtime.parallel(
         link_branch,
-        lambda: torch.sigmoid(run_stack(packed["se"], mean_p)).view(G, D),
-        lambda: torch.sigmoid(run_stack(packed["se"], mean_d)).view(G, P))
+        lambda: torch.sigmoid(run_stack(se_stack, mean_p)).view(G, D),
+        lambda: torch.sigmoid(run_stack(se_stack, mean_d)).view(G, P))
     return link, start, end, logits
 
 
-@torch.no_grad()
+def affinity_batched(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
+    """`affinity_scores_batched` with the heads of an RCNN module."""
+    return affinity_scores_batched(rcnn.link_layer, rcnn.se_layer, pred_features, det_features)
+
+
 def affinity(rcnn: RCNN, pred_features: torch.Tensor, det_features: torch.Tensor):
-    """Link and start/end scores between two sets of proposal features (reference tracker.py:81-112; the
-    training twin is rcnn.py:239-258).  pred_features (P, 512), det_features (D, 512) ->
-    link_scores (P, D) = (softmax_row + softmax_col) / 2, start (D,), end (P,) (after sigmoid),
-    plus the raw link logits (P, D)."""
-    P, D = pred_features.shape[0], det_features.shape[0]
-    packed = rcnn.packed
-    pt, dt = pred_features.t().contiguous(), det_features.t().contiguous()               # (512, P), (512, D)
-    cor = (pt.unsqueeze(2) - dt.unsqueeze(1)).abs()                                       # (512, P, D)
-    logits = run_stack(packed["link"], cor.view(1, -1, P * D))[0].view(P, D)
-    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
-    start_in = cor.mean(dim=1).unsqueeze(0).contiguous()                                  # (1, 512, D)
-    end_in = cor.mean(dim=2).unsqueeze(0).contiguous()                                    # (1, 512, P)
-    start = torch.sigmoid(run_stack(packed["se"], start_in)).flatten()
-    end = torch.sigmoid(run_stack(packed["se"], end_in)).flatten()
-    return link, start, end, logits
+    """One frame pair: pred_features (P, 512), det_features (D, 512) -> link (P, D), start (D,), end (P,), logits (P, D)."""
+    link, start, end, logits = affinity_scores_batched(rcnn.link_layer, rcnn.se_layer, pred_features.unsqueeze(0),
+                                                       det_features.unsqueeze(0))
+    return link[0], start[0], end[0], logits[0]

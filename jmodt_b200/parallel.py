@@ -46,6 +46,92 @@ def gather_rows(tile: torch.Tensor, total_rows: int, group=None) -> torch.Tensor
     return torch.cat(parts, dim=0)
 
 
+def gather_packed(parts, sizes_fn, group=None, timer=None):
+    """ONE all-gather for several ragged per-rank pieces: every rank flattens its pieces into one buffer padded to the
+    largest rank's size, the buffers are exchanged with a single `all_gather_into_tensor`, and piece k of rank r is
+    returned as a flat view of length sizes_fn(r)[k].  Returns a list (per piece) of lists (per rank)."""
+    world = dist.get_world_size(group)
+    sizes = [sizes_fn(r) for r in range(world)]
+    cap = max(sum(sz) for sz in sizes)
+    flat = torch.cat([p.reshape(-1) for p in parts]) if parts else None
+    buf = flat.new_zeros(cap)
+    buf[: flat.numel()] = flat
+    out = flat.new_empty(world * cap)
+    if timer is not None:
+        timer[0].record()
+    dist.all_gather_into_tensor(out, buf, group=group)
+    if timer is not None:
+        timer[1].record()
+    res = [[] for _ in parts]
+    for r in range(world):
+        off = r * cap
+        for k, n in enumerate(sizes[r]):
+            res[k].append(out[off: off + n])
+            off += n
+    return res
+
+
+@torch.no_grad()
+def sharded_affinity_device(link_model, se_model, pred_features: torch.Tensor, det_features: torch.Tensor, group=None,
+                            timer=None):
+    """BASELINE config 4 on the sm_100a kernels: one P x D frame pair scored by all ranks of `group`.
+
+    Both feature matrices are replicated (256 KB each).  Rank r owns predecessor rows [lo, hi) and successor columns
+    [clo, chi): it computes its (p, D) tile of link logits (pair-correlation kernel on its rows -> link stack on
+    tcgen05), the `end` scores of its rows, and the `start` scores of its columns over ALL predecessors.  The one
+    exchange is a single all-gather that carries the logit tile with the two score slices behind it (16.5 KB per
+    rank at 128 x 128 on 4 ranks); it is required because softmax(dim=0) (reference tracker.py:88) spans all rows.
+    A column of the layer kernel's output depends on that column's inputs only, so the gathered logits are
+    bit-identical to the single-GPU result.  Returns link (P, D), start (D,), end (P,), logits (P, D) on every rank."""
+    from .head import _stacks, pair_corr, run_stack
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    P, D = pred_features.shape[0], det_features.shape[0]
+    lo, hi = row_shard(P, rank, world)
+    clo, chi = row_shard(D, rank, world)
+    link_stack, se_stack = _stacks(link_model, se_model)
+    pt = pred_features.t().contiguous()            # (C, P)
+    dt = det_features.t().contiguous()             # (C, D)
+    dev = pred_features.device
+    tile = torch.empty((0, D), dtype=torch.float32, device=dev)
+    end_local = torch.empty(0, dtype=torch.float32, device=dev)
+    start_local = torch.empty(0, dtype=torch.float32, device=dev)
+    if hi > lo:
+        cor, _, mean_d = pair_corr(pt[:, lo:hi].contiguous().unsqueeze(0), dt.unsqueeze(0), want_mean_p=False)
+        tile = run_stack(link_stack, cor).view(hi - lo, D)
+        end_local = torch.sigmoid(run_stack(se_stack, mean_d)).view(-1)
+    if chi > clo:
+        _, mean_p, _ = pair_corr(pt.unsqueeze(0), dt[:, clo:chi].contiguous().unsqueeze(0), want_cor=False,
+                                 want_mean_d=False)
+        start_local = torch.sigmoid(run_stack(se_stack, mean_p)).view(-1)
+    if world > 1:
+        def sizes(r):
+            a, b = row_shard(P, r, world)
+            c, d = row_shard(D, r, world)
+            return ((b - a) * D, b - a, d - c)
+        tiles, ends, starts = gather_packed([tile, end_local, start_local], sizes, group, timer)
+        logits = torch.cat(tiles).view(P, D)
+        end, start = torch.cat(ends), torch.cat(starts)
+    else:
+        logits, end, start = tile, end_local, start_local
+    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
+    return link, start, end, logits
+
+
+def exchange_boundary_features(first_frame_features: torch.Tensor, group=None, timer=None):
+    """Frame-sharded sequences: the affinity pair that straddles two shards (last frame of rank r, first frame of rank
+    r + 1) needs the right neighbour's first-frame RCNN features (M, C).  One all-gather of those (256 KB per rank);
+    returns the neighbour's features, or None on the last rank."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    x = first_frame_features.contiguous()
+    out = x.new_empty((world,) + tuple(x.shape))
+    if timer is not None:
+        timer[0].record()
+    dist.all_gather_into_tensor(out, x, group=group)
+    if timer is not None:
+        timer[1].record()
+    return out[rank + 1] if rank + 1 < world else None
+
+
 def sharded_affinity(logits_fn: Callable, se_fn: Callable, pred_features: torch.Tensor, det_features: torch.Tensor,
                      group=None):
     """Link / start / end scores of one frame pair computed by all ranks of `group`.
@@ -59,8 +145,6 @@ def sharded_affinity(logits_fn: Callable, se_fn: Callable, pred_features: torch.
     P, D = pred_features.shape[0], det_features.shape[0]
     lo, hi = row_shard(P, rank, world)
     tile = logits_fn(pred_features[lo:hi], det_features) if hi > lo else pred_features.new_zeros(0, D)
-    logits = gather_rows(tile.contiguous(), P, group) if world > 1 else tile
-    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
     # end scores: mean over successors of |p_i - d_j| for the local rows
     cor_rows = (pred_features[lo:hi].unsqueeze(1) - det_features.unsqueeze(0)).abs()           # (p, D, C)
     end_local = se_fn(cor_rows.mean(dim=1)) if hi > lo else pred_features.new_zeros(0)
@@ -69,8 +153,13 @@ def sharded_affinity(logits_fn: Callable, se_fn: Callable, pred_features: torch.
     cor_cols = (pred_features.unsqueeze(1) - det_features[clo:chi].unsqueeze(0)).abs()         # (P, d, C)
     start_local = se_fn(cor_cols.mean(dim=0)) if chi > clo else pred_features.new_zeros(0)
     if world > 1:
-        end = gather_rows(end_local.view(-1, 1), P, group).flatten()
-        start = gather_rows(start_local.view(-1, 1), D, group).flatten()
+        def sizes(r):
+            a, b = row_shard(P, r, world)
+            c, d = row_shard(D, r, world)
+            return ((b - a) * D, b - a, d - c)
+        tiles, ends, starts = gather_packed([tile.contiguous(), end_local, start_local], sizes, group)   # the ONE exchange
+        logits, end, start = torch.cat(tiles).view(P, D), torch.cat(ends), torch.cat(starts)
     else:
-        end, start = end_local, start_local
+        logits, end, start = tile, end_local, start_local
+    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
     return link, start, end, logits

@@ -96,7 +96,8 @@ class _PointnetSAModuleBase(nn.Module):
 
         pooled = []
         for grouper, mlp in zip(self.groupers, self.mlps):
-            grouped = mlp(grouper(xyz, new_xyz, features))  # (B, mlp[-1], npoint, nsample)
+            with pt_utils.torch_layers():    # op-by-op composition: the SharedMLP runs its torch forward (autograd / reference)
+                grouped = mlp(grouper(xyz, new_xyz, features))  # (B, mlp[-1], npoint, nsample)
             if self.pool_method == 'max_pool':
                 grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
             elif self.pool_method == 'avg_pool':
@@ -113,11 +114,10 @@ class _PointnetSAModuleBase(nn.Module):
 
     # ---- fused inference path: grouping fused into the first layer, max-pool into the last ----------
     def pack(self):
-        self._packed = [pack_shared_mlp(m) for m in self.mlps]
-        return self._packed
+        return [pack_shared_mlp(m) for m in self.mlps]
 
     def _forward_fused(self, xyz, features, new_xyz, nbr):
-        packed = getattr(self, "_packed", None) or self.pack()
+        packed = tc.packed_for(self, self.pack)
         if features is not None:
             features = features.contiguous()
         fuse = getattr(self, "fuse_chain", True)
@@ -212,9 +212,10 @@ class PointnetFPModule(nn.Module):
         fused = _use_fused(self)
         packed = None
         if fused:
-            packed = getattr(self, "_packed", None)
-            if packed is None:
-                packed = self._packed = pack_shared_mlp(self.mlp)
+            def build():
+                self._first_linear = None
+                return pack_shared_mlp(self.mlp)
+            packed = tc.packed_for(self, build)
         if known is not None:
             idx, weight = plan if plan is not None else self.plan(unknown, known)
             if fused and self.interp_after_first_layer and packed[0].relu and packed[0]._w32 is not None and \
@@ -253,4 +254,5 @@ class PointnetFPModule(nn.Module):
             for layer in packed:
                 h = tc.mlp_layer(layer, h)
             return h
-        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+        with pt_utils.torch_layers():
+            return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)

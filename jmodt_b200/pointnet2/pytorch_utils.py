@@ -5,15 +5,64 @@ jmodt/ops/pointnet2/pytorch_utils.py:6-236), so reference checkpoints load key f
     <name>layer{i}.conv.weight / .conv.bias / .bn.bn.{weight,bias,running_mean,running_var}
 
 (`load_checkpoint` in the reference uses strict=False, train_utils.py:31-47, which would
-silently skip a renamed key.)  These modules only hold parameters and define the unfused
-forward; the fused sm_100a kernels read the same parameters through
-`jmodt_b200.fused.fold_shared_mlp`.
+silently skip a renamed key.)
+
+forward(): in eval mode with autograd off and CUDA input, every 1x1 conv / Linear block (+ folded eval-mode
+BatchNorm, + ReLU) runs on the tcgen05 layer kernel (`jmodt_b200.tc.mlp_layer`, csrc/tc_gemm.cu), so reference code
+that calls these modules directly — `rcnn.py:178-196`, `rpn.py:81-82`, `tracker.py:86,106,109` — reaches the
+tensor cores through the drop-in.  Training (or CPU tensors, or a block the kernel does not cover) takes the
+module's own torch forward, which is what autograd needs.  The fused set-abstraction / feature-propagation paths
+read the same parameters through `jmodt_b200.tc.fold_conv_bn`.
 """
 from __future__ import annotations
 
 from typing import List, Tuple
 
+import torch
 import torch.nn as nn
+
+
+_torch_only = 0
+
+
+class torch_layers:
+    """Context manager: inside it every block runs its torch (cuDNN / cuBLAS) forward even in eval mode — the
+    reference composition the parity tests compare the tensor-core path with."""
+
+    def __enter__(self):
+        global _torch_only
+        _torch_only += 1
+
+    def __exit__(self, *exc):
+        global _torch_only
+        _torch_only -= 1
+
+
+def _on_tensor_cores(module: nn.Module, x) -> bool:
+    """Inference on the device: eval mode, autograd off, fp32 CUDA input."""
+    return (_torch_only == 0 and not module.training and not torch.is_grad_enabled() and isinstance(x, torch.Tensor)
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2 and x.numel() > 0)
+
+
+def _tc_linear(packed, x: torch.Tensor) -> torch.Tensor:
+    """y[b, :, ...] = act(W . x[b, :, ...] + bias) on the tcgen05 layer kernel; x (B, C, *spatial) -> (B, M, *spatial).
+
+    A batch of single-column problems — (G, C, 1) is how the reference feeds its cls / reg / link / start-end heads
+    (`rcnn.py:195-196`, `tracker.py:86,106,109`) — is ONE (C, G) channel-first problem, not G tiles of one column: the
+    result is returned as the transposed view (G, M, 1) of the (M, G) output, which the next layer of the stack
+    recognises and consumes without a copy."""
+    from .. import tc
+    B, C = x.shape[0], x.shape[1]
+    spatial = x.shape[2:]
+    n = 1
+    for d in spatial:
+        n *= d
+    if n == 1 and B > 1:
+        xt = x.reshape(B, C).t()                      # (C, G): free when x is the previous layer's transposed view
+        y = tc.mlp_layer(packed, xt.contiguous().unsqueeze(0))[0]          # (M, G)
+        return y.t().reshape(B, packed.M, *spatial)   # a view: (G, M) has strides (1, G)
+    y = tc.mlp_layer(packed, x.reshape(B, C, n).contiguous())
+    return y.view(B, packed.M, *spatial)
 
 
 def _norm_act_conv(seq: nn.Sequential, *, conv, norm, act, inorm, preact: bool, name: str):
@@ -62,6 +111,25 @@ class _ConvBase(nn.Sequential):
         norm = batch_norm(width) if bn else None
         inorm = instance_norm_func(width, affine=False, track_running_stats=False) if instance_norm else None
         _norm_act_conv(self, conv=conv_unit, norm=norm, act=activation, inorm=inorm, preact=preact, name=name)
+        # conv -> [BN] -> [ReLU] with a 1x1 kernel is one tensor-core layer; anything else keeps the torch forward
+        one = all(k == 1 for k in conv_unit.kernel_size) and all(v == 1 for v in conv_unit.stride) and \
+            all(v == 0 for v in conv_unit.padding)
+        self._tc_ok = bool(one and not preact and not instance_norm and
+                           (activation is None or isinstance(activation, nn.ReLU)))
+        self._tc_names = (name + "conv", name + "bn" if bn else None, activation is not None)
+
+    def _pack(self):
+        from .. import tc
+        conv_name, bn_name, relu = self._tc_names
+        bn = getattr(self, bn_name).bn if bn_name else None
+        w, b = tc.fold_conv_bn(getattr(self, conv_name), bn)
+        return tc.PackedLayer(w, b, relu=relu)
+
+    def forward(self, x):
+        if self._tc_ok and _on_tensor_cores(self, x) and x.dim() >= 3:
+            from .. import tc
+            return _tc_linear(tc.packed_for(self, self._pack), x)
+        return super().forward(x)
 
 
 class Conv1d(_ConvBase):
@@ -120,3 +188,18 @@ class FC(nn.Sequential):
                 self.add_module(name + "bn", norm)
             if activation is not None:
                 self.add_module(name + "activation", activation)
+        self._tc_ok = bool(not preact and (activation is None or isinstance(activation, nn.ReLU)))
+        self._tc_names = (name + "fc", name + "bn" if bn else None, activation is not None)
+
+    def _pack(self):
+        from .. import tc
+        fc_name, bn_name, relu = self._tc_names
+        bn = getattr(self, bn_name).bn if bn_name else None
+        w, b = tc.fold_conv_bn(getattr(self, fc_name), bn)
+        return tc.PackedLayer(w, b, relu=relu)
+
+    def forward(self, x):
+        if self._tc_ok and _on_tensor_cores(self, x) and x.dim() == 2 and x.shape[0] > 1:
+            from .. import tc
+            return _tc_linear(tc.packed_for(self, self._pack), x.unsqueeze(-1)).squeeze(-1)      # (B, in) -> (B, out)
+        return super().forward(x)

@@ -6,6 +6,8 @@ stage is filled with ONE contiguous 16 KB bulk copy.
 """
 from __future__ import annotations
 
+import itertools
+
 import torch
 
 from . import _lib
@@ -60,6 +62,26 @@ class PackedLayer:
         if self._xyz_last_pack is None:
             self._xyz_last_pack = PackedLayer(self._w32, self.bias[: self.M], self.relu, xyz_last=True)
         return self._xyz_last_pack
+
+
+def weights_token(module) -> tuple:
+    """Identity of a module's current weights: (storage address, in-place version counter) of every parameter and
+    buffer.  `load_state_dict` and optimizer steps bump the version counter; `.to()` / `.cuda()` / `.float()`
+    replace the storage."""
+    return tuple((t.data_ptr(), t._version) for t in itertools.chain(module.parameters(), module.buffers()))
+
+
+def packed_for(module, build, attr: str = "_packed"):
+    """The packed weight images cached on `module` under `attr`, rebuilt by `build()` whenever the module's
+    parameters or buffers have changed since they were packed (the reference loads checkpoints with strict=False,
+    train_utils.py:31-47, after the model may already have run once — a stale image would go unnoticed)."""
+    d = module.__dict__
+    tok = weights_token(module)
+    if d.get(attr) is None or d.get("_pack_token") != tok:
+        d[attr] = None
+        d[attr] = build()
+        d["_pack_token"] = tok
+    return d[attr]
 
 
 def fold_conv_bn(conv, bn=None):

@@ -9,7 +9,14 @@ import torch.nn.functional as F
 
 
 def shared_mlp(seq, x):
-    """SharedMLP / Conv1d stack forward (pytorch_utils.py:6-33): the modules ARE torch modules."""
+    """SharedMLP / Conv1d stack forward (pytorch_utils.py:6-33) through the LEAF torch modules (nn.Conv1d/2d,
+    BatchNorm, ReLU, Dropout) in registration order — i.e. exactly nn.Sequential.forward of the reference classes,
+    spelled out so that a container whose own forward has been replaced (the package under test routes eval-mode
+    blocks to its tensor-core kernel) cannot put the code under test into its own oracle."""
+    if isinstance(seq, torch.nn.Sequential):
+        for child in seq:
+            x = shared_mlp(child, x)
+        return x
     return seq(x)
 
 
@@ -29,9 +36,9 @@ def rcnn_forward_points(rcnn, pts_input, fps_fn, ball_fn):
     cin = rcnn.rcnn_input_channel
     xyz = pts_input[..., 0:3].contiguous()
     xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous().unsqueeze(3)
-    xyz_feature = rcnn.xyz_up_layer(xyz_input)
+    xyz_feature = shared_mlp(rcnn.xyz_up_layer, xyz_input)
     rpn_feature = pts_input[..., cin:].transpose(1, 2).contiguous().unsqueeze(3)
-    merged = rcnn.merge_down_layer(torch.cat((xyz_feature, rpn_feature), dim=1))
+    merged = shared_mlp(rcnn.merge_down_layer, torch.cat((xyz_feature, rpn_feature), dim=1))
     l_xyz, l_feat = xyz, merged.squeeze(3)
     for sa in rcnn.SA_modules:
         if sa.npoint is not None:
@@ -42,11 +49,11 @@ def rcnn_forward_points(rcnn, pts_input, fps_fn, ball_fn):
         else:
             new_xyz = None
             grouped = torch.cat([l_xyz.transpose(1, 2).unsqueeze(2), l_feat.unsqueeze(2)], dim=1)
-        h = sa.mlps[0](grouped)
+        h = shared_mlp(sa.mlps[0], grouped)
         h = F.max_pool2d(h, kernel_size=[1, h.size(3)]).squeeze(-1)
         l_xyz, l_feat = new_xyz, h
-    rcnn_cls = rcnn.cls_layer(l_feat).squeeze(-1)
-    rcnn_reg = rcnn.reg_layer(l_feat).squeeze(-1)
+    rcnn_cls = shared_mlp(rcnn.cls_layer, l_feat).squeeze(-1)
+    rcnn_reg = shared_mlp(rcnn.reg_layer, l_feat).squeeze(-1)
     return rcnn_cls, rcnn_reg, l_feat
 
 
@@ -55,10 +62,10 @@ def affinity(link_layer, se_layer, pred_features, det_features):
     num_pred, num_det = pred_features.shape[0], det_features.shape[0]
     cor_feat = torch.abs(pred_features.unsqueeze(1).repeat(1, num_det, 1)
                          - det_features.unsqueeze(0).repeat(num_pred, 1, 1))
-    logits = link_layer(cor_feat.view(num_pred * num_det, -1, 1)).view(num_pred, num_det)
+    logits = shared_mlp(link_layer, cor_feat.view(num_pred * num_det, -1, 1)).view(num_pred, num_det)
     link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
-    start = torch.sigmoid(se_layer(cor_feat.mean(dim=0).unsqueeze(-1))).flatten()
-    end = torch.sigmoid(se_layer(cor_feat.mean(dim=1).unsqueeze(-1))).flatten()
+    start = torch.sigmoid(shared_mlp(se_layer, cor_feat.mean(dim=0).unsqueeze(-1))).flatten()
+    end = torch.sigmoid(shared_mlp(se_layer, cor_feat.mean(dim=1).unsqueeze(-1))).flatten()
     return link, start, end, logits
 
 
@@ -86,7 +93,7 @@ def sa_msg_forward(sa, xyz, features, cref):
         if features is not None:
             gf = torch.gather(features, 2, flat.expand(-1, features.shape[1], -1)).view(B, -1, m, ns)
             gx = torch.cat([gx, gf], dim=1)
-        h = mlp(gx)
+        h = shared_mlp(mlp, gx)
         outs.append(F.max_pool2d(h, kernel_size=[1, h.size(3)]).squeeze(-1))
     return new_xyz, torch.cat(outs, dim=1), idx
 
@@ -99,7 +106,7 @@ def fp_forward(fp, unknown, known, unknow_feats, known_feats, cref):
     weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
     interp = torch.from_numpy(cref.three_interpolate(_np(known_feats), idx, _np(weight)))
     new_features = interp if unknow_feats is None else torch.cat([interp, unknow_feats], dim=1)
-    return fp.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+    return shared_mlp(fp.mlp, new_features.unsqueeze(-1)).squeeze(-1)
 
 
 def ia_fusion_forward(fusion, point_features, img_features):

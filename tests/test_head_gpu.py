@@ -81,7 +81,8 @@ def test_rcnn_input_stage_single_kernel_vs_layers(cuda):
     rows[..., :133] = torch.randn(5, 512, 133, generator=g)
     rows = rows.to(cuda)
     got = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], rows)
-    with torch.no_grad():
+    from jmodt_b200.pointnet2 import pytorch_utils as pt_utils
+    with torch.no_grad(), pt_utils.torch_layers():                                       # torch (cuDNN fp32) forward
         xyz_in = rows[..., 128:133].transpose(1, 2).unsqueeze(3)                         # (G, 5, 512, 1)
         up = rcnn.xyz_up_layer(xyz_in)
         want = rcnn.merge_down_layer(torch.cat((up, rows[..., :128].transpose(1, 2).unsqueeze(3)), dim=1))
