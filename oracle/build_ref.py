@@ -55,7 +55,14 @@ def available() -> bool:
 
 
 def build(force: bool = False, jobs: int = 8) -> bool:
-    """Returns True if oracle/_ref holds all three extensions after the call."""
+    """Returns True if oracle/_ref holds all three extensions after the call.  Also refreshes the mirror of the
+    reference's python files under oracle/_ref/py (oracle/refpy.py) that the GPU-box golden generator and the drop-in
+    tests import."""
+    try:
+        from oracle import refpy
+    except ImportError:
+        import refpy
+    refpy.stage(force=force)
     if available() and not force:
         return True
     if not os.path.isdir(REF):
