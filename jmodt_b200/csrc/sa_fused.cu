@@ -30,30 +30,31 @@
 
 namespace jmb {
 
-// warp roles: 0-15 epilogue (half h = (w>>2)&1, TMEM lane quadrant w&3, 32-column sub-block w>>3),
-//             16-19 gather (64 threads per half: one neighbour each), 20-21 MMA issuers (one per half)
+// warp roles: 0-15 epilogue (TMEM lane quadrant w&3, 16-column block w>>2 of the part being drained),
+//             16-23 gather (two threads per column: alternate groups of four 8-channel k-groups),
+//             24 MMA issuer (one thread), 25 tile scheduler (one thread)
 constexpr int SF_EPI_WARPS = 16;
-constexpr int SF_GATHER_WARP0 = 16;
-constexpr int SF_ISSUER_WARP = 20;
-// A tile of 128 columns is processed as NP independent PARTS (NP = 2 halves of 64 columns, or 4 quarters of 32): each
-// part has its own accumulator columns, operand-image slice, barriers, gather threads and MMA-issuer warp, so the
-// dependent chain  gather -> L1 -> epilogue -> L2 -> epilogue -> L3 -> epilogue  of one part overlaps the chains of the
-// others.  The chain is latency-bound (three TMEM->register->shared hand-offs per tile); more, narrower parts keep the
-// tensor pipe busier at the price of more MMA instructions.
-template <int NP> struct SfCfg {
-    static constexpr int PART = TC_BN / NP;                          // columns per part
-    static constexpr int THREADS = (SF_ISSUER_WARP + NP) * 32;      // warps 20 .. 20+NP-1: one MMA issuer per part
-    static constexpr int EPI_PER_PART = SF_EPI_WARPS * 32 / NP;
-    static constexpr uint32_t PART_OFF = (PART / 8) * TC_SBO;        // byte offset of the next part inside an image
-    // kind::f16, BF16 x BF16 -> F32, M=128, N=PART, A K-major, B MN-major / B K-major (layer 1)
-    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                                      ((uint32_t)(PART >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    static constexpr uint32_t IDESC_L1 = IDESC & ~(1u << 16);
-};
+constexpr int SF_GATHER_WARP0 = 16, SF_GATHER_WARPS = 8;
+constexpr int SF_ISSUER_WARP = 24, SF_SCHED_WARP = 25;
+constexpr int SF_THREADS = (SF_SCHED_WARP + 1) * 32;      // 832
+// A tile of 128 columns is processed as two PARTS of 64 columns with their own accumulator columns, operand-image
+// slices and barriers.  The dependent chain of a part is  gather -> L1 -> epilogue -> L2 -> epilogue -> L3 -> epilogue;
+// ONE issuer thread walks the two chains interleaved (A.L1 B.L1 A.L2 B.L2 A.L3 B.L3 ...), so while the tensor pipe
+// runs one part's MMAs ALL sixteen epilogue warps drain the other part's accumulator.  (The first versions gave every
+// part its own issuer thread and its own eight epilogue warps: the two issuers shared the pipe, fell into lock-step —
+// both parts issuing, then both draining — and the pipe sat idle during every epilogue: in-kernel timeline
+// profiles/r01/sa_fused_parts.txt, 48 % of a tile period.)
+constexpr int SF_NP = 2;
+constexpr int SF_PART = TC_BN / SF_NP;                              // 64 columns per part
+constexpr uint32_t SF_PART_OFF = (SF_PART / 8) * TC_SBO;            // byte offset of part 1 inside an operand image
+// kind::f16, BF16 x BF16 -> F32, M=128, N=SF_PART, A K-major, B MN-major / B K-major (layer 1)
+constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                              ((uint32_t)(SF_PART >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+constexpr uint32_t SF_IDESC_L1 = SF_IDESC & ~(1u << 16);
 constexpr int SF_MAXKC1 = 5;
 constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chunk: 16 KB
 constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
-constexpr int SF_MAXPARTS = 4;
+constexpr int SF_TSLOTS = 4;                  // tile ring (dynamic scheduler)
 constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bases (hi at +0, lo at +64 of each block)
 
 struct SaFusedParams {
@@ -72,6 +73,8 @@ struct SaFusedParams {
     int w3_blocks;         // 128 x 128 blocks of W3 resident in tensor memory (SA: Mt3 row blocks; ROWS: 2 K blocks)
     long long rows;        // ROWS mode: number of input rows (points), a multiple of 128
     int row_pitch;         // ROWS mode: floats per input row (multiple of 4; 128 channels, then <= 8 extra inputs)
+    int *counter, *done;   // dynamic tile scheduler (tc_sched_slot): tiles are claimed with atomicAdd, so a CTA that shares
+                           // its SM with another stream's kernel simply takes fewer tiles; re-armed by the last CTA
     long long *dbg;        // optional timeline buffer (profiling aid): CTA 0 writes clock64() stamps
 };
 
@@ -132,28 +135,43 @@ __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_b
 //   W3[:, 0:128] . act2 + W3[:, 128:256] . channels (both A blocks in tensor memory, the second with the K-major row
 //   image as B), and every column is written point-major (rows, 128) — no pooling.  The (G, 256, 512) concat, both
 //   transposes of the pooled tensor and two activation round trips of the unfused path disappear.
-template <bool ROWS, int NP>
-__global__ void __launch_bounds__(SfCfg<NP>::THREADS, 1)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool ROWS>
+__global__ void __launch_bounds__(SF_THREADS, 1)
 sa_fused_kernel(const SaFusedParams p) {
-    using Cfg = SfCfg<NP>;
-    constexpr int PART = Cfg::PART;
-    constexpr int SF_THREADS = Cfg::THREADS;
+    constexpr int PART = SF_PART;
     extern __shared__ __align__(1024) uint8_t sf_smem[];
     uint8_t *s_w1 = sf_smem;
     uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[SF_MAXPARTS], s_x1_free[SF_MAXPARTS], s_acc_full[SF_MAXPARTS],
-        s_epi_done[SF_MAXPARTS], s_w1_full;
+    __shared__ __align__(8) uint64_t s_x1_full[SF_NP], s_x1_free[SF_NP], s_acc_full[SF_NP], s_epi_done[SF_NP], s_w1_full,
+        s_tfull[SF_TSLOTS], s_tempty[SF_TSLOTS];
+    __shared__ int s_tile[SF_TSLOTS];
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int h = 0; h < NP; ++h) {
-            mbar_init(&s_x1_full[h], PART / 32);              // one arrival per warp (elected lane after __syncwarp)
+        for (int h = 0; h < SF_NP; ++h) {
+            mbar_init(&s_x1_full[h], SF_GATHER_WARPS / SF_NP);   // one arrival per gather warp of the part
             mbar_init(&s_x1_free[h], 1);
             mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], Cfg::EPI_PER_PART / 32);
+            mbar_init(&s_epi_done[h], SF_EPI_WARPS);
+        }
+        for (int s = 0; s < SF_TSLOTS; ++s) {
+            mbar_init(&s_tfull[s], 1);
+            mbar_init(&s_tempty[s], SF_EPI_WARPS + SF_GATHER_WARPS + 1);
         }
         mbar_init(&s_w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,7 +212,7 @@ sa_fused_kernel(const SaFusedParams p) {
         if (!ROWS && p.w3_blocks == 1) {
             // one W3 block leaves 128 tensor-memory columns free: the first 128 input columns of W1 go there too, so
             // layer 1 runs in TS mode like layers 2 and 3 (an SS MMA re-reads its 4 KB A operand from shared memory for
-            // every 64 columns, which made layer 1 — a third of the MMAs — half of the MMA issue time)
+            // every 64 columns)
             const int n1 = p.Kc1 < 4 ? p.Kc1 : 4;
             weight_rows_to_tmem(p.w1, 0, m, lane_base + SF_TMEM_W3 + 128, n1);
             weight_rows_to_tmem(p.w1, 1, m, lane_base + SF_TMEM_W3 + 128 + 64, n1);
@@ -207,46 +225,53 @@ sa_fused_kernel(const SaFusedParams p) {
 
     const int N = ROWS ? TC_BN : p.npoint * p.nsample;
     const int Nt = N / TC_BN;
-    const long long total_tiles = ROWS ? p.rows / TC_BN : (long long)p.G * Nt;
+    const int total_tiles = ROWS ? (int)(p.rows / TC_BN) : p.G * Nt;     // < 2^31 (checked by the launcher)
     const int kmax16 = ((p.K1 + 15) / 16) * 16;  // rows the layer-1 MMAs actually read
+    const int nsteps = 2 + p.Mt3;                // layer 1, layer 2, Mt3 row blocks of layer 3
+
+    // tile ring, consumer side: slot i is read by every consumer warp and released with one arrival per warp
+    auto ring_read = [&](uint32_t i) -> int {
+        const int slot = i % SF_TSLOTS;
+        mbar_wait(&s_tfull[slot], (i / SF_TSLOTS) & 1);
+        return *reinterpret_cast<volatile int *>(&s_tile[slot]);
+    };
 
     if (warp < SF_EPI_WARPS) {
         // ====================================== epilogue warps ======================================
-        // warp w: columns [PART*h + 32*sblk, +32) of accumulator rows [32*quad, +32)
-        const int quad = warp & 3, h = (warp >> 2) % NP, sblk = (warp >> 2) / NP;
+        // every warp works on the part whose accumulator completed: rows [32*quad, +32) x columns [16*cb, +16) of the part
+        const int quad = warp & 3, cb = warp >> 2;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * PART;
-        uint32_t acc_phase = 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t acc_phase[SF_NP] = {0, 0};
 
-        // accumulator half -> next layer's operand image (row m of the accumulator is row k = m of the operand)
-        auto epilogue_act = [&](const float *bias_ptr) {
+        // accumulator part -> next layer's operand image (row m of the accumulator is row k = m of the operand)
+        auto epilogue_act = [&](int h, const float *bias_ptr) {
             const float bias = __ldg(bias_ptr + m);
             uint8_t *ahi = s_act + (size_t)quad * SF_CHUNK, *alo = ahi + TC_IMG;
             const uint32_t rowoff = (uint32_t)(lane >> 3) * TC_LBO + (uint32_t)(lane & 7) * 16;
-            {
-                const int c0 = sblk * 32;
-                float v[32];
-                tmem_ld32(taddr + c0, v);
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(h * PART + cb * 16), v);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 hh, ll;
-                    float *w = v + q * 8;
+            for (int q = 0; q < 2; ++q) {
+                uint4 hh, ll;
+                float *w = v + q * 8;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = fmaxf(w[j] + bias, 0.f);
-                    split2(w[0], w[1], hh.x, ll.x);
-                    split2(w[2], w[3], hh.y, ll.y);
-                    split2(w[4], w[5], hh.z, ll.z);
-                    split2(w[6], w[7], hh.w, ll.w);
-                    const uint32_t off = (uint32_t)(h * (PART / 8) + (c0 >> 3) + q) * TC_SBO + rowoff;
-                    *reinterpret_cast<uint4 *>(ahi + off) = hh;
-                    *reinterpret_cast<uint4 *>(alo + off) = ll;
-                }
+                for (int j = 0; j < 8; ++j) w[j] = fmaxf(w[j] + bias, 0.f);
+                split2(w[0], w[1], hh.x, ll.x);
+                split2(w[2], w[3], hh.y, ll.y);
+                split2(w[4], w[5], hh.z, ll.z);
+                split2(w[6], w[7], hh.w, ll.w);
+                const uint32_t off = (uint32_t)(h * (PART / 8) + cb * 2 + q) * TC_SBO + rowoff;
+                *reinterpret_cast<uint4 *>(ahi + off) = hh;
+                *reinterpret_cast<uint4 *>(alo + off) = ll;
             }
         };
 
-        auto epilogue_pool = [&](long long tile, int mt) {
-            const int g = (int)tile / Nt;              // total_tiles < 2^31 (checked by the launcher): 32-bit division
-            const int nt = (int)tile - g * Nt;
+        // max over the nsample columns of each centre (nsample divides 64: a window never leaves the part);
+        // the cb == 0 warp of each quadrant pools the whole part
+        auto epilogue_pool = [&](int tile, int mt, int h) {
+            const int g = tile / Nt;
+            const int nt = tile - g * Nt;
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
             const int c3 = p.C3, ch = mt * TC_BM + m, ctr0 = (nt * TC_BN + h * PART) / p.nsample;
             const bool live = ch < c3;     // zero-padded rows of a layer narrower than the 128-row MMA tile are not stored
@@ -260,7 +285,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll 1
             for (int c0 = 0; c0 < PART; c0 += 32) {
                 float v[32];
-                tmem_ld32(taddr + c0, v);
+                tmem_ld32(taddr + (uint32_t)(h * PART + c0), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias, 0.f);
                 if (sub == 32) {
@@ -271,11 +296,6 @@ sa_fused_kernel(const SaFusedParams p) {
                     if ((c0 + 32) % p.nsample == 0) {
                         if (live) orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = run;
                         run = -INFINITY;
-                    } else if (c0 + 32 == PART && live) {
-                        // the pooling window (nsample columns) is wider than this part: the parts that share it combine
-                        // through an integer max on the zero-initialised output (post-ReLU values are >= 0, and
-                        // non-negative floats order like their bit patterns)
-                        atomicMax(reinterpret_cast<int *>(orow), __float_as_int(run));
                     }
                 } else {
                     for (int w0 = 0; w0 < 32; w0 += sub) {
@@ -290,59 +310,63 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         // ROWS: every column is an output row; a warp's 32 channels of one column are one 128-byte store
-        auto epilogue_rows = [&](long long tile) {
+        auto epilogue_rows = [&](int tile, int h) {
             const float bias = __ldg(p.b3 + m);
-            const int c0 = sblk * 32;
-            float v[32];
-            tmem_ld32(taddr + c0, v);
-            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + c0) * TC_BM + m;
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(h * PART + cb * 16), v);
+            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + cb * 16) * TC_BM + m;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+            for (int j = 0; j < 16; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
         };
 
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
         int di = 0;
 #define SF_ESTAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int layer = 0; layer < 2; ++layer) {
-                SF_ESTAMP(20 + layer);
-                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                SF_ESTAMP(30 + layer);
-                epilogue_act(layer == 0 ? p.b1 : p.b2);
-                SF_ESTAMP(40 + layer);
-                tc_fence_before();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_epi_done[h]);
-                SF_ESTAMP(50 + layer);
+        uint32_t ti = 0;
+        int tile;
+        while ((tile = ring_read(ti)) >= 0) {
+            for (int step = 0; step < nsteps; ++step) {
+#pragma unroll
+                for (int h = 0; h < SF_NP; ++h) {
+                    SF_ESTAMP(20 + step * 2 + h);
+                    mbar_wait(&s_acc_full[h], acc_phase[h]); acc_phase[h] ^= 1;
+                    tc_fence_after();
+                    SF_ESTAMP(30 + step * 2 + h);
+                    if (step < 2) {
+                        epilogue_act(h, step == 0 ? p.b1 : p.b2);
+                        fence_proxy_async();
+                    } else if (ROWS) {
+                        epilogue_rows(tile, h);
+                    } else if (cb == 0) {
+                        epilogue_pool(tile, step - 2, h);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_epi_done[h]);
+                    SF_ESTAMP(40 + step * 2 + h);
+                }
             }
-            for (int mt = 0; mt < p.Mt3; ++mt) {
-                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                if (ROWS) epilogue_rows(tile);
-                else if (sblk == 0) epilogue_pool(tile, mt);   // one warp per quadrant pools all columns of the part
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_epi_done[h]);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+            ++ti;
         }
     } else if (warp < SF_ISSUER_WARP) {
         // ====================================== gather warps ======================================
         const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
-        const int h = tg / PART, nl = tg % PART;
+        const int sub = tg >> 7;                 // which alternate block of four k-groups this thread fetches
+        const int col = tg & 127, h = col / PART;
         const int n_groups = ROWS ? p.row_pitch / 8 : p.C / 8;   // feature k-groups; SA: group n_groups holds (dx, dy, dz, 0...)
-        // One thread = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
-        // channels in flight), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
+        // Two threads = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
+        // channels in flight per thread), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
         // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots: conflict-free).
-        auto produce_x1 = [&](long long tile) {
-            const int g = (int)tile / Nt;              // total_tiles < 2^31 (checked by the launcher): 32-bit division
-            const int nt = (int)tile - g * Nt;
-            const int n = nt * TC_BN + h * PART + nl;
+        auto produce_x1 = [&](int tile) {
+            const int g = tile / Nt;
+            const int nt = tile - g * Nt;
+            const int n = nt * TC_BN + col;
             const int pi = ROWS ? 0 : __ldg(p.idx + (size_t)g * N + n);
-            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + h * PART + nl) * p.row_pitch
+            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + col) * p.row_pitch
                                      : p.feats + ((size_t)g * p.n_pts + pi) * p.C;
-            const uint32_t noff = (uint32_t)(h * (PART / 8) + (nl >> 3)) * TC_SBO + (uint32_t)(nl & 7) * 16;
+            const uint32_t noff = (uint32_t)(col >> 3) * TC_SBO + (uint32_t)(col & 7) * 16;
             auto put = [&](int kg, const float (&v)[8]) {
                 uint4 hh, ll;
                 split2(v[0], v[1], hh.x, ll.x);
@@ -353,14 +377,14 @@ sa_fused_kernel(const SaFusedParams p) {
                 *reinterpret_cast<uint4 *>(img) = hh;
                 *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
             };
-            if (!ROWS) {   // relative coordinates: k-group n_groups
+            if (!ROWS && sub == ((n_groups >> 2) & 1)) {   // relative coordinates: k-group n_groups (the thread whose turn it would be)
                 const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
                 const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
                 float v[8] = {__fsub_rn(__ldg(pt), __ldg(cen)), __fsub_rn(__ldg(pt + 1), __ldg(cen + 1)),
                               __fsub_rn(__ldg(pt + 2), __ldg(cen + 2)), 0.f, 0.f, 0.f, 0.f, 0.f};
                 put(n_groups, v);
             }
-            for (int kg0 = 0; kg0 < n_groups; kg0 += 4) {
+            for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
                 float4 a4[4], b4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -380,109 +404,130 @@ sa_fused_kernel(const SaFusedParams p) {
             if (lane == 0) mbar_arrive(&s_x1_full[h]);
         };
 
-        uint32_t tile_ctr = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-            if (ROWS && nl == 0) {
-                // the rows of this CTA's next two tiles are contiguous: pull this half's share into L2 ahead of the
-                // gather, whose 64 threads alone cannot keep enough HBM requests in flight
-                const uint32_t bytes = (uint32_t)(PART * p.row_pitch * 4);
-                for (int a = (tile_ctr == 0 ? 1 : 2); a <= 2; ++a) {
-                    const long long t2 = tile + (long long)a * gridDim.x;
-                    if (t2 < total_tiles)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                                         p.feats + ((size_t)t2 * TC_BN + h * PART) * p.row_pitch), "r"(bytes) : "memory");
-                }
-            }
-            if (tile_ctr > 0) mbar_wait(&s_x1_free[h], (tile_ctr - 1) & 1);   // the MMAs that read this half of the previous tile are done
+        uint32_t ti = 0;
+        int tile;
+        while ((tile = ring_read(ti)) >= 0) {
+            if (ti > 0) mbar_wait(&s_x1_free[h], (ti - 1) & 1);   // the MMAs that read this part of the previous tile are done
             produce_x1(tile);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+            ++ti;
         }
-    } else {
+    } else if (warp == SF_ISSUER_WARP) {
         if (lane == 0) {
-            // ====================================== MMA issuers: one thread per part ======================================
-            // A single thread's instruction stream (descriptor arithmetic + 3 MMAs per K step) was the bottleneck of the
-            // tensor pipe, so each half has its own issuer, and descriptors are formed by adding constants to a base
-            // descriptor (the start-address field is the low 14 bits; images never cross it).
-            const int h = warp - SF_ISSUER_WARP;
+            // ====================================== MMA issuer: one thread ======================================
+            // Descriptors are formed by adding constants to a base descriptor (the start-address field is the low 14
+            // bits; images never cross it).
             mbar_wait(&s_w1_full, 0);
-            uint32_t epi_phase = 0;
-            bool first_use = true;
-            uint32_t tile_ctr = 0;
-            auto wait_epilogue = [&]() {     // accumulator half h is free / its activation image is ready
-                if (first_use) { first_use = false; return; }
-                mbar_wait(&s_epi_done[h], epi_phase); epi_phase ^= 1;
-                tc_fence_after();
-            };
-            const uint32_t acc = tmem_base + (uint32_t)h * PART;
+            uint32_t epi_phase[SF_NP] = {0, 0};
+            bool first_use[SF_NP] = {true, true};
             const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
-            const uint64_t x1_desc = make_smem_desc(smem_u32(s_x1) + h * Cfg::PART_OFF);
-            const uint64_t act_desc = make_smem_desc(smem_u32(s_act) + h * Cfg::PART_OFF);
-            constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4;
-            long long *dbg = (p.dbg && blockIdx.x == 0 && h == 0) ? p.dbg : nullptr;
+            const uint64_t x1_desc0 = make_smem_desc(smem_u32(s_x1));
+            const uint64_t act_desc0 = make_smem_desc(smem_u32(s_act));
+            constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4, D_PART = SF_PART_OFF >> 4;
+            const int steps_total = kmax16 / 16;
+            const int ts_steps = (!ROWS && p.w3_blocks == 1) ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
+            long long *dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
             int di = 0;
 #define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
-                // layer 1 (SS): A = W1 chunk images in shared memory, B = gathered X1 half (K-major)
-                SF_STAMP(1);
-                wait_epilogue();
-                SF_STAMP(2);
-                mbar_wait(&s_x1_full[h], tile_ctr & 1);
-                tc_fence_after();
-                SF_STAMP(3);
-                if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
-                    const uint64_t xd = x1_desc + 4 * D_CHUNK;
-                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc, xd, 0);
-                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc + D_IMG, xd, 1);
-                    umma_ss_part<Cfg::IDESC_L1>(acc, w1_desc, xd + D_IMG, 1);
-                }
-                if (!ROWS) {
-                    const int steps_total = kmax16 / 16;
-                    const int ts_steps = p.w3_blocks == 1 ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
-                    for (int st = 0; st < steps_total; ++st) {
-                        const uint64_t off = (uint64_t)(st >> 1) * D_CHUNK + (uint64_t)(st & 1) * D_K16;
-                        const uint64_t xd = x1_desc + off;
-                        if (st < ts_steps) {
-                            const uint32_t ahi = tmem_base + SF_TMEM_W3 + 128 + (uint32_t)st * 8;
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd, st != 0);
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi + 64, xd, 1);
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+            uint32_t ti = 0;
+            int tile;
+            while ((tile = ring_read(ti)) >= 0) {
+                for (int step = 0; step < nsteps; ++step) {
+#pragma unroll
+                    for (int h = 0; h < SF_NP; ++h) {
+                        const uint32_t acc = tmem_base + (uint32_t)h * PART;
+                        const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
+                        const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
+                        SF_STAMP(step * 2 + h);
+                        if (first_use[h]) {
+                            first_use[h] = false;
+                        } else {     // accumulator part h is free / its activation image is ready
+                            mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
+                            tc_fence_after();
+                        }
+                        if (step == 0) {
+                            // layer 1: A = W1 (tensor memory for its first 128 input columns when they fit, else chunk
+                            // images in shared memory), B = gathered X1 part (K-major)
+                            mbar_wait(&s_x1_full[h], ti & 1);
+                            tc_fence_after();
+                            SF_STAMP(10 + h);
+                            if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
+                                const uint64_t xd = x1_desc + 4 * D_CHUNK;
+                                umma_ss_part<SF_IDESC_L1>(acc, w1_desc, xd, 0);
+                                umma_ss_part<SF_IDESC_L1>(acc, w1_desc + D_IMG, xd, 1);
+                                umma_ss_part<SF_IDESC_L1>(acc, w1_desc, xd + D_IMG, 1);
+                            } else {
+                                for (int st = 0; st < steps_total; ++st) {
+                                    const uint64_t off = (uint64_t)(st >> 1) * D_CHUNK + (uint64_t)(st & 1) * D_K16;
+                                    const uint64_t xd = x1_desc + off;
+                                    if (st < ts_steps) {
+                                        const uint32_t ahi = tmem_base + SF_TMEM_W3 + 128 + (uint32_t)st * 8;
+                                        umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, st != 0);
+                                        umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
+                                        umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+                                    } else {
+                                        const uint64_t wd = w1_desc + off;
+                                        umma_ss_part<SF_IDESC_L1>(acc, wd, xd, st != 0);
+                                        umma_ss_part<SF_IDESC_L1>(acc, wd + D_IMG, xd, 1);
+                                        umma_ss_part<SF_IDESC_L1>(acc, wd, xd + D_IMG, 1);
+                                    }
+                                }
+                                umma_commit(&s_x1_free[h]);      // the gather warps may refill this part for the next tile
+                            }
                         } else {
-                            const uint64_t wd = w1_desc + off;
-                            umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd, st != 0);
-                            umma_ss_part<Cfg::IDESC_L1>(acc, wd + D_IMG, xd, 1);
-                            umma_ss_part<Cfg::IDESC_L1>(acc, wd, xd + D_IMG, 1);
+                            // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
+                            const int l = step - 1;
+                            const uint32_t wcol = tmem_base + (l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128);
+#pragma unroll
+                            for (int k16 = 0; k16 < 8; ++k16) {
+                                const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                                const uint32_t ahi = wcol + (uint32_t)k16 * 8;
+                                umma_ts_part<SF_IDESC>(acc, ahi, xd, k16 != 0);
+                                umma_ts_part<SF_IDESC>(acc, ahi + 64, xd, 1);
+                                umma_ts_part<SF_IDESC>(acc, ahi, xd + D_IMG, 1);
+                            }
+                            if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
+#pragma unroll
+                                for (int k16 = 0; k16 < 8; ++k16) {
+                                    const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                                    const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
+                                    umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, 1);
+                                    umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
+                                    umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+                                }
+                                umma_commit(&s_x1_free[h]);
+                            }
                         }
+                        umma_commit(&s_acc_full[h]);
                     }
                 }
-                if (!ROWS) umma_commit(&s_x1_free[h]);      // the gather warps may refill this half for the next tile
-                umma_commit(&s_acc_full[h]);
-                SF_STAMP(4);
-                // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
-                for (int l = 0; l < 1 + p.Mt3; ++l) {
-                    const uint32_t wcol = tmem_base + (l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128);
-                    wait_epilogue();
-                    SF_STAMP(5 + l);
-#pragma unroll
-                    for (int k16 = 0; k16 < 8; ++k16) {
-                        const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
-                        const uint32_t ahi = wcol + (uint32_t)k16 * 8;
-                        umma_ts_part<Cfg::IDESC>(acc, ahi, xd, k16 != 0);
-                        umma_ts_part<Cfg::IDESC>(acc, ahi + 64, xd, 1);
-                        umma_ts_part<Cfg::IDESC>(acc, ahi, xd + D_IMG, 1);
-                    }
-                    if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
-#pragma unroll
-                        for (int k16 = 0; k16 < 8; ++k16) {
-                            const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
-                            const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd, 1);
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi + 64, xd, 1);
-                            umma_ts_part<Cfg::IDESC_L1>(acc, ahi, xd + D_IMG, 1);
-                        }
-                        umma_commit(&s_x1_free[h]);
-                    }
-                    umma_commit(&s_acc_full[h]);
-                    SF_STAMP(8 + l);
+                mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+                ++ti;
+            }
+            SF_STAMP(99);
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+            // ====================================== tile scheduler ======================================
+            uint32_t ti = 0;
+            for (;;) {
+                int t = atomicAdd(p.counter, 1);
+                if (t >= total_tiles) t = -1;
+                if (ROWS && t >= 0) {
+                    // the rows of a tile are contiguous: pull them into L2 ahead of the gather (the scheduler runs up to
+                    // SF_TSLOTS tiles ahead), whose threads alone cannot keep enough HBM requests in flight
+                    const uint32_t bytes = (uint32_t)(TC_BN * p.row_pitch * 4);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                                     p.feats + (size_t)t * TC_BN * p.row_pitch), "r"(bytes) : "memory");
                 }
+                const int slot = ti % SF_TSLOTS;
+                mbar_wait(&s_tempty[slot], ((ti / SF_TSLOTS) & 1) ^ 1);
+                *reinterpret_cast<volatile int *>(&s_tile[slot]) = t;
+                mbar_arrive(&s_tfull[slot]);
+                ++ti;
+                if (t < 0) break;
             }
         }
         __syncwarp();
@@ -493,19 +538,16 @@ sa_fused_kernel(const SaFusedParams p) {
     if (warp == SF_ISSUER_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
-}
-
-// Parts per tile (see SfCfg): 2 unless JMB_SA_PARTS=4.  Measured on B200 (profiles/r01/sa_fused_parts.txt): quarters are
-// 2 % faster on the RCNN SA0 shape and 20-30 % slower on the narrow RPN levels — the in-kernel timeline shows the chain
-// is bound by MMA issue (two issuers share the pipe; the layer-1 SS MMAs re-read their A operand from shared memory for
-// every 64 columns), not by the epilogue hand-offs, so narrower parts do not pay.
-static int sf_parts() {
-    static int parts = 0;
-    if (parts == 0) {
-        const char *e = getenv("JMB_SA_PARTS");
-        parts = (e && e[0] == '4') ? 4 : 2;
+    if (threadIdx.x == 0) {
+        // the last CTA to leave re-arms the scheduler for the next launch that uses this slot
+        __threadfence();
+        const int old = atomicAdd(p.done, 1);
+        if (old == (int)gridDim.x - 1) {
+            *p.counter = 0;
+            *p.done = 0;
+            __threadfence();
+        }
     }
-    return parts;
 }
 
 }  // namespace jmb
@@ -543,18 +585,15 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         const int rc = device_info(&dev, &sms);
         if (rc != JMB_OK) return rc;
     }
-    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
-    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    {
+        const int rc = tc_sched_slot(dev, &p.counter, &p.done);
+        if (rc != JMB_OK) return rc;
+    }
     const long long tiles = (long long)G * ((long long)npoint * nsample / TC_BN);
     JMB_REQUIRE(tiles < (1LL << 31), "sa_fused: too many tiles");
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (sf_parts() == 4) {
-        if (nsample > SfCfg<4>::PART)     // pooling windows span two parts: they combine with atomicMax on a zeroed output
-            JMB_CUDA(cudaMemsetAsync(out, 0, (size_t)G * C3 * npoint * sizeof(float), (cudaStream_t)stream));
-        sa_fused_kernel<false, 4><<<grid, SfCfg<4>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
-    } else {
-        sa_fused_kernel<false, 2><<<grid, SfCfg<2>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
-    }
+    sa_fused_kernel<false><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
     if (dbg_on) {
         long long hbuf[1024];
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -595,12 +634,14 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
         const int rc = device_info(&dev, &sms);
         if (rc != JMB_OK) return rc;
     }
-    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
-    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    JMB_FUNC_ATTR_ONCE((sa_fused_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM, dev);
+    {
+        const int rc = tc_sched_slot(dev, &p.counter, &p.done);
+        if (rc != JMB_OK) return rc;
+    }
     const long long tiles = rows / TC_BN;
     JMB_REQUIRE(tiles < (1LL << 31), "rcnn_input_fused: too many rows");
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (sf_parts() == 4) sa_fused_kernel<true, 4><<<grid, SfCfg<4>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
-    else sa_fused_kernel<true, 2><<<grid, SfCfg<2>::THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
+    sa_fused_kernel<true><<<grid, SF_THREADS, SF_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("rcnn_input_fused");
 }

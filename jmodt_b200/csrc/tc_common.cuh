@@ -13,6 +13,9 @@ constexpr int TC_BK = 32;       // K per operand chunk image
 constexpr int TC_IMG = TC_BM * TC_BK * 2;          // bytes of one bf16 operand chunk image (8 KB)
 constexpr uint32_t TC_LBO = 2048, TC_SBO = 128;    // byte strides of the canonical no-swizzle layouts
 
+// (counter, done) pair of the dynamic tile scheduler for one launch on device `dev` (tc_gemm.cu)
+int tc_sched_slot(int dev, int **counter, int **done);
+
 // ---- thin PTX wrappers ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

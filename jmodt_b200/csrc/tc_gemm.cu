@@ -629,6 +629,8 @@ tc_gemm_kernel(const TcGemmParams p) {
 constexpr int TC_SCHED_SLOTS = 4096;
 __device__ int g_tc_sched[2 * TC_SCHED_SLOTS];
 
+int tc_sched_slot(int dev, int **counter, int **done);
+
 static int *tc_sched_buffer(int dev) {
     static int *bufs[JMB_MAX_DEVICES] = {nullptr};     // symbol address per device (same value written by every thread)
     int *b = __atomic_load_n(&bufs[dev], __ATOMIC_ACQUIRE);
@@ -639,6 +641,21 @@ static int *tc_sched_buffer(int dev) {
         __atomic_store_n(&bufs[dev], b, __ATOMIC_RELEASE);
     }
     return b;
+}
+
+// (counter, done) pair for one launch of a dynamically scheduled kernel on device `dev` (shared by tc_gemm_kernel and
+// sa_fused_kernel)
+int tc_sched_slot(int dev, int **counter, int **done) {
+    int *sched = tc_sched_buffer(dev);
+    if (!sched) {
+        set_error("cannot resolve the tile-scheduler counters");
+        return JMB_ERR_CUDA;
+    }
+    static unsigned launch_seq = 0;
+    const unsigned slot = __atomic_fetch_add(&launch_seq, 1u, __ATOMIC_RELAXED) % TC_SCHED_SLOTS;
+    *counter = sched + 2 * slot;
+    *done = sched + 2 * slot + 1;
+    return JMB_OK;
 }
 
 }  // namespace jmb
@@ -683,12 +700,10 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
         const int rc = device_info(&dev, &sms);
         if (rc != JMB_OK) return rc;
     }
-    int *sched = tc_sched_buffer(dev);
-    JMB_REQUIRE(sched != nullptr, "tc_mlp_layer: cannot resolve the scheduler counters");
-    static unsigned launch_seq = 0;
-    const unsigned slot = __atomic_fetch_add(&launch_seq, 1u, __ATOMIC_RELAXED) % TC_SCHED_SLOTS;
-    p.counter = sched + 2 * slot;
-    p.done = sched + 2 * slot + 1;
+    {
+        const int rc = tc_sched_slot(dev, &p.counter, &p.done);
+        if (rc != JMB_OK) return rc;
+    }
 
     static long long *dbg_buf = nullptr;          // JMB_TC_DEBUG=1: CTA 0 records a clock64() timeline (profiling aid)
     static int dbg_on = -1;

@@ -150,6 +150,26 @@ class AttentionFusion(nn.Module):
         return tc.mlp_layer(packed, torch.cat([point_features, img_features], dim=1).contiguous())
 
 
+class GeometryPlan:
+    """Output of PointNet2MSG.geometry(): one SAPlan per set-abstraction level and one (idx, weight) pair per
+    feature-propagation level.  `tensors()` lists them in a fixed order; `copy_from()` overwrites this plan's tensors
+    with another plan's (same shapes) — the hand-over between two pipelined steps."""
+
+    def __init__(self, sa, fp):
+        self.sa, self.fp = sa, fp
+
+    def tensors(self):
+        out = []
+        for pl in self.sa:
+            out.extend(pl.tensors())
+        for i in sorted(self.fp):
+            out.extend(self.fp[i])
+        return out
+
+    def copy_from(self, other: "GeometryPlan"):
+        torch._foreach_copy_(self.tensors(), other.tensors())
+
+
 class PointNet2MSG(nn.Module):
     """backbone.py:92-198"""
 
@@ -204,6 +224,21 @@ class PointNet2MSG(nn.Module):
         de = torch.cat([dc(m) for dc, m in zip(self.DeConv, maps)], dim=1)
         fused = F.relu(self.image_fusion_bn(self.image_fusion_conv(de)))
         return maps, fused
+
+    def geometry(self, xyz: torch.Tensor) -> "GeometryPlan":
+        """The coordinate-only stage of the whole backbone on the CURRENT stream: FPS + centres + both ball-query
+        neighbour lists of the four set-abstraction levels, three_nn indices + interpolation weights of the four
+        feature-propagation levels (pointnet2_modules.py:36-50,146-152).  It depends on the cloud alone, so a caller
+        that streams frames can compute it for batch k + 1 while batch k's tensor-core stages run
+        (`runtime.GeometryAhead`) and hand it to forward(..., geometry=...)."""
+        sa, fp, xs = [], {}, [xyz.contiguous()]
+        for m in self.SA_modules:
+            plan = m.plan(xs[-1])
+            sa.append(plan)
+            xs.append(plan.new_xyz)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            fp[i] = self.FP_modules[i].plan(xs[i - 1], xs[i])
+        return GeometryPlan(sa, fp)
 
     overlap_geometry = True
     # Opt-in (JMB_L0_CHUNKS=8): consume the level-0 FPS output in prefixes while the sampler is still running.  The
@@ -276,14 +311,19 @@ class PointNet2MSG(nn.Module):
         return torch.cat(outs, dim=2)
 
     @torch.no_grad()
-    def forward(self, pc, image=None, xy=None, image_maps=None):
-        """image_maps = (maps, fused) from image_features() may be passed to skip the image stack."""
+    def forward(self, pc, image=None, xy=None, image_maps=None, geometry=None):
+        """image_maps = (maps, fused) from image_features() may be passed to skip the image stack; geometry = the
+        result of geometry(xyz) computed earlier (in stream order before this call) to skip the coordinate stage."""
         xyz, features = self._break_up_pc(pc)
         l_xyz, l_features, l_xy = [xyz], [features], [xy]
         if self.cfg.li_fusion and image_maps is None:
             image_maps = self.image_features(image)
-        sa_plans, fp_plans = self._geometry(xyz)
-        main = torch.cuda.current_stream()
+        if geometry is not None:
+            sa_plans = [(pl, None) for pl in geometry.sa]
+            fp_plans = {i: (pl, None) for i, pl in geometry.fp.items()}
+        else:
+            sa_plans, fp_plans = self._geometry(xyz)
+        main = torch.cuda.current_stream() if xyz.is_cuda else None
         for i, sa in enumerate(self.SA_modules):
             if sa_plans is not None:
                 plan_i, ev = sa_plans[i]
@@ -292,7 +332,8 @@ class PointNet2MSG(nn.Module):
                     main.wait_event(ev)
                     li_xyz, li_index = plan_i.new_xyz, plan_i.idx
                 else:
-                    main.wait_event(ev)
+                    if ev is not None:
+                        main.wait_event(ev)
                     li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i], plan=plan_i)
             else:
                 li_xyz, li_features, li_index = sa(l_xyz[i], l_features[i])
@@ -307,7 +348,8 @@ class PointNet2MSG(nn.Module):
             plan_i = None
             if fp_plans is not None:
                 plan_i, ev = fp_plans[i]
-                main.wait_event(ev)
+                if ev is not None:
+                    main.wait_event(ev)
             l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i],
                                                    plan=plan_i)
         if self.cfg.li_fusion:
@@ -345,13 +387,13 @@ class RPN(nn.Module):
         return super().train(mode)
 
     @torch.no_grad()
-    def forward(self, input_data, image_maps=None):
+    def forward(self, input_data, image_maps=None, geometry=None):
         from .head import _pack_stack, run_stack
         if self.training:
             raise RuntimeError("jmodt_b200.detector.RPN is inference only: call .eval() first")
         packed = tc.packed_for(self, lambda: (_pack_stack(self.rpn_cls_layer), _pack_stack(self.rpn_reg_layer)))
         xyz, feats = self.backbone_net(input_data["pts_input"], input_data.get("img"), input_data.get("pts_xy"),
-                                       image_maps=image_maps)
+                                       image_maps=image_maps, geometry=geometry)
         rpn_cls, rpn_reg = runtime.parallel(
             lambda: run_stack(packed[0], feats, point_major_out=True),      # (B, N, 1): transposed by the epilogue
             lambda: run_stack(packed[1], feats, point_major_out=True))      # (B, N, 76)
@@ -521,11 +563,16 @@ class PointRCNN(nn.Module):
         self.rcnn_net = RCNN(num_classes=num_classes, input_channels=128, use_xyz=use_xyz, mode=mode, cfg=head_cfg)
 
     @torch.no_grad()
-    def forward(self, input_data, image_maps=None, rois=None):
+    def geometry(self, pts_input: torch.Tensor) -> GeometryPlan:
+        """Coordinate-only stage of a batch (see PointNet2MSG.geometry): pts_input (B, N, 3+)."""
+        return self.rpn.backbone_net.geometry(pts_input[..., 0:3])
+
+    @torch.no_grad()
+    def forward(self, input_data, image_maps=None, rois=None, geometry=None):
         """input_data: pts_input (B,N,3), img (B,3,384,1280), pts_xy (B,N,2).  `rois` (B,M,7) may be injected
-        to bypass the proposal layer."""
+        to bypass the proposal layer; `geometry` = self.geometry(pts_input) computed earlier."""
         output = {}
-        rpn_output = self.rpn(input_data, image_maps=image_maps)
+        rpn_output = self.rpn(input_data, image_maps=image_maps, geometry=geometry)
         output.update(rpn_output)
         backbone_xyz, backbone_features = rpn_output["backbone_xyz"], rpn_output["backbone_features"]
         rpn_scores_raw = rpn_output["rpn_cls"][:, :, 0]
