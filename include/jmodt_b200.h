@@ -203,9 +203,11 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
  * (128 or 256) x 128, w1 with its input columns reordered to [channels, xyz] (tc.PackedLayer(..., xyz_last=True)).
  * C_in % 8 == 0 (0 = coordinates only, feats may be NULL), C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample
  * a multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
- * centres (G, npoint, 3) -> out (G, C3, npoint), or point-major (G, npoint, C3) if out_point_major != 0. */
+ * centres (G, npoint, 3) -> out (G, C3, npoint), or point-major (G, npoint, C3) if out_point_major != 0.
+ * C1, C2: the real widths of the first two layers (the kernel skips the zero padding: k-steps of the next layer's
+ * MMAs and accumulator rows of the epilogues beyond them). */
 JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                         const float *b3, int C_in, int C3, int G, int npoint, int nsample, int n_pts,
+                         const float *b3, int C_in, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
                          const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                          int out_point_major, void *stream);
 

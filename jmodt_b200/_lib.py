@@ -47,7 +47,7 @@ SIGNATURES = {
     "jmb_nms_workspace_bytes": [_i],
     "jmb_nms": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
-    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

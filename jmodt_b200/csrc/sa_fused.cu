@@ -30,7 +30,7 @@
 
 namespace jmb {
 
-// warp roles: 0-15 epilogue (TMEM lane quadrant w&3, 16-column block w>>2 of the part being drained),
+// warp roles: 0-15 epilogue (TMEM lane quadrant w&3, part (w>>2)&1, 32-column block w>>3 of the part),
 //             16-23 gather (two threads per column: alternate groups of four 8-channel k-groups),
 //             24 MMA issuer (one thread), 25 tile scheduler (one thread)
 constexpr int SF_EPI_WARPS = 16;
@@ -40,10 +40,11 @@ constexpr int SF_THREADS = (SF_SCHED_WARP + 1) * 32;      // 832
 // A tile of 128 columns is processed as two PARTS of 64 columns with their own accumulator columns, operand-image
 // slices and barriers.  The dependent chain of a part is  gather -> L1 -> epilogue -> L2 -> epilogue -> L3 -> epilogue;
 // ONE issuer thread walks the two chains interleaved (A.L1 B.L1 A.L2 B.L2 A.L3 B.L3 ...), so while the tensor pipe
-// runs one part's MMAs ALL sixteen epilogue warps drain the other part's accumulator.  (The first versions gave every
-// part its own issuer thread and its own eight epilogue warps: the two issuers shared the pipe, fell into lock-step —
-// both parts issuing, then both draining — and the pipe sat idle during every epilogue: in-kernel timeline
-// profiles/r01/sa_fused_parts.txt, 48 % of a tile period.)
+// runs one part's MMAs the other part's eight epilogue warps drain its accumulator.  (The first versions gave every
+// part its own issuer thread: the two issuers shared the pipe, fell into lock-step — both parts issuing, then both
+// draining — and the pipe sat idle during every epilogue: in-kernel timeline profiles/r01/sa_fused_parts.txt, 48 % of
+// a tile period.  Putting all sixteen epilogue warps on one part at a time does not help either: an epilogue is a
+// ~1 100-cycle latency chain whatever its width, profiles/r02/sa_fused_timeline_v5a.txt.)
 constexpr int SF_NP = 2;
 constexpr int SF_PART = TC_BN / SF_NP;                              // 64 columns per part
 constexpr uint32_t SF_PART_OFF = (SF_PART / 8) * TC_SBO;            // byte offset of part 1 inside an operand image
@@ -61,6 +62,7 @@ struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
     const float *b1, *b2, *b3;
     int K1, Kc1, Mt3;      // K1 = Cp + 3 with Cp = C_in rounded up to 8 (channels first, xyz last)
+    int C1, C2;            // real widths of layers 1 and 2: rows / k-steps beyond them are zero padding and are skipped
     int C3;                // real width of the last layer (<= 128 * Mt3; rows beyond it are zero padding)
     int C;                 // feature channels
     int G, npoint, nsample, n_pts;
@@ -167,7 +169,7 @@ sa_fused_kernel(const SaFusedParams p) {
             mbar_init(&s_x1_full[h], SF_GATHER_WARPS / SF_NP);   // one arrival per gather warp of the part
             mbar_init(&s_x1_free[h], 1);
             mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], SF_EPI_WARPS);
+            mbar_init(&s_epi_done[h], SF_EPI_WARPS / SF_NP);
         }
         for (int s = 0; s < SF_TSLOTS; ++s) {
             mbar_init(&s_tfull[s], 1);
@@ -238,21 +240,24 @@ sa_fused_kernel(const SaFusedParams p) {
 
     if (warp < SF_EPI_WARPS) {
         // ====================================== epilogue warps ======================================
-        // every warp works on the part whose accumulator completed: rows [32*quad, +32) x columns [16*cb, +16) of the part
-        const int quad = warp & 3, cb = warp >> 2;
+        // warp w drains part h = (w >> 2) & 1: rows [32*quad, +32) x columns [32*sblk, +32) of the part.  The two parts
+        // have their own eight warps so that their epilogues (a ~1 100-cycle latency chain each: barrier wake-up,
+        // tcgen05.ld, bias / ReLU / bf16 split, shared-memory stores, proxy fence, arrival) overlap each other as well
+        // as the other part's MMAs.
+        const int quad = warp & 3, h = (warp >> 2) & 1, sblk = warp >> 3;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint32_t acc_phase[SF_NP] = {0, 0};
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * PART);
+        uint32_t acc_phase = 0;
 
         // accumulator part -> next layer's operand image (row m of the accumulator is row k = m of the operand)
-        auto epilogue_act = [&](int h, const float *bias_ptr) {
+        auto epilogue_act = [&](const float *bias_ptr) {
             const float bias = __ldg(bias_ptr + m);
             uint8_t *ahi = s_act + (size_t)quad * SF_CHUNK, *alo = ahi + TC_IMG;
             const uint32_t rowoff = (uint32_t)(lane >> 3) * TC_LBO + (uint32_t)(lane & 7) * 16;
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)(h * PART + cb * 16), v);
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 uint4 hh, ll;
                 float *w = v + q * 8;
 #pragma unroll
@@ -261,15 +266,15 @@ sa_fused_kernel(const SaFusedParams p) {
                 split2(w[2], w[3], hh.y, ll.y);
                 split2(w[4], w[5], hh.z, ll.z);
                 split2(w[6], w[7], hh.w, ll.w);
-                const uint32_t off = (uint32_t)(h * (PART / 8) + cb * 2 + q) * TC_SBO + rowoff;
+                const uint32_t off = (uint32_t)(h * (PART / 8) + sblk * 4 + q) * TC_SBO + rowoff;
                 *reinterpret_cast<uint4 *>(ahi + off) = hh;
                 *reinterpret_cast<uint4 *>(alo + off) = ll;
             }
         };
 
         // max over the nsample columns of each centre (nsample divides 64: a window never leaves the part);
-        // the cb == 0 warp of each quadrant pools the whole part
-        auto epilogue_pool = [&](int tile, int mt, int h) {
+        // the sblk == 0 warp of each quadrant pools the whole part
+        auto epilogue_pool = [&](int tile, int mt) {
             const int g = tile / Nt;
             const int nt = tile - g * Nt;
             const float bias = __ldg(p.b3 + mt * TC_BM + m);
@@ -285,7 +290,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll 1
             for (int c0 = 0; c0 < PART; c0 += 32) {
                 float v[32];
-                tmem_ld32(taddr + (uint32_t)(h * PART + c0), v);
+                tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias, 0.f);
                 if (sub == 32) {
@@ -310,13 +315,13 @@ sa_fused_kernel(const SaFusedParams p) {
         };
 
         // ROWS: every column is an output row; a warp's 32 channels of one column are one 128-byte store
-        auto epilogue_rows = [&](int tile, int h) {
+        auto epilogue_rows = [&](int tile) {
             const float bias = __ldg(p.b3 + m);
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)(h * PART + cb * 16), v);
-            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + cb * 16) * TC_BM + m;
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
+            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + sblk * 32) * TC_BM + m;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+            for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
         };
 
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
@@ -326,25 +331,26 @@ sa_fused_kernel(const SaFusedParams p) {
         int tile;
         while ((tile = ring_read(ti)) >= 0) {
             for (int step = 0; step < nsteps; ++step) {
-#pragma unroll
-                for (int h = 0; h < SF_NP; ++h) {
-                    SF_ESTAMP(20 + step * 2 + h);
-                    mbar_wait(&s_acc_full[h], acc_phase[h]); acc_phase[h] ^= 1;
-                    tc_fence_after();
-                    SF_ESTAMP(30 + step * 2 + h);
-                    if (step < 2) {
-                        epilogue_act(h, step == 0 ? p.b1 : p.b2);
+                SF_ESTAMP(20 + step);
+                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
+                tc_fence_after();
+                SF_ESTAMP(30 + step);
+                if (step < 2) {
+                    // accumulator rows >= the layer's real width are zero padding nobody reads (the next layer's
+                    // MMAs stop at its last real k-step): their quadrants' warps only hand the barrier on
+                    if (quad * 32 < (((step == 0 ? p.C1 : p.C2) + 15) & ~15)) {
+                        epilogue_act(step == 0 ? p.b1 : p.b2);
                         fence_proxy_async();
-                    } else if (ROWS) {
-                        epilogue_rows(tile, h);
-                    } else if (cb == 0) {
-                        epilogue_pool(tile, step - 2, h);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_epi_done[h]);
-                    SF_ESTAMP(40 + step * 2 + h);
+                } else if (ROWS) {
+                    epilogue_rows(tile);
+                } else if (sblk == 0 && (step - 2) * TC_BM + quad * 32 < p.C3) {
+                    epilogue_pool(tile, step - 2);
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_epi_done[h]);
+                SF_ESTAMP(40 + step);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
@@ -414,44 +420,45 @@ sa_fused_kernel(const SaFusedParams p) {
             ++ti;
         }
     } else if (warp == SF_ISSUER_WARP) {
-        if (lane == 0) {
-            // ====================================== MMA issuer: one thread ======================================
-            // Descriptors are formed by adding constants to a base descriptor (the start-address field is the low 14
-            // bits; images never cross it).
-            mbar_wait(&s_w1_full, 0);
-            uint32_t epi_phase[SF_NP] = {0, 0};
-            bool first_use[SF_NP] = {true, true};
-            const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
-            const uint64_t x1_desc0 = make_smem_desc(smem_u32(s_x1));
-            const uint64_t act_desc0 = make_smem_desc(smem_u32(s_act));
-            constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4, D_PART = SF_PART_OFF >> 4;
-            const int steps_total = kmax16 / 16;
-            const int ts_steps = (!ROWS && p.w3_blocks == 1) ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
-            long long *dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
-            int di = 0;
+        // ====================================== MMA issuer ======================================
+        // The whole warp walks the loops and waits on the barriers (uniform control flow); the MMAs and commits of one
+        // (layer, part) are issued by one elected lane (see elect_one()).  Descriptors are formed by adding constants
+        // to a base descriptor (the start-address field is the low 14 bits; images never cross it).
+        mbar_wait(&s_w1_full, 0);
+        uint32_t epi_phase[SF_NP] = {0, 0};
+        bool first_use[SF_NP] = {true, true};
+        const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
+        const uint64_t x1_desc0 = make_smem_desc(smem_u32(s_x1));
+        const uint64_t act_desc0 = make_smem_desc(smem_u32(s_act));
+        constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4, D_PART = SF_PART_OFF >> 4;
+        const int steps_total = kmax16 / 16;
+        const int nk2 = (p.C1 + 15) / 16, nk3 = (p.C2 + 15) / 16;
+        const int ts_steps = (!ROWS && p.w3_blocks == 1) ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
+        long long *dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
+        int di = 0;
 #define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
-            uint32_t ti = 0;
-            int tile;
-            while ((tile = ring_read(ti)) >= 0) {
-                for (int step = 0; step < nsteps; ++step) {
+        uint32_t ti = 0;
+        int tile;
+        while ((tile = ring_read(ti)) >= 0) {
+            for (int step = 0; step < nsteps; ++step) {
 #pragma unroll
-                    for (int h = 0; h < SF_NP; ++h) {
-                        const uint32_t acc = tmem_base + (uint32_t)h * PART;
-                        const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
-                        const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
-                        SF_STAMP(step * 2 + h);
-                        if (first_use[h]) {
-                            first_use[h] = false;
-                        } else {     // accumulator part h is free / its activation image is ready
-                            mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
-                            tc_fence_after();
-                        }
+                for (int h = 0; h < SF_NP; ++h) {
+                    const uint32_t acc = tmem_base + (uint32_t)h * PART;
+                    const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
+                    const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
+                    SF_STAMP(1 + step * 2 + h);
+                    if (first_use[h]) {
+                        first_use[h] = false;
+                    } else {     // accumulator part h is free / its activation image is ready
+                        mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
+                    }
+                    if (step == 0) mbar_wait(&s_x1_full[h], ti & 1);
+                    tc_fence_after();
+                    SF_STAMP(10 + step * 2 + h);
+                    if (elect_one()) {
                         if (step == 0) {
                             // layer 1: A = W1 (tensor memory for its first 128 input columns when they fit, else chunk
                             // images in shared memory), B = gathered X1 part (K-major)
-                            mbar_wait(&s_x1_full[h], ti & 1);
-                            tc_fence_after();
-                            SF_STAMP(10 + h);
                             if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
                                 const uint64_t xd = x1_desc + 4 * D_CHUNK;
                                 umma_ss_part<SF_IDESC_L1>(acc, w1_desc, xd, 0);
@@ -479,8 +486,9 @@ sa_fused_kernel(const SaFusedParams p) {
                             // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
                             const int l = step - 1;
                             const uint32_t wcol = tmem_base + (l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128);
-#pragma unroll
-                            for (int k16 = 0; k16 < 8; ++k16) {
+                            const int nk = l == 0 ? nk2 : nk3;     // k-steps that hold real input rows
+#pragma unroll 2
+                            for (int k16 = 0; k16 < nk; ++k16) {
                                 const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
                                 const uint32_t ahi = wcol + (uint32_t)k16 * 8;
                                 umma_ts_part<SF_IDESC>(acc, ahi, xd, k16 != 0);
@@ -488,7 +496,7 @@ sa_fused_kernel(const SaFusedParams p) {
                                 umma_ts_part<SF_IDESC>(acc, ahi, xd + D_IMG, 1);
                             }
                             if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
-#pragma unroll
+#pragma unroll 2
                                 for (int k16 = 0; k16 < 8; ++k16) {
                                     const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
                                     const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
@@ -501,13 +509,13 @@ sa_fused_kernel(const SaFusedParams p) {
                         }
                         umma_commit(&s_acc_full[h]);
                     }
+                    __syncwarp();
                 }
-                mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
-                ++ti;
             }
-            SF_STAMP(99);
+            if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+            ++ti;
         }
-        __syncwarp();
+        SF_STAMP(99);
     } else {
         if (lane == 0) {
             // ====================================== tile scheduler ======================================
@@ -553,7 +561,7 @@ sa_fused_kernel(const SaFusedParams p) {
 }  // namespace jmb
 
 extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                            const float *b3, int C, int C3, int G, int npoint, int nsample, int n_pts,
+                            const float *b3, int C, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
                             const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
                             int out_point_major, void *stream) {
     using namespace jmb;
@@ -571,12 +579,13 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     const int K1 = C + 3;   // C is a multiple of 8, so the xyz group starts right after the channels
     JMB_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15u) == 0, "sa_fused: feats must be 16-byte aligned");
     JMB_REQUIRE(C3 >= 1 && C3 <= 256, "sa_fused: last layer width %d must be in 1..256", C3);
+    JMB_REQUIRE(C1 >= 1 && C1 <= 128 && C2 >= 1 && C2 <= 128, "sa_fused: layer widths %d, %d must be in 1..128", C1, C2);
     JMB_REQUIRE(nsample % 8 == 0 && 64 % nsample == 0, "sa_fused: nsample must be 8, 16, 32 or 64");
     JMB_REQUIRE(((long long)npoint * nsample) % TC_BN == 0, "sa_fused: npoint*nsample must be a multiple of 128");
     SaFusedParams p;
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = div_up(C3, TC_BM); p.C3 = C3; p.C = C;
+    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = div_up(C3, TC_BM); p.C3 = C3; p.C = C; p.C1 = C1; p.C2 = C2;
     p.w3_blocks = p.Mt3; p.rows = 0; p.row_pitch = 0;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
     p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
@@ -601,7 +610,7 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
         for (int part = 0; part < 2; ++part) {
             const long long *b = hbuf + part * 512;
             fprintf(stderr, "[sa_fused timeline %s] ", part ? "epilogue warp 0" : "issuer h0");
-            for (int i = 0; i + 1 < 96 && b[i]; i += 2) fprintf(stderr, "%lld:%lld ", b[i], b[i + 1] - b[1]);
+            for (int i = 0; i + 1 < 160 && b[i]; i += 2) fprintf(stderr, "%lld:%lld ", b[i], b[i + 1] - hbuf[1]);
             fprintf(stderr, "\n");
         }
         cudaMemset(dbg_buf, 0, 1024 * sizeof(long long));
@@ -626,7 +635,7 @@ extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void 
     SaFusedParams p = {};
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C = 128; p.w3_blocks = 2;
+    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C = 128; p.C1 = 128; p.C2 = 128; p.w3_blocks = 2;
     p.G = 1; p.npoint = 1; p.nsample = TC_BN; p.n_pts = 0;
     p.feats = in; p.out = out; p.out_point_major = 1; p.rows = rows; p.row_pitch = row_pitch;
     int dev = 0, sms = 0;

@@ -71,6 +71,22 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (elect.sync).  tcgen05.mma / tcgen05.commit take uniform-register operands; issued under
+// a `lane == 0` test the compiler cannot prove the region single-threaded and wraps EVERY such instruction in an
+// ELECT / BRA.U.ANY serialisation loop (~60 issue cycles per MMA measured: profiles/r02/sa_fused_timeline_v5b.txt).
+// With the warp's control flow uniform and the issue predicated on elect.sync the instruction is emitted once.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mov.u32 %0, 1;\n\t"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");

@@ -566,22 +566,25 @@ tc_gemm_kernel(const TcGemmParams p) {
         uint32_t xctr = 0, wctr = 0, tile_ctr = 0;
         long long *mdbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
         int mdi = 0;
+        // The whole warp walks the loop and waits on the barriers (uniform control flow); the six MMAs and the commits of
+        // a K chunk are issued by one elected lane (elect_one(): under a `lane == 0` test every tcgen05 instruction is
+        // wrapped in an ELECT / BRA.U.ANY serialisation loop that costs ~60 issue cycles per MMA).
         int cur = ring_read(tctr);
         while (cur >= 0) {
-            if (lane == 0) {
-                const int buf = tile_ctr % TC_ACC_BUFS;
-                TC_STAMP(mdbg, mdi, 0);
-                mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
+            const int buf = tile_ctr % TC_ACC_BUFS;
+            TC_STAMP(mdbg, mdi, 0);
+            mbar_wait(&s_acc_empty[buf], ((tile_ctr / TC_ACC_BUFS) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
+            for (int kc = 0; kc < p.Kc; ++kc, ++xctr, ++wctr) {
+                const int sx = xctr % TC_XSTAGES, sw = wctr % TC_WSTAGES;
+                TC_STAMP(mdbg, mdi, 1);
+                mbar_wait(&s_wfull[sw], (wctr / TC_WSTAGES) & 1);
+                TC_STAMP(mdbg, mdi, 2);
+                mbar_wait(&s_xfull[sx], (xctr / TC_XSTAGES) & 1);
+                TC_STAMP(mdbg, mdi, 3);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)buf * TC_BN;
-                for (int kc = 0; kc < p.Kc; ++kc, ++xctr, ++wctr) {
-                    const int sx = xctr % TC_XSTAGES, sw = wctr % TC_WSTAGES;
-                    TC_STAMP(mdbg, mdi, 1);
-                    mbar_wait(&s_wfull[sw], (wctr / TC_WSTAGES) & 1);
-                    TC_STAMP(mdbg, mdi, 2);
-                    mbar_wait(&s_xfull[sx], (xctr / TC_XSTAGES) & 1);
-                    TC_STAMP(mdbg, mdi, 3);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t xd = make_smem_desc(smem_u32(tc_smem + TC_OFF_X + (size_t)sx * TC_CHUNK));
                     const uint64_t wd = make_smem_desc(smem_u32(tc_smem + TC_OFF_W + (size_t)sw * TC_CHUNK));
                     umma_ss(acc, wd, xd, kc != 0);
@@ -592,9 +595,10 @@ tc_gemm_kernel(const TcGemmParams p) {
                     umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
                     umma_commit(&s_xempty[sx]);
                     umma_commit(&s_wempty[sw]);
-                    TC_STAMP(mdbg, mdi, 4);
+                    if (kc == p.Kc - 1) umma_commit(&s_acc_full[buf]);
                 }
-                umma_commit(&s_acc_full[buf]);
+                __syncwarp();
+                TC_STAMP(mdbg, mdi, 4);
             }
             ++tile_ctr;
             ring_release(tctr);

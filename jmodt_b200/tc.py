@@ -195,7 +195,8 @@ def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor | None, idx: torch.T
     flops = 2.0 * G * npoint * nsample * sum(l.M * l.K for l in layers)
     profiler.launch(flops, lambda: _lib.check(
         _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
-                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, C3, G, npoint, nsample, n_pts,
+                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, layers[0].M, layers[1].M, C3, G, npoint,
+                                nsample, n_pts,
                                 _lib.ptr(feats), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
                                 out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel",
         desc=f"sa_fused C={C} widths={layers[0].M},{layers[1].M},{C3} G={G} npoint={npoint} ns={nsample}")

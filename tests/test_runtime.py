@@ -78,3 +78,60 @@ def test_captured_step_replays_bit_identically(cuda):
         torch.cuda.synchronize()
         for k in want:
             assert torch.equal(got[k], want[k]), k
+
+
+@pytest.mark.gpu
+def test_geometry_one_step_ahead_equals_the_unpipelined_forward(cuda):
+    """runtime.GeometryAhead: the coordinate stage of batch k + 1 computed on a side stream under batch k's feature
+    stages (eagerly and as a captured graph) must give, for every batch of a stream of DIFFERENT batches, exactly the
+    unpipelined forward's outputs."""
+    from jmodt_b200 import synth
+    from jmodt_b200.detector import PointRCNN, RpnConfig
+    from jmodt_b200.runtime import CapturedPath, GeometryAhead
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    model = synth.fill_deterministic(PointRCNN(rpn_cfg=RpnConfig(post_nms_top_n=64))).to(cuda).eval()
+    batches = []
+    for seed in (3, 4, 5, 6):
+        b = synth.make_batch(seed * 10, 2, with_image=(seed == 3))
+        batches.append({k: torch.from_numpy(b[k]).to(cuda) for k in ("pts", "pts_xy", "rois")})
+        if seed == 3:
+            with torch.no_grad():
+                maps, fused = model.rpn.backbone_net.image_features(torch.from_numpy(b["img"]).to(cuda))
+    image_maps = ([m.contiguous() for m in maps], fused.contiguous())
+    keys = ("rpn_cls", "rpn_reg", "rois", "rcnn_cls", "rcnn_reg", "rcnn_feat")
+
+    def forward(b, plan=None):
+        out = model({"pts_input": b["pts"], "pts_xy": b["pts_xy"]}, image_maps=image_maps, geometry=plan)
+        return {k: out[k] for k in keys}
+
+    want = [{k: v.clone() for k, v in forward(b).items()} for b in batches]
+    # eager pipeline
+    ahead = GeometryAhead(model.geometry, batches[0]["pts"])
+    for i, b in enumerate(batches):
+        nxt = batches[(i + 1) % len(batches)]["pts"]
+        got = ahead.step(lambda plan: forward(b, plan), nxt)
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(got[k], want[i][k]), (i, k)
+    # the same as one captured graph over static buffers
+    static = {"pts": batches[0]["pts"].clone(), "pts_xy": batches[0]["pts_xy"].clone(), "next_pts": batches[0]["pts"].clone()}
+    ahead2 = GeometryAhead(model.geometry, static["pts"])
+
+    def step(d):
+        out = ahead2.step(lambda plan: forward(d, plan), d["next_pts"])
+        d["pts"].copy_(d["next_pts"])
+        return out
+    cap = CapturedPath(step, static, warmup=1)
+    # after the warm-up / capture calls the static state is "current = next = batch 0"; stream batches 1, 2, 3 through it
+    cap.load({"next_pts": batches[1]["pts"], "pts_xy": batches[0]["pts_xy"]})
+    got0 = {k: v.clone() for k, v in cap.replay().items()}
+    for k in keys:
+        assert torch.equal(got0[k], want[0][k]), ("graph", 0, k)
+    for i in (1, 2):
+        cap.load({"next_pts": batches[i + 1]["pts"], "pts_xy": batches[i]["pts_xy"]})
+        got = cap.replay()
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(got[k], want[i][k]), ("graph", i, k)
