@@ -198,26 +198,31 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
                                float *out, void *stream);
 
 /* One whole single-scale set-abstraction layer (reference pointnet2_modules.py:20-63 with QueryAndGroup and a
- * 3-layer SharedMLP) in ONE kernel: grouped gather -> MLP -> max over nsample.  Layer widths C1, C2 <= 128 and
- * C3 <= 256; w1/w2/w3 are packed layers (jmodt_b200/tc.py) ZERO-PADDED to 128 x K1, 128 x 128 and
- * (128 or 256) x 128, w1 with its input columns reordered to [channels, xyz] (tc.PackedLayer(..., xyz_last=True)).
- * C_in % 8 == 0 (0 = coordinates only, feats may be NULL), C_in + 3 <= 160, nsample in {8,16,32,64}, npoint*nsample
- * a multiple of 128.  feats (G, n_pts, C_in) POINT-MAJOR, idx (G, npoint, nsample), xyz (G, n_pts, 3),
- * centres (G, npoint, 3) -> out (G, C3, npoint), or point-major (G, npoint, C3) if out_point_major != 0.
- * C1, C2: the real widths of the first two layers (the kernel skips the zero padding: k-steps of the next layer's
- * MMAs and accumulator rows of the epilogues beyond them). */
-JMB_API int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                         const float *b3, int C_in, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
-                         const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
-                         int out_point_major, void *stream);
+ * 3-layer SharedMLP) in ONE kernel: grouped gather -> MLP -> max over nsample.  The first layer is linear up to its
+ * ReLU and grouping only selects columns, so it is applied BEFORE the gather: the caller passes
+ *     z   (G, n_pts, C1) point-major = W1[:, 3:] . features of the n_pts points (one dense layer, jmb_tc_mlp_layer
+ *         with out_mode 2; NULL when the layer has no input features), and
+ *     w1x (C1, 4) fp32 rows [W1[k, 0], W1[k, 1], W1[k, 2], b1[k]] (the coordinate columns and the bias) in HOST memory:
+ *         the 2 KB table is copied into the launch parameters (constant bank), so a captured launch keeps the values
+ *         it was captured with,
+ * and the kernel's gather finishes the layer, relu(z[idx] + W1x . (xyz[idx] - centre) + b1), while it stages the operand.
+ * Layer widths C1, C2 <= 128 (C1 % 8 == 0) and C3 <= 256; w2 / w3 are packed layers (jmodt_b200/tc.py) ZERO-PADDED to
+ * 128 x 128 and (128 or 256) x 128; nsample in {8,16,32,64}, npoint*nsample a multiple of 128.
+ * idx (G, npoint, nsample), xyz (G, n_pts, 3), centres (G, npoint, 3) -> out (G, C3, npoint), or point-major
+ * (G, npoint, C3) if out_point_major != 0. */
+JMB_API int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const float *b2, const void *w3,
+                         const float *b3, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
+                         const int *idx, const float *xyz, const float *centres, float *out, int out_point_major,
+                         void *stream);
 
 /* Input stage of the per-proposal network (reference rcnn.py:172-186: xyz_up_layer 5->128->128, cat with the 128
  * RPN channels, merge_down_layer 256->128) in ONE kernel over consecutive rows of the pooled tensor in the
  * "head layout" written by jmb_roipool3d_canonical_head: in (rows, 136) = [128 channels | x,y,z,mask,depth | 0,0,0]
- * -> out (rows, 128) point-major.  w1 is the packed 128 x 8 first layer, w2 128 x 128, w3 128 x 256. */
+ * -> out (rows, 128) point-major, or — rows_per_group > 0 (a multiple of 128) — channel-first
+ * (rows / rows_per_group, 128, rows_per_group).  w1 is the packed 128 x 8 first layer, w2 128 x 128, w3 128 x 256. */
 JMB_API int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
                                  const float *b3, long long rows, int row_pitch, const float *in, float *out,
-                                 void *stream);
+                                 int rows_per_group, void *stream);
 
 /* Pair correlation features of the link / start-end heads (reference jmodt/tracking/tracker.py:81-112,
  * rcnn.py:239-258): pt (G, K, P) predecessor and dt (G, K, D) successor features, channel-first ->

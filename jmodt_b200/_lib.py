@@ -37,7 +37,7 @@ SIGNATURES = {
     "jmb_roipool3d": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_roipool3d_canonical": [_i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_roipool3d_canonical_head": [_i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "jmb_rcnn_input_fused": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, _vp, _vp, _vp],
+    "jmb_rcnn_input_fused": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, _vp, _vp, _i, _vp],
     "jmb_pair_corr": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_pack_point_features": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_boxes_dist": [_i, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp],
@@ -47,7 +47,7 @@ SIGNATURES = {
     "jmb_nms_workspace_bytes": [_i],
     "jmb_nms": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
-    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

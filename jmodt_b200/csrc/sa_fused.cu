@@ -6,24 +6,23 @@
 // round-trips a 549 MB/frame grouped tensor and two 537 MB/frame activations through HBM; here a tile of 128
 // (centre, sample) columns never leaves the SM, and NO weight is re-read after the prologue:
 //
-//   * layer-2 / layer-3 weights (bf16 hi and lo parts) stay in TENSOR MEMORY and are the A operand of TS-mode MMAs
-//     (TMEM map: 128 accumulator columns, 128 for W2, 128 per 128-row block of W3 -> at most 512);
-//   * layer-1 weights (K1 <= 160) stay in shared memory for the lifetime of the persistent CTA (SS MMA); when W3 is
-//     a single block (C3 <= 128) the 128 tensor-memory columns left over hold W1[:, :128] and layer 1 runs in TS mode
-//     as well (an SS MMA re-reads its 4 KB A operand from shared memory for every 64 columns);
-//   * a tile is processed as two 64-column halves with separate accumulators, operand images and worker groups
-//     (4 warps each), so one half's epilogue (TMEM -> bias/ReLU -> bf16 split -> next operand image, or max-pool)
-//     and its gather of the NEXT tile run while the tensor core works on the other half;
-//   * every fp32 product is three bf16 MMAs accumulated in fp32: W_hi.X_hi + W_lo.X_hi + W_hi.X_lo.
+//   * THE FIRST LAYER IS APPLIED BEFORE THE GATHER.  It is linear up to its ReLU, and grouping only selects columns:
+//         relu(W1 . [xyz_j - c ; f_j] + b1) = relu(Z_j + W1x . (xyz_j - c) + b1),     Z = W1f . F  over the n_pts points.
+//     Z is one small dense GEMM over the POINTS (tc_gemm_kernel; 8x fewer columns than the npoint x nsample grouped
+//     neighbours at the RCNN SA0 shape) and this kernel's gather threads finish the layer on the CUDA cores — three
+//     FMAs per channel — while they convert the row to the bf16 hi/lo operand image anyway.  That takes a third of
+//     the MMAs (27 of 75 per part at C_in = 128) off the tensor pipe, frees the 80 KB W1 image and its tensor-memory
+//     columns, and removes the C_in <= 152 limit of the earlier versions;
+//   * layer-2 / layer-3 weights (bf16 hi and lo parts) stay in TENSOR MEMORY and are the A operand of TS-mode MMAs;
+//   * a tile is processed as two 64-column parts with separate accumulators, operand-image slices, barriers and
+//     epilogue warps, walked interleaved by ONE elected issuer lane (see SF_NP below);
+//   * every fp32 product is three bf16 MMAs accumulated in fp32: W_hi.X_hi + W_lo.X_hi + W_hi.X_lo;
+//   * the gather reads POINT-MAJOR rows Z (G, n_pts, C1): one neighbour = one contiguous row, fetched with 16-byte
+//     loads; the layer-2 operand is therefore staged K-major (B operand, b_major = K).
 //
-//   * the gather reads POINT-MAJOR features (G, n_pts, C): one neighbour = one contiguous row, fetched with 16-byte
-//     loads (a channel-first source costs a 32-byte sector per 4-byte element: 8x the L2 traffic, which bounded the
-//     first version of this kernel).  The layer-1 operand is therefore staged K-major (B operand, b_major = K) with
-//     the channels first and the three relative coordinates last; W1's columns are permuted to match at pack time.
-//
-// Shapes: layer widths C1, C2 <= 128 and C3 <= 256 (weights zero-padded to the 128-row tile); C_in % 8 == 0 (0 = coordinates
-// only), C_in + 3 <= 160; nsample in {8, 16, 32, 64}; npoint * nsample a multiple of 128.  The ROWS instantiation of the same
-// kernel is the input stage of the per-proposal network (see the comment above sa_fused_kernel).
+// Shapes: layer widths C1, C2 <= 128 (C1 % 8 == 0) and C3 <= 256 (weights zero-padded to the 128-row tile); any C_in
+// (0 = coordinates only: Z is NULL); nsample in {8, 16, 32, 64}; npoint * nsample a multiple of 128.  The ROWS instantiation
+// of the same kernel is the input stage of the per-proposal network (see the comment above sa_fused_kernel).
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -61,16 +60,19 @@ constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bas
 struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
     const float *b1, *b2, *b3;
-    int K1, Kc1, Mt3;      // K1 = Cp + 3 with Cp = C_in rounded up to 8 (channels first, xyz last)
+    int K1, Kc1, Mt3;      // ROWS mode: layer-1 depth (8) and its chunk count; Mt3 = 128-row blocks of the last layer
     int C1, C2;            // real widths of layers 1 and 2: rows / k-steps beyond them are zero padding and are skipped
     int C3;                // real width of the last layer (<= 128 * Mt3; rows beyond it are zero padding)
-    int C;                 // feature channels
     int G, npoint, nsample, n_pts;
-    const float *feats;    // (G, n_pts, C) POINT-MAJOR
+    const float *z;        // SA mode: (G, n_pts, C1) POINT-MAJOR rows of W1f . F (no bias), or null when C_in == 0
+    float4 w1x[TC_BM];     // SA mode: rows [w_dx, w_dy, w_dz, b1] of the first layer, by value (constant bank)
+    const float *feats;    // ROWS mode: (rows, row_pitch) input rows
     const int *idx;        // (G, npoint, nsample)
     const float *xyz;      // (G, n_pts, 3)
     const float *centres;  // (G, npoint, 3)
-    float *out;            // (G, 128*Mt3, npoint), or (G, npoint, 128*Mt3) if out_point_major
+    float *out;            // (G, 128*Mt3, npoint), or (G, npoint, 128*Mt3) if out_point_major; ROWS: (rows, 128) or, with
+                           // rows_per_group > 0, channel-first (rows / rows_per_group, 128, rows_per_group)
+    int rows_per_group;
     int out_point_major;
     int w3_blocks;         // 128 x 128 blocks of W3 resident in tensor memory (SA: Mt3 row blocks; ROWS: 2 K blocks)
     long long rows;        // ROWS mode: number of input rows (points), a multiple of 128
@@ -196,10 +198,12 @@ sa_fused_kernel(const SaFusedParams p) {
     fence_proxy_async();
 
     // ---- prologue: all weights become resident (W1 in shared memory, W2 / W3 in tensor memory) ----
-    if (threadIdx.x == SF_ISSUER_WARP * 32) {
-        mbar_arrive_expect_tx(&s_w1_full, (uint32_t)p.Kc1 * SF_CHUNK);
-        for (int c = 0; c < p.Kc1; ++c)
-            bulk_g2s(s_w1 + (size_t)c * SF_CHUNK, p.w1 + (size_t)c * (SF_CHUNK / 2), SF_CHUNK, &s_w1_full);
+    if (ROWS) {
+        if (threadIdx.x == SF_ISSUER_WARP * 32) {
+            mbar_arrive_expect_tx(&s_w1_full, (uint32_t)p.Kc1 * SF_CHUNK);
+            for (int c = 0; c < p.Kc1; ++c)
+                bulk_g2s(s_w1 + (size_t)c * SF_CHUNK, p.w1 + (size_t)c * (SF_CHUNK / 2), SF_CHUNK, &s_w1_full);
+        }
     }
     if (warp < 4) {
         const int m = warp * 32 + lane;
@@ -211,14 +215,6 @@ sa_fused_kernel(const SaFusedParams p) {
             weight_rows_to_tmem(blk, 0, m, lane_base + SF_TMEM_W3 + mt * 128);
             weight_rows_to_tmem(blk, 1, m, lane_base + SF_TMEM_W3 + mt * 128 + 64);
         }
-        if (!ROWS && p.w3_blocks == 1) {
-            // one W3 block leaves 128 tensor-memory columns free: the first 128 input columns of W1 go there too, so
-            // layer 1 runs in TS mode like layers 2 and 3 (an SS MMA re-reads its 4 KB A operand from shared memory for
-            // every 64 columns)
-            const int n1 = p.Kc1 < 4 ? p.Kc1 : 4;
-            weight_rows_to_tmem(p.w1, 0, m, lane_base + SF_TMEM_W3 + 128, n1);
-            weight_rows_to_tmem(p.w1, 1, m, lane_base + SF_TMEM_W3 + 128 + 64, n1);
-        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -228,8 +224,8 @@ sa_fused_kernel(const SaFusedParams p) {
     const int N = ROWS ? TC_BN : p.npoint * p.nsample;
     const int Nt = N / TC_BN;
     const int total_tiles = ROWS ? (int)(p.rows / TC_BN) : p.G * Nt;     // < 2^31 (checked by the launcher)
-    const int kmax16 = ((p.K1 + 15) / 16) * 16;  // rows the layer-1 MMAs actually read
-    const int nsteps = 2 + p.Mt3;                // layer 1, layer 2, Mt3 row blocks of layer 3
+    // MMA phases of a part: ROWS: layer 1, layer 2, layer 3; SA: layer 2 (layer 1 came with the gather), Mt3 row blocks of layer 3
+    const int nsteps = ROWS ? 3 : 1 + p.Mt3;
 
     // tile ring, consumer side: slot i is read by every consumer warp and released with one arrival per warp
     auto ring_read = [&](uint32_t i) -> int {
@@ -319,9 +315,21 @@ sa_fused_kernel(const SaFusedParams p) {
             const float bias = __ldg(p.b3 + m);
             float v[32];
             tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
-            float *dst = p.out + ((size_t)tile * TC_BN + h * PART + sblk * 32) * TC_BM + m;
+            const size_t row0 = (size_t)tile * TC_BN + h * PART + sblk * 32;
+            if (p.rows_per_group > 0) {
+                // channel-first (group, 128, rows_per_group): this thread's 32 consecutive rows of channel m are 128
+                // contiguous bytes (a tile never straddles a group: rows_per_group is a multiple of 128)
+                const size_t grp = row0 / (size_t)p.rows_per_group, r = row0 - grp * (size_t)p.rows_per_group;
+                float4 *dst4 = reinterpret_cast<float4 *>(p.out + (grp * TC_BM + m) * (size_t)p.rows_per_group + r);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+                for (int j = 0; j < 32; j += 4)
+                    dst4[j >> 2] = make_float4(fmaxf(v[j] + bias, 0.f), fmaxf(v[j + 1] + bias, 0.f),
+                                               fmaxf(v[j + 2] + bias, 0.f), fmaxf(v[j + 3] + bias, 0.f));
+            } else {
+                float *dst = p.out + row0 * TC_BM + m;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+            }
         };
 
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
@@ -335,17 +343,22 @@ sa_fused_kernel(const SaFusedParams p) {
                 mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
                 tc_fence_after();
                 SF_ESTAMP(30 + step);
-                if (step < 2) {
-                    // accumulator rows >= the layer's real width are zero padding nobody reads (the next layer's
-                    // MMAs stop at its last real k-step): their quadrants' warps only hand the barrier on
-                    if (quad * 32 < (((step == 0 ? p.C1 : p.C2) + 15) & ~15)) {
+                if (ROWS) {
+                    if (step < 2) {
                         epilogue_act(step == 0 ? p.b1 : p.b2);
                         fence_proxy_async();
+                    } else {
+                        epilogue_rows(tile);
                     }
-                } else if (ROWS) {
-                    epilogue_rows(tile);
-                } else if (sblk == 0 && (step - 2) * TC_BM + quad * 32 < p.C3) {
-                    epilogue_pool(tile, step - 2);
+                } else if (step == 0) {
+                    // accumulator rows >= the layer's real width are zero padding nobody reads (the next layer's
+                    // MMAs stop at its last real k-step): their quadrants' warps only hand the barrier on
+                    if (quad * 32 < ((p.C2 + 15) & ~15)) {
+                        epilogue_act(p.b2);
+                        fence_proxy_async();
+                    }
+                } else if (sblk == 0 && (step - 1) * TC_BM + quad * 32 < p.C3) {
+                    epilogue_pool(tile, step - 1);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -361,79 +374,129 @@ sa_fused_kernel(const SaFusedParams p) {
         const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
         const int sub = tg >> 7;                 // which alternate block of four k-groups this thread fetches
         const int col = tg & 127, h = col / PART;
-        const int n_groups = ROWS ? p.row_pitch / 8 : p.C / 8;   // feature k-groups; SA: group n_groups holds (dx, dy, dz, 0...)
-        // Two threads = one neighbour (column): its contiguous point-major row is read with 16-byte loads (4 groups of 8
-        // channels in flight per thread), split to bf16 hi/lo, and stored as 16-byte slots of the K-major operand image
-        // (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots: conflict-free).
-        auto produce_x1 = [&](int tile) {
-            const int g = tile / Nt;
-            const int nt = tile - g * Nt;
-            const int n = nt * TC_BN + col;
-            const int pi = ROWS ? 0 : __ldg(p.idx + (size_t)g * N + n);
-            const float *frow = ROWS ? p.feats + ((size_t)tile * TC_BN + col) * p.row_pitch
-                                     : p.feats + ((size_t)g * p.n_pts + pi) * p.C;
-            const uint32_t noff = (uint32_t)(col >> 3) * TC_SBO + (uint32_t)(col & 7) * 16;
-            auto put = [&](int kg, const float (&v)[8]) {
-                uint4 hh, ll;
-                split2(v[0], v[1], hh.x, ll.x);
-                split2(v[2], v[3], hh.y, ll.y);
-                split2(v[4], v[5], hh.z, ll.z);
-                split2(v[6], v[7], hh.w, ll.w);
-                uint8_t *img = s_x1 + (size_t)(kg >> 2) * SF_CHUNK + (uint32_t)(kg & 3) * TC_LBO + noff;
-                *reinterpret_cast<uint4 *>(img) = hh;
-                *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
-            };
-            if (!ROWS && sub == ((n_groups >> 2) & 1)) {   // relative coordinates: k-group n_groups (the thread whose turn it would be)
-                const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
-                const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
-                float v[8] = {__fsub_rn(__ldg(pt), __ldg(cen)), __fsub_rn(__ldg(pt + 1), __ldg(cen + 1)),
-                              __fsub_rn(__ldg(pt + 2), __ldg(cen + 2)), 0.f, 0.f, 0.f, 0.f, 0.f};
-                put(n_groups, v);
-            }
-            for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
-                float4 a4[4], b4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (kg0 + u < n_groups) {
-                        a4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8));
-                        b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
-                    }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (kg0 + u < n_groups) {
-                        const float v[8] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w, b4[u].x, b4[u].y, b4[u].z, b4[u].w};
-                        put(kg0 + u, v);
-                    }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_x1_full[h]);
+        const int n_groups = ROWS ? p.row_pitch / 8 : p.C1 / 8;   // k-groups of 8 channels this column's image row holds
+        // Two threads = one column: its contiguous point-major row is split to bf16 hi/lo and stored as 16-byte slots of
+        // the K-major operand image (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots:
+        // conflict-free).
+        const uint32_t noff = (uint32_t)(col >> 3) * TC_SBO + (uint32_t)(col & 7) * 16;
+        auto put = [&](int kg, const float (&v)[8]) {
+            uint4 hh, ll;
+            split2(v[0], v[1], hh.x, ll.x);
+            split2(v[2], v[3], hh.y, ll.y);
+            split2(v[4], v[5], hh.z, ll.z);
+            split2(v[6], v[7], hh.w, ll.w);
+            uint8_t *img = s_x1 + (size_t)(kg >> 2) * SF_CHUNK + (uint32_t)(kg & 3) * TC_LBO + noff;
+            *reinterpret_cast<uint4 *>(img) = hh;
+            *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
         };
-
         uint32_t ti = 0;
         int tile;
-        while ((tile = ring_read(ti)) >= 0) {
-            if (ti > 0) mbar_wait(&s_x1_free[h], (ti - 1) & 1);   // the MMAs that read this part of the previous tile are done
-            produce_x1(tile);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
-            ++ti;
+        if (ROWS) {
+            // ROWS: consecutive rows of the input (pulled into L2 ahead of time by the scheduler), 16-byte loads, 4 groups
+            // of 8 channels in flight per thread
+            while ((tile = ring_read(ti)) >= 0) {
+                if (ti > 0) mbar_wait(&s_x1_free[h], (ti - 1) & 1);   // the MMAs that read this part of the previous tile are done
+                const float *frow = p.feats + ((size_t)tile * TC_BN + col) * p.row_pitch;
+                for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
+                    float4 a4[4], b4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kg0 + u < n_groups) {
+                            a4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8));
+                            b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kg0 + u < n_groups) {
+                            const float v[8] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w, b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+                            put(kg0 + u, v);
+                        }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&s_x1_full[h]);
+                    mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+                }
+                ++ti;
+            }
+        } else {
+            // SA: the row is Z = W1f . f of the neighbour idx[n]; the thread adds W1x . (xyz - centre) + b1 and applies the
+            // ReLU, i.e. it emits layer 1's OUTPUT as layer 2's operand.  W1x / b1 come from the kernel-parameter
+            // constant bank (a warp-uniform index: no shared-memory traffic — broadcast LDS.128 of a 2 KB table cost
+            // 2 000 shared-memory cycles per tile and made this stage the bottleneck, profiles/r02/sa_fused_timeline_v6a.txt).
+            // The neighbour index of the NEXT tile is fetched while this one is produced.
+            auto col_index = [&](int tl) -> int {
+                const int g = tl / Nt;
+                const int n = (tl - g * Nt) * TC_BN + col;
+                return __ldg(p.idx + (size_t)g * N + n);
+            };
+            tile = ring_read(0);
+            int pi = tile >= 0 ? col_index(tile) : 0;
+            while (tile >= 0) {
+                const int next_tile = ring_read(ti + 1);
+                const int pi_next = next_tile >= 0 ? col_index(next_tile) : 0;     // in flight while this tile is produced
+                const int g = tile / Nt;
+                const int n = (tile - g * Nt) * TC_BN + col;
+                // relative coordinates (pointnet2_utils.py:252: grouped_xyz -= new_xyz)
+                const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
+                const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
+                const float *frow = p.z ? p.z + ((size_t)g * p.n_pts + pi) * p.C1 : nullptr;
+                const float dx = __fsub_rn(__ldg(pt), __ldg(cen));
+                const float dy = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
+                const float dz = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
+                bool waited = ti == 0;
+                for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
+                    float4 a4[4], b4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (frow && kg0 + u < n_groups) {
+                            a4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8));
+                            b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
+                        }
+                    }
+                    if (!waited) {     // the MMAs that read this part of the previous tile are done (loads already in flight)
+                        mbar_wait(&s_x1_free[h], (ti - 1) & 1);
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kg0 + u < n_groups) {
+                            float v[8] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w, b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 w = p.w1x[(kg0 + u) * 8 + j];     // constant bank, warp-uniform index
+                                v[j] = fmaxf(fmaf(w.x, dx, fmaf(w.y, dy, fmaf(w.z, dz, v[j]))) + w.w, 0.f);
+                            }
+                            put(kg0 + u, v);
+                        }
+                }
+                if (!waited) mbar_wait(&s_x1_free[h], (ti - 1) & 1);     // a thread without a k-group of its own still keeps the phase order
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&s_x1_full[h]);
+                    mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+                }
+                tile = next_tile;
+                pi = pi_next;
+                ++ti;
+            }
         }
     } else if (warp == SF_ISSUER_WARP) {
         // ====================================== MMA issuer ======================================
         // The whole warp walks the loops and waits on the barriers (uniform control flow); the MMAs and commits of one
         // (layer, part) are issued by one elected lane (see elect_one()).  Descriptors are formed by adding constants
         // to a base descriptor (the start-address field is the low 14 bits; images never cross it).
-        mbar_wait(&s_w1_full, 0);
+        if (ROWS) mbar_wait(&s_w1_full, 0);
         uint32_t epi_phase[SF_NP] = {0, 0};
         bool first_use[SF_NP] = {true, true};
         const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
         const uint64_t x1_desc0 = make_smem_desc(smem_u32(s_x1));
         const uint64_t act_desc0 = make_smem_desc(smem_u32(s_act));
         constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4, D_CHUNK = SF_CHUNK >> 4, D_PART = SF_PART_OFF >> 4;
-        const int steps_total = kmax16 / 16;
-        const int nk2 = (p.C1 + 15) / 16, nk3 = (p.C2 + 15) / 16;
-        const int ts_steps = (!ROWS && p.w3_blocks == 1) ? (steps_total < 8 ? steps_total : 8) : 0;   // W1[:, :128] in tensor memory
+        const int nk2 = (p.C1 + 15) / 16, nk3 = (p.C2 + 15) / 16;     // k-steps that hold real input rows
         long long *dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
         int di = 0;
 #define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
@@ -456,55 +519,57 @@ sa_fused_kernel(const SaFusedParams p) {
                     tc_fence_after();
                     SF_STAMP(10 + step * 2 + h);
                     if (elect_one()) {
-                        if (step == 0) {
-                            // layer 1: A = W1 (tensor memory for its first 128 input columns when they fit, else chunk
-                            // images in shared memory), B = gathered X1 part (K-major)
-                            if (ROWS) {   // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
+                        if (ROWS) {
+                            if (step == 0) {
+                                // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
                                 const uint64_t xd = x1_desc + 4 * D_CHUNK;
                                 umma_ss_part<SF_IDESC_L1>(acc, w1_desc, xd, 0);
                                 umma_ss_part<SF_IDESC_L1>(acc, w1_desc + D_IMG, xd, 1);
                                 umma_ss_part<SF_IDESC_L1>(acc, w1_desc, xd + D_IMG, 1);
                             } else {
-                                for (int st = 0; st < steps_total; ++st) {
-                                    const uint64_t off = (uint64_t)(st >> 1) * D_CHUNK + (uint64_t)(st & 1) * D_K16;
-                                    const uint64_t xd = x1_desc + off;
-                                    if (st < ts_steps) {
-                                        const uint32_t ahi = tmem_base + SF_TMEM_W3 + 128 + (uint32_t)st * 8;
-                                        umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, st != 0);
+                                // layers 2 and 3 (TS): A = weights resident in tensor memory, B = the activation image
+                                const uint32_t wcol = tmem_base + (step == 1 ? SF_TMEM_W2 : SF_TMEM_W3);
+#pragma unroll 2
+                                for (int k16 = 0; k16 < 8; ++k16) {
+                                    const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                                    const uint32_t ahi = wcol + (uint32_t)k16 * 8;
+                                    umma_ts_part<SF_IDESC>(acc, ahi, xd, k16 != 0);
+                                    umma_ts_part<SF_IDESC>(acc, ahi + 64, xd, 1);
+                                    umma_ts_part<SF_IDESC>(acc, ahi, xd + D_IMG, 1);
+                                }
+                                if (step == 2) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
+#pragma unroll 2
+                                    for (int k16 = 0; k16 < 8; ++k16) {
+                                        const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                                        const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
+                                        umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, 1);
                                         umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
                                         umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
-                                    } else {
-                                        const uint64_t wd = w1_desc + off;
-                                        umma_ss_part<SF_IDESC_L1>(acc, wd, xd, st != 0);
-                                        umma_ss_part<SF_IDESC_L1>(acc, wd + D_IMG, xd, 1);
-                                        umma_ss_part<SF_IDESC_L1>(acc, wd, xd + D_IMG, 1);
                                     }
+                                    umma_commit(&s_x1_free[h]);
                                 }
-                                umma_commit(&s_x1_free[h]);      // the gather warps may refill this part for the next tile
                             }
-                        } else {
-                            // layer 2 and the Mt3 row blocks of layer 3 (TS): A = weights resident in tensor memory
-                            const int l = step - 1;
-                            const uint32_t wcol = tmem_base + (l == 0 ? SF_TMEM_W2 : SF_TMEM_W3 + (uint32_t)(l - 1) * 128);
-                            const int nk = l == 0 ? nk2 : nk3;     // k-steps that hold real input rows
+                        } else if (step == 0) {
+                            // layer 2 (TS): A = W2 in tensor memory, B = layer 1's output as the gather threads wrote it (K-major)
 #pragma unroll 2
-                            for (int k16 = 0; k16 < nk; ++k16) {
+                            for (int k16 = 0; k16 < nk2; ++k16) {
+                                const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                                const uint32_t ahi = tmem_base + SF_TMEM_W2 + (uint32_t)k16 * 8;
+                                umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, k16 != 0);
+                                umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
+                                umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+                            }
+                            umma_commit(&s_x1_free[h]);      // the gather warps may refill this part for the next tile
+                        } else {
+                            // row block step-1 of layer 3 (TS): A = W3 block in tensor memory, B = layer 2's output (MN-major)
+                            const uint32_t wcol = tmem_base + SF_TMEM_W3 + (uint32_t)(step - 1) * 128;
+#pragma unroll 2
+                            for (int k16 = 0; k16 < nk3; ++k16) {
                                 const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
                                 const uint32_t ahi = wcol + (uint32_t)k16 * 8;
                                 umma_ts_part<SF_IDESC>(acc, ahi, xd, k16 != 0);
                                 umma_ts_part<SF_IDESC>(acc, ahi + 64, xd, 1);
                                 umma_ts_part<SF_IDESC>(acc, ahi, xd + D_IMG, 1);
-                            }
-                            if (ROWS && l == 1) {   // + W3[:, 128:256] . channels: A block 1 in tensor memory, B = the K-major row image
-#pragma unroll 2
-                                for (int k16 = 0; k16 < 8; ++k16) {
-                                    const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
-                                    const uint32_t ahi = wcol + 128 + (uint32_t)k16 * 8;
-                                    umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, 1);
-                                    umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
-                                    umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
-                                }
-                                umma_commit(&s_x1_free[h]);
                             }
                         }
                         umma_commit(&s_acc_full[h]);
@@ -560,10 +625,10 @@ sa_fused_kernel(const SaFusedParams p) {
 
 }  // namespace jmb
 
-extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
-                            const float *b3, int C, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
-                            const float *feats, const int *idx, const float *xyz, const float *centres, float *out,
-                            int out_point_major, void *stream) {
+extern "C" int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const float *b2, const void *w3,
+                            const float *b3, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
+                            const int *idx, const float *xyz, const float *centres, float *out, int out_point_major,
+                            void *stream) {
     using namespace jmb;
     static long long *dbg_buf = nullptr;          // JMB_SA_DEBUG=1: CTA 0 records a clock64() timeline (profiling aid)
     static int dbg_on = -1;
@@ -574,21 +639,22 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
     }
     JMB_REQUIRE(G >= 0 && npoint > 0 && nsample > 0 && n_pts > 0, "sa_fused: bad sizes");
     if (G == 0) return JMB_OK;
-    JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && (feats || C == 0) && idx && xyz && centres && out, "sa_fused: null pointer");
-    JMB_REQUIRE(C >= 0 && C % 8 == 0 && C + 3 <= SF_MAXKC1 * TC_BK, "sa_fused: C_in = %d must be a multiple of 8 and <= 152", C);
-    const int K1 = C + 3;   // C is a multiple of 8, so the xyz group starts right after the channels
-    JMB_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15u) == 0, "sa_fused: feats must be 16-byte aligned");
+    JMB_REQUIRE(w1x && w2 && w3 && b2 && b3 && idx && xyz && centres && out, "sa_fused: null pointer");
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15u) == 0, "sa_fused: z must be 16-byte aligned");
     JMB_REQUIRE(C3 >= 1 && C3 <= 256, "sa_fused: last layer width %d must be in 1..256", C3);
-    JMB_REQUIRE(C1 >= 1 && C1 <= 128 && C2 >= 1 && C2 <= 128, "sa_fused: layer widths %d, %d must be in 1..128", C1, C2);
+    JMB_REQUIRE(C1 >= 8 && C1 <= 128 && C1 % 8 == 0, "sa_fused: first layer width %d must be a multiple of 8 in 8..128", C1);
+    JMB_REQUIRE(C2 >= 1 && C2 <= 128, "sa_fused: second layer width %d must be in 1..128", C2);
     JMB_REQUIRE(nsample % 8 == 0 && 64 % nsample == 0, "sa_fused: nsample must be 8, 16, 32 or 64");
     JMB_REQUIRE(((long long)npoint * nsample) % TC_BN == 0, "sa_fused: npoint*nsample must be a multiple of 128");
     SaFusedParams p;
-    p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
-    p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = K1; p.Kc1 = div_up(K1, TC_BK); p.Mt3 = div_up(C3, TC_BM); p.C3 = C3; p.C = C; p.C1 = C1; p.C2 = C2;
+    p = SaFusedParams{};
+    p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
+    p.b2 = b2; p.b3 = b3; p.z = z;
+    for (int k = 0; k < C1; ++k) p.w1x[k] = make_float4(w1x[4 * k], w1x[4 * k + 1], w1x[4 * k + 2], w1x[4 * k + 3]);
+    p.Mt3 = div_up(C3, TC_BM); p.C3 = C3; p.C1 = C1; p.C2 = C2;
     p.w3_blocks = p.Mt3; p.rows = 0; p.row_pitch = 0;
     p.G = G; p.npoint = npoint; p.nsample = nsample; p.n_pts = n_pts;
-    p.feats = feats; p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
+    p.idx = idx; p.xyz = xyz; p.centres = centres; p.out = out; p.out_point_major = out_point_major; p.dbg = dbg_buf;
     int dev = 0, sms = 0;
     {
         const int rc = device_info(&dev, &sms);
@@ -624,18 +690,20 @@ extern "C" int jmb_sa_fused(const void *w1, const float *b1, const void *w2, con
 // w1: 128 x 8 (extra inputs, zero padded), w2: 128 x 128, w3: 128 x 256, all packed as tc.PackedLayer images.
 extern "C" int jmb_rcnn_input_fused(const void *w1, const float *b1, const void *w2, const float *b2, const void *w3,
                                     const float *b3, long long rows, int row_pitch, const float *in, float *out,
-                                    void *stream) {
+                                    int rows_per_group, void *stream) {
     using namespace jmb;
     JMB_REQUIRE(rows >= 0, "rcnn_input_fused: negative size");
     if (rows == 0) return JMB_OK;
     JMB_REQUIRE(w1 && w2 && w3 && b1 && b2 && b3 && in && out, "rcnn_input_fused: null pointer");
     JMB_REQUIRE(rows % TC_BN == 0, "rcnn_input_fused: rows = %lld must be a multiple of 128", rows);
     JMB_REQUIRE(row_pitch == 136, "rcnn_input_fused: row pitch %d (expected 128 channels + 8 extra inputs)", row_pitch);
+    JMB_REQUIRE(rows_per_group >= 0 && rows_per_group % TC_BN == 0 && (rows_per_group == 0 || rows % rows_per_group == 0),
+                "rcnn_input_fused: rows_per_group %d must be 0 or a multiple of 128 dividing the row count", rows_per_group);
     JMB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15u) == 0, "rcnn_input_fused: input must be 16-byte aligned");
     SaFusedParams p = {};
     p.w1 = (const __nv_bfloat16 *)w1; p.w2 = (const __nv_bfloat16 *)w2; p.w3 = (const __nv_bfloat16 *)w3;
     p.b1 = b1; p.b2 = b2; p.b3 = b3;
-    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C = 128; p.C1 = 128; p.C2 = 128; p.w3_blocks = 2;
+    p.K1 = 8; p.Kc1 = 1; p.Mt3 = 1; p.C3 = 128; p.C1 = 128; p.C2 = 128; p.w3_blocks = 2; p.rows_per_group = rows_per_group;
     p.G = 1; p.npoint = 1; p.nsample = TC_BN; p.n_pts = 0;
     p.feats = in; p.out = out; p.out_point_major = 1; p.rows = rows; p.row_pitch = row_pitch;
     int dev = 0, sms = 0;

@@ -197,7 +197,8 @@ class RCNN(nn.Module):
         if pts_input.shape[-1] == head_pitch and head_pitch != cin + 128:
             # head layout from pool_rois: [128 channels | x, y, z, extras | 0...]; one kernel for the whole input stage
             xyz = pts_input[..., 128:131].contiguous()
-            h = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], pts_input.contiguous())
+            h = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], pts_input.contiguous(),
+                                    channel_first=True)                                   # (G, 128, 512)
         else:
             xyz = pts_input[..., 0:3].contiguous()
             xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()               # (G, 5, 512)
@@ -209,13 +210,11 @@ class RCNN(nn.Module):
             h = xyz_input
             for i, layer in enumerate(P["xyz_up"]):
                 h = tc.mlp_layer(layer, h, out=both[:, :c_up] if i == len(P["xyz_up"]) - 1 else None)
-            # The fused set-abstraction kernel gathers from POINT-MAJOR features, so the producers write that layout
-            # directly: merge_down -> (G, 512, 128), SA0 -> (G, 128, 128); no transposes in between.
             md = P["merge_down"]
             h = both
             for i, layer in enumerate(md):
-                h = tc.mlp_layer(layer, h, point_major_out=(chain_ok[0] and i == len(md) - 1))
-        l_xyz, l_feat, pm = xyz, h, chain_ok[0]                                           # pm: l_feat is point-major
+                h = tc.mlp_layer(layer, h)
+        l_xyz, l_feat, pm = xyz, h, False                                                 # pm: l_feat is point-major
         for k, (sa, packed) in enumerate(sa_list):
             grouper = sa.groupers[0]
             if sa.npoint is not None:
@@ -223,10 +222,10 @@ class RCNN(nn.Module):
                 new_xyz = pu.gather_operation(l_xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
                 idx = pu.ball_query(grouper.radius, grouper.nsample, l_xyz, new_xyz)
                 if chain_ok[k]:
-                    next_pm = k + 1 < len(sa_list) and chain_ok[k + 1]
-                    l_feat = tc.sa_fused(packed, l_xyz, l_feat, idx, new_xyz, feats_point_major=pm,
-                                         out_point_major=next_pm)
-                    l_xyz, pm = new_xyz, next_pm
+                    # channel-first in, channel-first out: the layer's first-layer GEMM over the points (tc.sa_fused)
+                    # reads the layout the previous stage writes, no transposes in between
+                    l_feat = tc.sa_fused(packed, l_xyz, l_feat, idx, new_xyz, feats_point_major=pm)
+                    l_xyz, pm = new_xyz, False
                     continue
                 if pm:
                     l_feat, pm = l_feat.transpose(1, 2).contiguous(), False
@@ -292,6 +291,13 @@ def pair_corr(pt: torch.Tensor, dt: torch.Tensor, want_cor: bool = True, want_me
     return cor, mean_p, mean_d
 
 
+def dual_softmax(logits: torch.Tensor) -> torch.Tensor:
+    """(softmax over successors + softmax over predecessors) / 2 of link logits (..., P, D) — tracker.py:87-89.  One
+    definition for the single-GPU and the sharded path, so that equal logits give bit-equal link scores."""
+    col = torch.softmax(logits.transpose(-1, -2).contiguous(), dim=-1).transpose(-1, -2)   # softmax over predecessors
+    return (torch.softmax(logits, dim=-1) + col) / 2
+
+
 def _stacks(link_model, se_model):
     """Packed layer stacks of the link / start-end heads (any pt_utils.Conv1d nn.Sequential, e.g. the reference's
     `rcnn_net.link_layer` / `se_layer` handed to the tracker at tools/eval.py:333-336); cached on the modules."""
@@ -314,8 +320,7 @@ def affinity_scores_batched(link_model, se_model, pred_features: torch.Tensor, d
 
     def link_branch():
         logits = run_stack(link_stack, cor).view(G, P, D)
-        col = torch.softmax(logits.transpose(1, 2).contiguous(), dim=2).transpose(1, 2)   # softmax over predecessors
-        return (torch.softmax(logits, dim=2) + col) / 2, logits
+        return dual_softmax(logits), logits
 
     (link, logits), start, end = runtime.parallel(
         link_branch,

@@ -83,7 +83,7 @@ def sharded_affinity_device(link_model, se_model, pred_features: torch.Tensor, d
     rank at 128 x 128 on 4 ranks); it is required because softmax(dim=0) (reference tracker.py:88) spans all rows.
     A column of the layer kernel's output depends on that column's inputs only, so the gathered logits are
     bit-identical to the single-GPU result.  Returns link (P, D), start (D,), end (P,), logits (P, D) on every rank."""
-    from .head import _stacks, pair_corr, run_stack
+    from .head import _stacks, dual_softmax, pair_corr, run_stack
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     P, D = pred_features.shape[0], det_features.shape[0]
     lo, hi = row_shard(P, rank, world)
@@ -113,8 +113,7 @@ def sharded_affinity_device(link_model, se_model, pred_features: torch.Tensor, d
         end, start = torch.cat(ends), torch.cat(starts)
     else:
         logits, end, start = tile, end_local, start_local
-    link = (torch.softmax(logits, dim=1) + torch.softmax(logits, dim=0)) / 2
-    return link, start, end, logits
+    return dual_softmax(logits), start, end, logits
 
 
 def exchange_boundary_features(first_frame_features: torch.Tensor, group=None, timer=None):

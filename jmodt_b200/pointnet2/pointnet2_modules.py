@@ -125,8 +125,6 @@ class _PointnetSAModuleBase(nn.Module):
         one_kernel = [isinstance(g, pointnet2_utils.QueryAndGroup) and fuse and
                       tc.sa_fused_supported(layers, c_in, new_xyz.shape[1], g.nsample)
                       for g, layers in zip(self.groupers, packed)]
-        # point-major copy of the features, shared by the scales that run as one kernel
-        feats_pm = features.transpose(1, 2).contiguous() if (features is not None and any(one_kernel)) else None
 
         def scale(gi):
             grouper, layers = self.groupers[gi], packed[gi]
@@ -135,7 +133,7 @@ class _PointnetSAModuleBase(nn.Module):
                 idx = nbr[gi]
                 pool = grouper.nsample
                 if one_kernel[gi]:
-                    return tc.sa_fused(layers, xyz, feats_pm, idx, new_xyz, feats_point_major=True)   # whole layer in one kernel
+                    return tc.sa_fused(layers, xyz, features, idx, new_xyz)   # first-layer GEMM over the points + one kernel
                 h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
                                            pool=pool if len(layers) == 1 else 0)
             else:  # GroupAll

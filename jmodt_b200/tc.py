@@ -151,17 +151,20 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
 
 def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) -> bool:
     """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu): three ReLU layers of widths
-    C1, C2 <= 128 and C3 <= 256 (narrower layers run zero-padded to the 128-row MMA tile), 0 <= C_in <= 152."""
-    return (len(layers) == 3 and layers[0].M <= 128 and layers[1].M <= 128 and layers[1].K == layers[0].M
-            and layers[2].K == layers[1].M and layers[2].M <= 256 and all(l.relu for l in layers)
-            and all(l._w32 is not None for l in layers)
-            and n_feat_channels % 8 == 0 and 0 <= n_feat_channels <= 152 and layers[0].K == n_feat_channels + 3
+    C1, C2 <= 128 (C1 a multiple of 8) and C3 <= 256 (narrower layers run zero-padded to the 128-row MMA tile); any
+    number of input feature channels (the first layer is applied to the points before the gather)."""
+    return (len(layers) == 3 and layers[0].M <= 128 and layers[0].M % 8 == 0 and layers[1].M <= 128
+            and layers[1].K == layers[0].M and layers[2].K == layers[1].M and layers[2].M <= 256
+            and all(l.relu for l in layers) and all(l._w32 is not None for l in layers)
+            and n_feat_channels >= 0 and layers[0].K == n_feat_channels + 3
             and nsample in (8, 16, 32, 64) and (npoint * nsample) % 128 == 0)
 
 
 def _sa_fused_packs(layers):
-    """The three layers as the images sa_fused_kernel keeps resident: W1 (128 x K1, columns [channels, xyz]),
-    W2 (128 x 128), W3 (128|256 x 128), zero-padded; cached on the first layer."""
+    """What sa_fused_kernel consumes of the three layers (cached on the first):
+    W1f = W1[:, 3:] as a linear PackedLayer (applied to the POINTS before the gather; None without input features),
+    w1x (C1, 4) fp32 rows [W1[k, 0:3], b1[k]] (finished by the gather threads), W2 (128 x 128) and W3 (128|256 x 128)
+    zero-padded images."""
     l1, l2, l3 = layers
     cache = getattr(l1, "_sa_packs", None)
     if cache is None:
@@ -169,54 +172,70 @@ def _sa_fused_packs(layers):
             w = torch.zeros(layer.M, K, dtype=torch.float32, device=layer.bias.device)
             w[:, : layer.K] = layer._w32
             return PackedLayer(w, layer.bias[: layer.M], layer.relu)
-        cache = l1._sa_packs = (l1.repacked_xyz_last(), l2 if l2.K == 128 else padded(l2, 128),
-                                l3 if l3.K == 128 else padded(l3, 128))
+        w1 = l1._w32
+        w1f = PackedLayer(w1[:, 3:].contiguous(), None, relu=False) if l1.K > 3 else None
+        w1x = torch.cat((w1[:, :3], l1.bias[: l1.M, None]), dim=1).contiguous().cpu()     # host table: goes into the launch parameters
+        cache = l1._sa_packs = (w1f, w1x, l2 if l2.K == 128 else padded(l2, 128), l3 if l3.K == 128 else padded(l3, 128))
     return cache
 
 
 def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor | None, idx: torch.Tensor, centres: torch.Tensor,
              feats_point_major: bool = False, out_point_major: bool = False) -> torch.Tensor:
-    """Whole set-abstraction layer in one kernel: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first (transposed
-    here to the point-major layout the gather wants), (G, n_pts, C) with feats_point_major, or None (coordinates
-    only), idx (G, npoint, nsample) int32, centres (G, npoint, 3) -> (G, C3, npoint) or point-major (G, npoint, C3)."""
+    """Whole set-abstraction layer: xyz (G, n_pts, 3), feats (G, C, n_pts) channel-first ((G, n_pts, C) with
+    feats_point_major: transposed here), or None (coordinates only), idx (G, npoint, nsample) int32, centres
+    (G, npoint, 3) -> (G, C3, npoint) or point-major (G, npoint, C3).  Two launches: Z = W1[:, 3:] . feats over the n_pts
+    points (tc_gemm_kernel, point-major rows), then sa_fused_kernel (gather + rest of layer 1 + layers 2, 3 + max-pool)."""
     G, n_pts, _ = xyz.shape
     C = 0 if feats is None else (feats.shape[2] if feats_point_major else feats.shape[1])
     npoint, nsample = idx.shape[1], idx.shape[2]
     assert layers[0].K == 3 + C and idx.is_contiguous() and xyz.is_contiguous()
-    l1, l2, l3 = _sa_fused_packs(layers)
-    C3 = layers[2].M
+    w1f, w1x, l2, l3 = _sa_fused_packs(layers)
+    C1, C2, C3 = layers[0].M, layers[1].M, layers[2].M
+    z = None
     if feats is not None:
-        if not feats_point_major:
-            feats = feats.transpose(1, 2)               # (G, n_pts, C): one neighbour = one contiguous row
-        feats = feats.contiguous()
+        if feats_point_major:
+            feats = feats.transpose(1, 2)
+        z = mlp_layer(w1f, feats.contiguous(), point_major_out=True)          # (G, n_pts, C1)
     oshape = (G, npoint, C3) if out_point_major else (G, C3, npoint)
     out = torch.empty(oshape, dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)
-    flops = 2.0 * G * npoint * nsample * sum(l.M * l.K for l in layers)
+    cols = float(G) * npoint * nsample
+    # algorithmic = the reference layer (three 1x1 convs over the grouped tensor); the kernel itself executes layers 2
+    # and 3 on the tensor cores and the coordinate part of layer 1 on the CUDA cores (its feature part is the Z launch)
+    flops = 2.0 * cols * sum(l.M * l.K for l in layers)
+    executed = 2.0 * cols * (C1 * 3 + C2 * C1 + C3 * C2)
     profiler.launch(flops, lambda: _lib.check(
-        _lib.lib().jmb_sa_fused(l1.wpack.data_ptr(), l1.bias.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
-                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C, layers[0].M, layers[1].M, C3, G, npoint,
-                                nsample, n_pts,
-                                _lib.ptr(feats), idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
+        _lib.lib().jmb_sa_fused(_lib.ptr(z), w1x.data_ptr(), l2.wpack.data_ptr(), l2.bias.data_ptr(),
+                                l3.wpack.data_ptr(), l3.bias.data_ptr(), C1, C2, C3, G, npoint, nsample, n_pts,
+                                idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
                                 out.data_ptr(), int(out_point_major), st), "sa_fused"), kind="sa_fused_kernel",
-        desc=f"sa_fused C={C} widths={layers[0].M},{layers[1].M},{C3} G={G} npoint={npoint} ns={nsample}")
+        desc=f"sa_fused C={C} widths={C1},{C2},{C3} G={G} npoint={npoint} ns={nsample} executed_flops={executed:.4g}")
     return out
 
 
-def rcnn_input_fused(w1: PackedLayer, w2: PackedLayer, w3: PackedLayer, rows_in: torch.Tensor) -> torch.Tensor:
+def rcnn_input_fused(w1: PackedLayer, w2: PackedLayer, w3: PackedLayer, rows_in: torch.Tensor,
+                     channel_first: bool = False) -> torch.Tensor:
     """xyz_up_layer (2 layers) + concat + merge_down_layer of the per-proposal network (rcnn.py:172-186) in one
     kernel: rows_in (..., 136) in the head layout [128 channels | x, y, z, mask, depth | 0, 0, 0] ->
-    (..., 128) point-major merged features.  w1 is the first xyz_up layer packed as 128 x 8."""
+    (..., 128) point-major merged features, or — channel_first, rows_in (G, S, 136) with S a multiple of 128 —
+    (G, 128, S), the layout the reference's merge_down_layer produces (rcnn.py:186).  w1 is the first xyz_up layer
+    packed as 128 x 8."""
     assert rows_in.is_contiguous() and rows_in.dtype == torch.float32 and rows_in.shape[-1] == 136
     assert (w1.M, w1.K) == (128, 8) and (w2.M, w2.K) == (128, 128) and (w3.M, w3.K) == (128, 256)
     assert w1.relu and w2.relu and w3.relu
     rows = rows_in.numel() // 136
-    out = torch.empty(rows_in.shape[:-1] + (128,), dtype=torch.float32, device=rows_in.device)
+    rpg = 0
+    if channel_first:
+        assert rows_in.dim() == 3 and rows_in.shape[1] % 128 == 0
+        rpg = rows_in.shape[1]
+        out = torch.empty((rows_in.shape[0], 128, rpg), dtype=torch.float32, device=rows_in.device)
+    else:
+        out = torch.empty(rows_in.shape[:-1] + (128,), dtype=torch.float32, device=rows_in.device)
     st = _lib.stream_and_device(rows_in)
     flops = 2.0 * rows * (128 * 5 + 128 * 128 + 128 * 256)
     profiler.launch(flops, lambda: _lib.check(
         _lib.lib().jmb_rcnn_input_fused(w1.wpack.data_ptr(), w1.bias.data_ptr(), w2.wpack.data_ptr(),
                                         w2.bias.data_ptr(), w3.wpack.data_ptr(), w3.bias.data_ptr(), rows, 136,
-                                        rows_in.data_ptr(), out.data_ptr(), st), "rcnn_input_fused"),
+                                        rows_in.data_ptr(), out.data_ptr(), rpg, st), "rcnn_input_fused"),
         kind="rcnn_input_kernel", desc=f"rcnn_input_fused rows={rows}")
     return out

@@ -52,6 +52,8 @@ def test_row_shards_reproduce_the_unsharded_logits_bit_for_bit(cuda, P, D, world
             starts.append(torch.sigmoid(run_stack(se_stack, mean_p)).view(-1))
     assert torch.equal(torch.cat(tiles), logits)
     assert torch.equal(torch.cat(ends), end) and torch.equal(torch.cat(starts), start)
+    from jmodt_b200.head import dual_softmax
+    assert torch.equal(dual_softmax(torch.cat(tiles)), link)
 
 
 def _nccl_worker(rank, world, port, P, D, q):
@@ -67,14 +69,15 @@ def _nccl_worker(rank, world, port, P, D, q):
     pred, det = (t.to(dev) for t in _features(P, D))
     link, start, end, logits = sharded_affinity_device(rcnn.link_layer, rcnn.se_layer, pred, det)
     wl, ws, we, wlog = affinity(rcnn, pred, det)
-    ok = (torch.equal(logits, wlog) and torch.equal(link, wl) and torch.equal(start, ws) and torch.equal(end, we)
-          and logits.shape == (P, D))
+    checks = {"logits": torch.equal(logits, wlog), "link": torch.equal(link, wl), "start": torch.equal(start, ws),
+              "end": torch.equal(end, we), "shape": logits.shape == (P, D)}
     # shard-boundary exchange: rank r receives rank r + 1's first-frame features
     mine = torch.full((8, 512), float(rank), device=dev)
     nb = exchange_boundary_features(mine)
-    ok = ok and ((nb is None) if rank == world - 1 else bool((nb == rank + 1).all()))
+    checks["boundary"] = (nb is None) if rank == world - 1 else bool((nb == rank + 1).all())
     torch.cuda.synchronize()
-    q.put((rank, bool(ok)))
+    bad = [k for k, v in checks.items() if not v]
+    q.put((rank, True if not bad else "mismatch: " + ",".join(bad)))
     dist.barrier()
     dist.destroy_process_group()
 
