@@ -29,21 +29,24 @@
 
 namespace jmb {
 
-// warp roles: 0-15 epilogue (TMEM lane quadrant w&3, part (w>>2)&1, 32-column block w>>3 of the part),
-//             16-23 gather (two threads per column: alternate groups of four 8-channel k-groups),
-//             24 MMA issuer (one thread), 25 tile scheduler (one thread)
-constexpr int SF_EPI_WARPS = 16;
-constexpr int SF_GATHER_WARP0 = 16, SF_GATHER_WARPS = 8;
+// warp roles: 0-7   epilogue (TMEM lane quadrant w&3, part w>>2: one warp drains its quadrant's 64 columns of the part),
+//             8-23  gather (four threads per column, one block of four 8-channel k-groups each: a single batch of
+//                   eight 16-byte loads in flight per thread),
+//             24    MMA issuer (warp-uniform control flow, one elected lane issues), 25 tile scheduler (one thread)
+constexpr int SF_EPI_WARPS = 8;
+constexpr int SF_GATHER_WARP0 = 8, SF_GATHER_WARPS = 16;
 constexpr int SF_ISSUER_WARP = 24, SF_SCHED_WARP = 25;
 constexpr int SF_THREADS = (SF_SCHED_WARP + 1) * 32;      // 832
 // A tile of 128 columns is processed as two PARTS of 64 columns with their own accumulator columns, operand-image
-// slices and barriers.  The dependent chain of a part is  gather -> L1 -> epilogue -> L2 -> epilogue -> L3 -> epilogue;
-// ONE issuer thread walks the two chains interleaved (A.L1 B.L1 A.L2 B.L2 A.L3 B.L3 ...), so while the tensor pipe
-// runs one part's MMAs the other part's eight epilogue warps drain its accumulator.  (The first versions gave every
-// part its own issuer thread: the two issuers shared the pipe, fell into lock-step — both parts issuing, then both
-// draining — and the pipe sat idle during every epilogue: in-kernel timeline profiles/r01/sa_fused_parts.txt, 48 % of
-// a tile period.  Putting all sixteen epilogue warps on one part at a time does not help either: an epilogue is a
-// ~1 100-cycle latency chain whatever its width, profiles/r02/sa_fused_timeline_v5a.txt.)
+// slices, barriers and epilogue warps.  The dependent chain of a part is  gather (+ layer 1) -> L2 -> epilogue -> L3 ->
+// pooling epilogue;  ONE issuer walks the two chains interleaved (A.L2 B.L2 A.L3 B.L3 ...), so while the tensor pipe runs
+// one part's MMAs the other part's epilogue warps drain its accumulator.  When the last layer is a single 128-row block,
+// tensor memory has room for a SECOND accumulator per part: layer 2 accumulates into X, layer 3 into Y, and the pooling
+// epilogue of tile t (reading Y) overlaps layer 2 of tile t+1 (writing X).
+// History (in-kernel timelines under profiles/): one issuer thread per part -> the issuers fell into lock-step and the
+// pipe idled during every epilogue (r01/sa_fused_parts.txt); all epilogue warps on one part at a time -> no gain, an
+// epilogue is a ~1 100-cycle latency chain whatever its width (r02/sa_fused_timeline_v5a.txt); `if (lane == 0)` around
+// tcgen05.mma -> an ELECT/BRA serialisation loop per instruction, ~60 issue cycles per MMA (v5b -> v5c: 3.3 -> 2.2 ms).
 constexpr int SF_NP = 2;
 constexpr int SF_PART = TC_BN / SF_NP;                              // 64 columns per part
 constexpr uint32_t SF_PART_OFF = (SF_PART / 8) * TC_SBO;            // byte offset of part 1 inside an operand image
@@ -56,6 +59,7 @@ constexpr int SF_CHUNK = 2 * TC_IMG;          // hi + lo image of one 32-row chu
 constexpr int SF_SMEM = (SF_MAXKC1 + SF_MAXKC1 + 4) * SF_CHUNK;   // W1 + X1 + activations = 224 KB
 constexpr int SF_TSLOTS = 4;                  // tile ring (dynamic scheduler)
 constexpr uint32_t SF_TMEM_W2 = 128, SF_TMEM_W3 = 256;             // column bases (hi at +0, lo at +64 of each block)
+constexpr uint32_t SF_TMEM_ACC_Y = 384;                            // second accumulator pair (free when W3 is one block)
 
 struct SaFusedParams {
     const __nv_bfloat16 *w1, *w2, *w3;
@@ -139,18 +143,6 @@ __device__ __forceinline__ void weight_rows_to_tmem(const __nv_bfloat16 *wpack_b
 //   W3[:, 0:128] . act2 + W3[:, 128:256] . channels (both A blocks in tensor memory, the second with the K-major row
 //   image as B), and every column is written point-major (rows, 128) — no pooling.  The (G, 256, 512) concat, both
 //   transposes of the pooled tensor and two activation round trips of the unfused path disappear.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 template <bool ROWS>
 __global__ void __launch_bounds__(SF_THREADS, 1)
 sa_fused_kernel(const SaFusedParams p) {
@@ -159,7 +151,9 @@ sa_fused_kernel(const SaFusedParams p) {
     uint8_t *s_w1 = sf_smem;
     uint8_t *s_x1 = sf_smem + SF_MAXKC1 * SF_CHUNK;
     uint8_t *s_act = s_x1 + SF_MAXKC1 * SF_CHUNK;
-    __shared__ __align__(8) uint64_t s_x1_full[SF_NP], s_x1_free[SF_NP], s_acc_full[SF_NP], s_epi_done[SF_NP], s_w1_full,
+    // per part: x1_full / x1_free (gather <-> issuer), and per accumulator c (0 = X, 1 = Y): acc_full (issuer -> epilogue),
+    // epi_done (epilogue -> issuer)
+    __shared__ __align__(8) uint64_t s_x1_full[SF_NP], s_x1_free[SF_NP], s_acc_full[SF_NP][2], s_epi_done[SF_NP][2], s_w1_full,
         s_tfull[SF_TSLOTS], s_tempty[SF_TSLOTS];
     __shared__ int s_tile[SF_TSLOTS];
     __shared__ uint32_t s_tmem_base;
@@ -170,8 +164,10 @@ sa_fused_kernel(const SaFusedParams p) {
         for (int h = 0; h < SF_NP; ++h) {
             mbar_init(&s_x1_full[h], SF_GATHER_WARPS / SF_NP);   // one arrival per gather warp of the part
             mbar_init(&s_x1_free[h], 1);
-            mbar_init(&s_acc_full[h], 1);
-            mbar_init(&s_epi_done[h], SF_EPI_WARPS / SF_NP);
+            for (int c = 0; c < 2; ++c) {
+                mbar_init(&s_acc_full[h][c], 1);
+                mbar_init(&s_epi_done[h][c], SF_EPI_WARPS / SF_NP);
+            }
         }
         for (int s = 0; s < SF_TSLOTS; ++s) {
             mbar_init(&s_tfull[s], 1);
@@ -191,13 +187,13 @@ sa_fused_kernel(const SaFusedParams p) {
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    // The X1 image rows between K1 and the next multiple of 16 are read by the last layer-1 MMA but never written by
-    // the gather: clear the whole image once (their weights are zero, but 0 * garbage-NaN would poison the sum).
-    for (int i = threadIdx.x; i < SF_MAXKC1 * SF_CHUNK / 16; i += SF_THREADS)
+    // Image rows between the layer width and the next multiple of 16 are read by the last k-step's MMAs but never
+    // written: clear the images once (their weights are zero, but 0 * garbage-NaN would poison the sum).
+    for (int i = threadIdx.x; i < (SF_MAXKC1 + 4) * SF_CHUNK / 16; i += SF_THREADS)
         reinterpret_cast<uint4 *>(s_x1)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
 
-    // ---- prologue: all weights become resident (W1 in shared memory, W2 / W3 in tensor memory) ----
+    // ---- prologue: all weights become resident (ROWS: W1 in shared memory; W2 / W3 in tensor memory) ----
     if (ROWS) {
         if (threadIdx.x == SF_ISSUER_WARP * 32) {
             mbar_arrive_expect_tx(&s_w1_full, (uint32_t)p.Kc1 * SF_CHUNK);
@@ -224,8 +220,10 @@ sa_fused_kernel(const SaFusedParams p) {
     const int N = ROWS ? TC_BN : p.npoint * p.nsample;
     const int Nt = N / TC_BN;
     const int total_tiles = ROWS ? (int)(p.rows / TC_BN) : p.G * Nt;     // < 2^31 (checked by the launcher)
-    // MMA phases of a part: ROWS: layer 1, layer 2, layer 3; SA: layer 2 (layer 1 came with the gather), Mt3 row blocks of layer 3
-    const int nsteps = ROWS ? 3 : 1 + p.Mt3;
+    // SA: layer 2 accumulates into X (columns 0..127), the Mt3 row blocks of layer 3 into Y — a second pair of
+    // accumulators when tensor memory has room for it (one W3 block), else X again
+    const bool split_acc = !ROWS && p.w3_blocks == 1;
+    const uint32_t acc_y = split_acc ? SF_TMEM_ACC_Y : 0u;
 
     // tile ring, consumer side: slot i is read by every consumer warp and released with one arrival per warp
     auto ring_read = [&](uint32_t i) -> int {
@@ -236,40 +234,39 @@ sa_fused_kernel(const SaFusedParams p) {
 
     if (warp < SF_EPI_WARPS) {
         // ====================================== epilogue warps ======================================
-        // warp w drains part h = (w >> 2) & 1: rows [32*quad, +32) x columns [32*sblk, +32) of the part.  The two parts
-        // have their own eight warps so that their epilogues (a ~1 100-cycle latency chain each: barrier wake-up,
-        // tcgen05.ld, bias / ReLU / bf16 split, shared-memory stores, proxy fence, arrival) overlap each other as well
-        // as the other part's MMAs.
-        const int quad = warp & 3, h = (warp >> 2) & 1, sblk = warp >> 3;
+        // warp w drains part h = w >> 2: accumulator rows [32*quad, +32), all 64 columns of the part (two 32-column loads)
+        const int quad = warp & 3, h = warp >> 2;
         const int m = quad * 32 + lane;  // accumulator row (output channel) of this thread
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * PART);
-        uint32_t acc_phase = 0;
+        uint32_t ph[2] = {0, 0};
 
         // accumulator part -> next layer's operand image (row m of the accumulator is row k = m of the operand)
         auto epilogue_act = [&](const float *bias_ptr) {
             const float bias = __ldg(bias_ptr + m);
             uint8_t *ahi = s_act + (size_t)quad * SF_CHUNK, *alo = ahi + TC_IMG;
             const uint32_t rowoff = (uint32_t)(lane >> 3) * TC_LBO + (uint32_t)(lane & 7) * 16;
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
+#pragma unroll 1
+            for (int sblk = 0; sblk < 2; ++sblk) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 hh, ll;
-                float *w = v + q * 8;
+                for (int q = 0; q < 4; ++q) {
+                    uint4 hh, ll;
+                    float *w = v + q * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = fmaxf(w[j] + bias, 0.f);
-                split2(w[0], w[1], hh.x, ll.x);
-                split2(w[2], w[3], hh.y, ll.y);
-                split2(w[4], w[5], hh.z, ll.z);
-                split2(w[6], w[7], hh.w, ll.w);
-                const uint32_t off = (uint32_t)(h * (PART / 8) + sblk * 4 + q) * TC_SBO + rowoff;
-                *reinterpret_cast<uint4 *>(ahi + off) = hh;
-                *reinterpret_cast<uint4 *>(alo + off) = ll;
+                    for (int j = 0; j < 8; ++j) w[j] = fmaxf(w[j] + bias, 0.f);
+                    split2(w[0], w[1], hh.x, ll.x);
+                    split2(w[2], w[3], hh.y, ll.y);
+                    split2(w[4], w[5], hh.z, ll.z);
+                    split2(w[6], w[7], hh.w, ll.w);
+                    const uint32_t off = (uint32_t)(h * (PART / 8) + sblk * 4 + q) * TC_SBO + rowoff;
+                    *reinterpret_cast<uint4 *>(ahi + off) = hh;
+                    *reinterpret_cast<uint4 *>(alo + off) = ll;
+                }
             }
         };
 
-        // max over the nsample columns of each centre (nsample divides 64: a window never leaves the part);
-        // the sblk == 0 warp of each quadrant pools the whole part
+        // max over the nsample columns of each centre (nsample divides 64: a window never leaves the part)
         auto epilogue_pool = [&](int tile, int mt) {
             const int g = tile / Nt;
             const int nt = tile - g * Nt;
@@ -286,7 +283,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll 1
             for (int c0 = 0; c0 < PART; c0 += 32) {
                 float v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
+                tmem_ld32(taddr + acc_y + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias, 0.f);
                 if (sub == 32) {
@@ -310,60 +307,77 @@ sa_fused_kernel(const SaFusedParams p) {
             }
         };
 
-        // ROWS: every column is an output row; a warp's 32 channels of one column are one 128-byte store
+        // ROWS: every column is an output row
         auto epilogue_rows = [&](int tile) {
             const float bias = __ldg(p.b3 + m);
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
-            const size_t row0 = (size_t)tile * TC_BN + h * PART + sblk * 32;
-            if (p.rows_per_group > 0) {
-                // channel-first (group, 128, rows_per_group): this thread's 32 consecutive rows of channel m are 128
-                // contiguous bytes (a tile never straddles a group: rows_per_group is a multiple of 128)
-                const size_t grp = row0 / (size_t)p.rows_per_group, r = row0 - grp * (size_t)p.rows_per_group;
-                float4 *dst4 = reinterpret_cast<float4 *>(p.out + (grp * TC_BM + m) * (size_t)p.rows_per_group + r);
+#pragma unroll 1
+            for (int sblk = 0; sblk < 2; ++sblk) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)(sblk * 32), v);
+                const size_t row0 = (size_t)tile * TC_BN + h * PART + sblk * 32;
+                if (p.rows_per_group > 0) {
+                    // channel-first (group, 128, rows_per_group): this thread's 32 consecutive rows of channel m are 128
+                    // contiguous bytes (a tile never straddles a group: rows_per_group is a multiple of 128)
+                    const size_t grp = row0 / (size_t)p.rows_per_group, r = row0 - grp * (size_t)p.rows_per_group;
+                    float4 *dst4 = reinterpret_cast<float4 *>(p.out + (grp * TC_BM + m) * (size_t)p.rows_per_group + r);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    dst4[j >> 2] = make_float4(fmaxf(v[j] + bias, 0.f), fmaxf(v[j + 1] + bias, 0.f),
-                                               fmaxf(v[j + 2] + bias, 0.f), fmaxf(v[j + 3] + bias, 0.f));
-            } else {
-                float *dst = p.out + row0 * TC_BM + m;
+                    for (int j = 0; j < 32; j += 4)
+                        dst4[j >> 2] = make_float4(fmaxf(v[j] + bias, 0.f), fmaxf(v[j + 1] + bias, 0.f),
+                                                   fmaxf(v[j + 2] + bias, 0.f), fmaxf(v[j + 3] + bias, 0.f));
+                } else {
+                    float *dst = p.out + row0 * TC_BM + m;      // a warp's 32 channels of one row are one 128-byte store
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_BM] = fmaxf(v[j] + bias, 0.f);
+                }
             }
         };
 
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg + 512 : nullptr;
         int di = 0;
 #define SF_ESTAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
+        auto wait_full = [&](int c) {
+            mbar_wait(&s_acc_full[h][c], ph[c]); ph[c] ^= 1;
+            tc_fence_after();
+        };
+        auto hand_back = [&](int c) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_epi_done[h][c]);
+        };
         uint32_t ti = 0;
         int tile;
         while ((tile = ring_read(ti)) >= 0) {
-            for (int step = 0; step < nsteps; ++step) {
-                SF_ESTAMP(20 + step);
-                mbar_wait(&s_acc_full[h], acc_phase); acc_phase ^= 1;
-                tc_fence_after();
-                SF_ESTAMP(30 + step);
-                if (ROWS) {
+            if (ROWS) {
+                for (int step = 0; step < 3; ++step) {
+                    wait_full(0);
                     if (step < 2) {
                         epilogue_act(step == 0 ? p.b1 : p.b2);
                         fence_proxy_async();
                     } else {
                         epilogue_rows(tile);
                     }
-                } else if (step == 0) {
-                    // accumulator rows >= the layer's real width are zero padding nobody reads (the next layer's
-                    // MMAs stop at its last real k-step): their quadrants' warps only hand the barrier on
-                    if (quad * 32 < ((p.C2 + 15) & ~15)) {
-                        epilogue_act(p.b2);
-                        fence_proxy_async();
-                    }
-                } else if (sblk == 0 && (step - 1) * TC_BM + quad * 32 < p.C3) {
-                    epilogue_pool(tile, step - 1);
+                    hand_back(0);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_epi_done[h]);
-                SF_ESTAMP(40 + step);
+            } else {
+                SF_ESTAMP(20);
+                wait_full(0);
+                SF_ESTAMP(30);
+                // accumulator rows >= the layer's real width are zero padding nobody reads (the next layer's MMAs stop at
+                // its last real k-step): their quadrants' warps only hand the barrier on
+                if (quad * 32 < ((p.C2 + 15) & ~15)) {
+                    epilogue_act(p.b2);
+                    fence_proxy_async();
+                }
+                hand_back(0);
+                SF_ESTAMP(40);
+                for (int mt = 0; mt < p.Mt3; ++mt) {
+                    SF_ESTAMP(21 + mt);
+                    wait_full(1);
+                    SF_ESTAMP(31 + mt);
+                    if (mt * TC_BM + quad * 32 < p.C3) epilogue_pool(tile, mt);
+                    hand_back(1);
+                    SF_ESTAMP(41 + mt);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
@@ -372,10 +386,10 @@ sa_fused_kernel(const SaFusedParams p) {
     } else if (warp < SF_ISSUER_WARP) {
         // ====================================== gather warps ======================================
         const int tg = threadIdx.x - SF_GATHER_WARP0 * 32;
-        const int sub = tg >> 7;                 // which alternate block of four k-groups this thread fetches
+        const int sub = tg >> 7;                 // which block of four k-groups this thread fetches (0..3)
         const int col = tg & 127, h = col / PART;
         const int n_groups = ROWS ? p.row_pitch / 8 : p.C1 / 8;   // k-groups of 8 channels this column's image row holds
-        // Two threads = one column: its contiguous point-major row is split to bf16 hi/lo and stored as 16-byte slots of
+        // Four threads = one column: the contiguous point-major row is split to bf16 hi/lo and stored as 16-byte slots of
         // the K-major operand image (offset = (k/8)*LBO + (n/8)*SBO + (n%8)*16; consecutive threads -> consecutive slots:
         // conflict-free).
         const uint32_t noff = (uint32_t)(col >> 3) * TC_SBO + (uint32_t)(col & 7) * 16;
@@ -389,15 +403,22 @@ sa_fused_kernel(const SaFusedParams p) {
             *reinterpret_cast<uint4 *>(img) = hh;
             *reinterpret_cast<uint4 *>(img + TC_IMG) = ll;
         };
+        auto publish = [&](uint32_t ti) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&s_x1_full[h]);
+                mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
+            }
+        };
         uint32_t ti = 0;
         int tile;
         if (ROWS) {
-            // ROWS: consecutive rows of the input (pulled into L2 ahead of time by the scheduler), 16-byte loads, 4 groups
-            // of 8 channels in flight per thread
+            // ROWS: consecutive rows of the input (pulled into L2 ahead of time by the scheduler), 16-byte loads
             while ((tile = ring_read(ti)) >= 0) {
-                if (ti > 0) mbar_wait(&s_x1_free[h], (ti - 1) & 1);   // the MMAs that read this part of the previous tile are done
                 const float *frow = p.feats + ((size_t)tile * TC_BN + col) * p.row_pitch;
-                for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
+                bool waited = ti == 0;
+                for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 16) {
                     float4 a4[4], b4[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -405,6 +426,10 @@ sa_fused_kernel(const SaFusedParams p) {
                             a4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8));
                             b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
                         }
+                    if (!waited) {     // the MMAs that read this part of the previous tile are done (loads already in flight)
+                        mbar_wait(&s_x1_free[h], (ti - 1) & 1);
+                        waited = true;
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (kg0 + u < n_groups) {
@@ -412,12 +437,8 @@ sa_fused_kernel(const SaFusedParams p) {
                             put(kg0 + u, v);
                         }
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&s_x1_full[h]);
-                    mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
-                }
+                if (!waited) mbar_wait(&s_x1_free[h], (ti - 1) & 1);
+                publish(ti);
                 ++ti;
             }
         } else {
@@ -431,6 +452,7 @@ sa_fused_kernel(const SaFusedParams p) {
                 const int n = (tl - g * Nt) * TC_BN + col;
                 return __ldg(p.idx + (size_t)g * N + n);
             };
+            const int kg0 = sub * 4;       // C1 <= 128: at most 16 k-groups, one block of four per thread
             tile = ring_read(0);
             int pi = tile >= 0 ? col_index(tile) : 0;
             while (tile >= 0) {
@@ -438,16 +460,10 @@ sa_fused_kernel(const SaFusedParams p) {
                 const int pi_next = next_tile >= 0 ? col_index(next_tile) : 0;     // in flight while this tile is produced
                 const int g = tile / Nt;
                 const int n = (tile - g * Nt) * TC_BN + col;
-                // relative coordinates (pointnet2_utils.py:252: grouped_xyz -= new_xyz)
-                const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
-                const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
-                const float *frow = p.z ? p.z + ((size_t)g * p.n_pts + pi) * p.C1 : nullptr;
-                const float dx = __fsub_rn(__ldg(pt), __ldg(cen));
-                const float dy = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
-                const float dz = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
-                bool waited = ti == 0;
-                for (int kg0 = sub * 4; kg0 < n_groups; kg0 += 8) {
-                    float4 a4[4], b4[4];
+                float4 a4[4], b4[4];
+                float dx = 0.f, dy = 0.f, dz = 0.f;
+                if (kg0 < n_groups) {
+                    const float *frow = p.z ? p.z + ((size_t)g * p.n_pts + pi) * p.C1 : nullptr;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -456,10 +472,15 @@ sa_fused_kernel(const SaFusedParams p) {
                             b4[u] = __ldg(reinterpret_cast<const float4 *>(frow + (kg0 + u) * 8) + 1);
                         }
                     }
-                    if (!waited) {     // the MMAs that read this part of the previous tile are done (loads already in flight)
-                        mbar_wait(&s_x1_free[h], (ti - 1) & 1);
-                        waited = true;
-                    }
+                    // relative coordinates (pointnet2_utils.py:252: grouped_xyz -= new_xyz)
+                    const float *cen = p.centres + ((size_t)g * p.npoint + n / p.nsample) * 3;
+                    const float *pt = p.xyz + ((size_t)g * p.n_pts + pi) * 3;
+                    dx = __fsub_rn(__ldg(pt), __ldg(cen));
+                    dy = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
+                    dz = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
+                }
+                if (ti > 0) mbar_wait(&s_x1_free[h], (ti - 1) & 1);     // the MMAs that read this part of the previous tile are done
+                if (kg0 < n_groups) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (kg0 + u < n_groups) {
@@ -472,13 +493,7 @@ sa_fused_kernel(const SaFusedParams p) {
                             put(kg0 + u, v);
                         }
                 }
-                if (!waited) mbar_wait(&s_x1_free[h], (ti - 1) & 1);     // a thread without a k-group of its own still keeps the phase order
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&s_x1_full[h]);
-                    mbar_arrive(&s_tempty[ti % SF_TSLOTS]);
-                }
+                publish(ti);
                 tile = next_tile;
                 pi = pi_next;
                 ++ti;
@@ -490,8 +505,7 @@ sa_fused_kernel(const SaFusedParams p) {
         // (layer, part) are issued by one elected lane (see elect_one()).  Descriptors are formed by adding constants
         // to a base descriptor (the start-address field is the low 14 bits; images never cross it).
         if (ROWS) mbar_wait(&s_w1_full, 0);
-        uint32_t epi_phase[SF_NP] = {0, 0};
-        bool first_use[SF_NP] = {true, true};
+        uint32_t dph[SF_NP][2] = {{0, 0}, {0, 0}};      // phases of epi_done[h][c]
         const uint64_t w1_desc = make_smem_desc(smem_u32(s_w1));
         const uint64_t x1_desc0 = make_smem_desc(smem_u32(s_x1));
         const uint64_t act_desc0 = make_smem_desc(smem_u32(s_act));
@@ -500,26 +514,23 @@ sa_fused_kernel(const SaFusedParams p) {
         long long *dbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
         int di = 0;
 #define SF_STAMP(tag) do { if (dbg && di < 480) { dbg[di++] = (tag); dbg[di++] = clock64(); } } while (0)
+        auto wait_done = [&](int h, int c) {
+            mbar_wait(&s_epi_done[h][c], dph[h][c]); dph[h][c] ^= 1;
+        };
         uint32_t ti = 0;
         int tile;
         while ((tile = ring_read(ti)) >= 0) {
-            for (int step = 0; step < nsteps; ++step) {
+            if (ROWS) {
+                for (int step = 0; step < 3; ++step) {
 #pragma unroll
-                for (int h = 0; h < SF_NP; ++h) {
-                    const uint32_t acc = tmem_base + (uint32_t)h * PART;
-                    const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
-                    const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
-                    SF_STAMP(1 + step * 2 + h);
-                    if (first_use[h]) {
-                        first_use[h] = false;
-                    } else {     // accumulator part h is free / its activation image is ready
-                        mbar_wait(&s_epi_done[h], epi_phase[h]); epi_phase[h] ^= 1;
-                    }
-                    if (step == 0) mbar_wait(&s_x1_full[h], ti & 1);
-                    tc_fence_after();
-                    SF_STAMP(10 + step * 2 + h);
-                    if (elect_one()) {
-                        if (ROWS) {
+                    for (int h = 0; h < SF_NP; ++h) {
+                        const uint32_t acc = tmem_base + (uint32_t)h * PART;
+                        const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
+                        const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
+                        if (ti > 0 || step > 0) wait_done(h, 0);     // accumulator free / activation image ready
+                        if (step == 0) mbar_wait(&s_x1_full[h], ti & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
                             if (step == 0) {
                                 // layer 1 reads only the extra inputs: k-groups 16, 17 = first k16 step of image chunk 4
                                 const uint64_t xd = x1_desc + 4 * D_CHUNK;
@@ -549,20 +560,55 @@ sa_fused_kernel(const SaFusedParams p) {
                                     umma_commit(&s_x1_free[h]);
                                 }
                             }
-                        } else if (step == 0) {
-                            // layer 2 (TS): A = W2 in tensor memory, B = layer 1's output as the gather threads wrote it (K-major)
+                            umma_commit(&s_acc_full[h][0]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
+                // ---- layer 2 of both parts: A = W2 in tensor memory, B = layer 1's output as the gather wrote it (K-major).
+                // X is free: layer 3 of the previous tile (issued earlier) waited for the epilogue that drained it.  Without
+                // the second accumulator pair X also holds layer 3, so its last pooling epilogue must be over.
+#pragma unroll
+                for (int h = 0; h < SF_NP; ++h) {
+                    const uint32_t acc = tmem_base + (uint32_t)h * PART;
+                    const uint64_t x1_desc = x1_desc0 + (uint64_t)h * D_PART;
+                    SF_STAMP(1 + h);
+                    if (!split_acc && ti > 0) wait_done(h, 1);
+                    mbar_wait(&s_x1_full[h], ti & 1);
+                    tc_fence_after();
+                    SF_STAMP(10 + h);
+                    if (elect_one()) {
 #pragma unroll 2
-                            for (int k16 = 0; k16 < nk2; ++k16) {
-                                const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
-                                const uint32_t ahi = tmem_base + SF_TMEM_W2 + (uint32_t)k16 * 8;
-                                umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, k16 != 0);
-                                umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
-                                umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
-                            }
-                            umma_commit(&s_x1_free[h]);      // the gather warps may refill this part for the next tile
+                        for (int k16 = 0; k16 < nk2; ++k16) {
+                            const uint64_t xd = x1_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
+                            const uint32_t ahi = tmem_base + SF_TMEM_W2 + (uint32_t)k16 * 8;
+                            umma_ts_part<SF_IDESC_L1>(acc, ahi, xd, k16 != 0);
+                            umma_ts_part<SF_IDESC_L1>(acc, ahi + 64, xd, 1);
+                            umma_ts_part<SF_IDESC_L1>(acc, ahi, xd + D_IMG, 1);
+                        }
+                        umma_commit(&s_x1_free[h]);      // the gather warps may refill this part for the next tile
+                        umma_commit(&s_acc_full[h][0]);
+                    }
+                    __syncwarp();
+                }
+                // ---- the Mt3 row blocks of layer 3: A = W3 block in tensor memory, B = layer 2's output (MN-major)
+                for (int mt = 0; mt < p.Mt3; ++mt) {
+#pragma unroll
+                    for (int h = 0; h < SF_NP; ++h) {
+                        const uint32_t acc = tmem_base + acc_y + (uint32_t)h * PART;
+                        const uint64_t act_desc = act_desc0 + (uint64_t)h * D_PART;
+                        SF_STAMP(3 + mt * 2 + h);
+                        if (mt == 0) {
+                            wait_done(h, 0);                                  // layer 2's epilogue wrote the activation image
+                            if (split_acc && ti > 0) wait_done(h, 1);         // Y drained by the previous tile's pooling
                         } else {
-                            // row block step-1 of layer 3 (TS): A = W3 block in tensor memory, B = layer 2's output (MN-major)
-                            const uint32_t wcol = tmem_base + SF_TMEM_W3 + (uint32_t)(step - 1) * 128;
+                            wait_done(h, 1);                                  // previous row block pooled
+                        }
+                        tc_fence_after();
+                        SF_STAMP(12 + mt * 2 + h);
+                        if (elect_one()) {
+                            const uint32_t wcol = tmem_base + SF_TMEM_W3 + (uint32_t)mt * 128;
 #pragma unroll 2
                             for (int k16 = 0; k16 < nk3; ++k16) {
                                 const uint64_t xd = act_desc + (uint64_t)(k16 >> 1) * D_CHUNK + (uint64_t)(k16 & 1) * D_K16;
@@ -571,10 +617,10 @@ sa_fused_kernel(const SaFusedParams p) {
                                 umma_ts_part<SF_IDESC>(acc, ahi + 64, xd, 1);
                                 umma_ts_part<SF_IDESC>(acc, ahi, xd + D_IMG, 1);
                             }
+                            umma_commit(&s_acc_full[h][1]);
                         }
-                        umma_commit(&s_acc_full[h]);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
             if (lane == 0) mbar_arrive(&s_tempty[ti % SF_TSLOTS]);

@@ -93,7 +93,11 @@ class CapturedPath:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        # kernel nodes inherit the priority of the stream they were captured on: JMB_MAIN_PRIORITY=-1 captures the step on
+        # a high-priority stream (its forked branch streams stay at the default priority)
+        prio = int(os.environ.get("JMB_MAIN_PRIORITY", "0"))
+        cap_stream = torch.cuda.Stream(priority=prio) if prio else None
+        with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local"):
             self.outputs = fn(inputs)
         self.launches_per_replay = _lib.launch_count - n0     # this library's kernels inside one replay
         torch.cuda.synchronize()
@@ -124,7 +128,7 @@ class GeometryAhead:
     def __init__(self, geometry_fn, first_points: torch.Tensor):
         self.geometry_fn = geometry_fn
         self.plan = geometry_fn(first_points)
-        self.side = torch.cuda.Stream(device=first_points.device, priority=-1)
+        self.side = torch.cuda.Stream(device=first_points.device, priority=int(os.environ.get("JMB_GEO_PRIORITY", "-1")))
 
     def step(self, main_fn, next_points: torch.Tensor):
         main = torch.cuda.current_stream()
