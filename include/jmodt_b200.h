@@ -200,12 +200,12 @@ JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *f
 /* One whole single-scale set-abstraction layer (reference pointnet2_modules.py:20-63 with QueryAndGroup and a
  * 3-layer SharedMLP) in ONE kernel: grouped gather -> MLP -> max over nsample.  The first layer is linear up to its
  * ReLU and grouping only selects columns, so it is applied BEFORE the gather: the caller passes
- *     z   (G, n_pts, C1) point-major = W1[:, 3:] . features of the n_pts points (one dense layer, jmb_tc_mlp_layer
- *         with out_mode 2; NULL when the layer has no input features), and
+ *     z   (G, n_pts, C1) point-major = W1[:, 3:] . features + b1 of the n_pts points (one dense layer with bias,
+ *         jmb_tc_mlp_layer with out_mode 2; NULL when the layer has no input features — b1 is then taken from w1x), and
  *     w1x (C1, 4) fp32 rows [W1[k, 0], W1[k, 1], W1[k, 2], b1[k]] (the coordinate columns and the bias) in HOST memory:
  *         the 2 KB table is copied into the launch parameters (constant bank), so a captured launch keeps the values
  *         it was captured with,
- * and the kernel's gather finishes the layer, relu(z[idx] + W1x . (xyz[idx] - centre) + b1), while it stages the operand.
+ * and the kernel's gather finishes the layer, relu(z[idx] + W1x . (xyz[idx] - centre)), while it stages the operand.
  * Layer widths C1, C2 <= 128 (C1 % 8 == 0) and C3 <= 256; w2 / w3 are packed layers (jmodt_b200/tc.py) ZERO-PADDED to
  * 128 x 128 and (128 or 256) x 128; nsample in {8,16,32,64}, npoint*nsample a multiple of 128.
  * idx (G, npoint, nsample), xyz (G, n_pts, 3), centres (G, npoint, 3) -> out (G, C3, npoint), or point-major

@@ -282,17 +282,17 @@ sa_fused_kernel(const SaFusedParams p) {
             float run = -INFINITY;
 #pragma unroll 1
             for (int c0 = 0; c0 < PART; c0 += 32) {
+                // bias and ReLU AFTER the maximum: relu(. + b) is monotone and b is per row, so
+                // max_j relu(v_j + b) = relu(max_j v_j + b) exactly — one add / max per window instead of per element
                 float v[32];
                 tmem_ld32(taddr + acc_y + (uint32_t)c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias, 0.f);
                 if (sub == 32) {
                     float mx = v[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
                     run = fmaxf(run, mx);
                     if ((c0 + 32) % p.nsample == 0) {
-                        if (live) orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = run;
+                        if (live) orow[(size_t)((c0 + 32) / p.nsample - 1) * ostride] = fmaxf(run + bias, 0.f);
                         run = -INFINITY;
                     }
                 } else {
@@ -301,7 +301,7 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j >= w0 && j < w0 + sub) mx = fmaxf(mx, v[j]);
-                        if (live) orow[(size_t)((c0 + w0) / p.nsample) * ostride] = mx;
+                        if (live) orow[(size_t)((c0 + w0) / p.nsample) * ostride] = fmaxf(mx + bias, 0.f);
                     }
                 }
             }
@@ -488,7 +488,9 @@ sa_fused_kernel(const SaFusedParams p) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 w = p.w1x[(kg0 + u) * 8 + j];     // constant bank, warp-uniform index
-                                v[j] = fmaxf(fmaf(w.x, dx, fmaf(w.y, dy, fmaf(w.z, dz, v[j]))) + w.w, 0.f);
+                                // b1 is already in Z (the points' GEMM adds it); without input features it comes from w.w
+                                const float base = p.z ? v[j] : w.w;
+                                v[j] = fmaxf(fmaf(w.x, dx, fmaf(w.y, dy, fmaf(w.z, dz, base))), 0.f);
                             }
                             put(kg0 + u, v);
                         }

@@ -162,8 +162,8 @@ def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) 
 
 def _sa_fused_packs(layers):
     """What sa_fused_kernel consumes of the three layers (cached on the first):
-    W1f = W1[:, 3:] as a linear PackedLayer (applied to the POINTS before the gather; None without input features),
-    w1x (C1, 4) fp32 rows [W1[k, 0:3], b1[k]] (finished by the gather threads), W2 (128 x 128) and W3 (128|256 x 128)
+    W1f = W1[:, 3:] with b1 as a linear PackedLayer (applied to the POINTS before the gather; None without input features),
+    w1x (C1, 4) fp32 rows [W1[k, 0:3], b1[k]] (finished by the gather threads; b1 is used only when there is no Z), W2 (128 x 128) and W3 (128|256 x 128)
     zero-padded images."""
     l1, l2, l3 = layers
     cache = getattr(l1, "_sa_packs", None)
@@ -173,7 +173,7 @@ def _sa_fused_packs(layers):
             w[:, : layer.K] = layer._w32
             return PackedLayer(w, layer.bias[: layer.M], layer.relu)
         w1 = l1._w32
-        w1f = PackedLayer(w1[:, 3:].contiguous(), None, relu=False) if l1.K > 3 else None
+        w1f = PackedLayer(w1[:, 3:].contiguous(), l1.bias[: l1.M], relu=False) if l1.K > 3 else None      # Z carries b1
         w1x = torch.cat((w1[:, :3], l1.bias[: l1.M, None]), dim=1).contiguous().cpu()     # host table: goes into the launch parameters
         cache = l1._sa_packs = (w1f, w1x, l2 if l2.K == 128 else padded(l2, 128), l3 if l3.K == 128 else padded(l3, 128))
     return cache
