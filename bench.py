@@ -37,7 +37,21 @@ RPN_NSAMPLE = [[16, 32]] * 4                              # config.py:77
 FP_CHANNELS = [512, 512, 256, 128]                        # features interpolated at FP levels 3..0 (known side)
 RCNN_NPOINTS, RCNN_RADII, RCNN_NSAMPLE = [128, 32], [0.2, 0.4], [64, 64]   # config.py:133-136
 NMS_BINS = [6300, 2700]                                   # proposal_layer.py:66-70 with PRE_NMS_TOP_N=9000
-SA_FUSED_DRAM_BYTES_PER_LAUNCH = 325.6e6  # dram__bytes_read+write of the SA0 launch, ncu --set full (profiles/r01/sa_fused_v4.ncu.txt)
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02", "traffic.json")   # written by profiles/ncu_traffic.py from the .ncu-rep files
+
+
+def measured_traffic(kernel_substr, min_us=0.0):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the longest profiled launch of a kernel (ncu --set full capture of
+    this repo's bench step, summarised by profiles/ncu_traffic.py); None if no capture is committed."""
+    try:
+        launches = [l for l in json.load(open(TRAFFIC_JSON))["launches"]
+                    if kernel_substr in l["kernel"] and l["duration_us_under_ncu"] >= min_us]
+        best = max(launches, key=lambda l: l["duration_us_under_ncu"])
+        return {"bytes": best["dram_bytes"], "source": "profiles/r02/traffic.json <- " + os.path.basename(best["source"])}
+    except Exception:
+        return None
+
+
 ROIPOOL_BYTES_PER_FRAME = N_PTS * (12 + (FEAT_C + 2) * 4) + N_ROI * ROI_PTS * (3 + FEAT_C + 2) * 4  # 43.6 MB (SURVEY 8d)
 
 
@@ -482,7 +496,10 @@ def run_b200(args):
             ach = lambda r: r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else float("nan")
             achieved = ach(sa_sum)
             roofline = {"bound": "tensor", "kernel": "sa_fused_kernel", "launch": top_desc, "achieved": achieved, "peak": tf_peak,
-                        "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": SA_FUSED_DRAM_BYTES_PER_LAUNCH,
+                        "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                        "traffic": (measured_traffic("sa_fused_kernel", 1000.0) or {}).get("bytes"),
+                        "traffic_source": (measured_traffic("sa_fused_kernel", 1000.0) or {}).get("source"),
+                        "algorithmic_bytes_per_launch": float(B * N_ROI) * (ROI_PTS * 128 * 4 + 128 * 64 * 4 + 128 * 128 * 4),
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                         if peaks else "fallback 1590 TFLOP/s",
                         "algorithmic_flops_per_launch": sa_sum["flops"] / max(1, sa_sum["launches"]),
@@ -496,7 +513,10 @@ def run_b200(args):
                                                "launches_per_step": tc_sum["launches"] / n_probe,
                                                "share_of_step": tc_sum["ms"] / n_probe / ms_per_step,
                                                "note": "sum of per-launch times; sibling launches overlap on forked streams"},
-                        "note": "fp32-grade result = 3 bf16 MMAs per product (W_hi.X_hi + W_lo.X_hi + W_hi.X_lo)"}
+                        "note": "fp32-grade result = 3 bf16 MMAs per product (W_hi.X_hi + W_lo.X_hi + W_hi.X_lo); algorithmic = "
+                                "the reference layer's three 1x1 convs over the grouped tensor; the kernel executes layers "
+                                "2-3 on the tensor cores and finishes layer 1 (applied to the points by a separate small GEMM) "
+                                "in its gather, see executed_flops in `launch`"}
             workload = ("end-to-end region-proposal fusion + link/start-end affinity (BASELINE config 3): RPN point path "
                         "with LI-Fusion on precomputed image maps, proposal layer, roipool3d+canonical, per-proposal "
                         "RCNN, pair affinity; image 3x3 conv stack outside the timed region (SURVEY 8f.1); RCNN on "
@@ -506,7 +526,7 @@ def run_b200(args):
             rp_ms = kernel_ms.get("roipool3d", float("nan"))
             achieved = ROIPOOL_BYTES_PER_FRAME * B / (rp_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": "roipool3d_kernel<true>", "achieved": achieved, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": (measured_traffic("roipool3d_kernel") or {}).get("bytes"),
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                         "algorithmic_bytes_per_launch": ROIPOOL_BYTES_PER_FRAME * B, "kernel_ms": rp_ms}
             workload = ("jmodt/ops suite (BASELINE config 2 op list at the real network shapes): FPS x6, ball_query x10, "

@@ -197,6 +197,16 @@ JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K,
 JMB_API int jmb_feature_gather(int b, int c, int h, int w, int n, const float *fmap, const float *xy,
                                float *out, void *stream);
 
+/* HOST helpers of the reference's roipool3d module (roipool3d.cpp:97-195 `pts_in_boxes3d_cpu`, `roipool3d_cpu`; called by
+ * the reference's dataset code on CPU tensors).  All pointers are HOST pointers; no CUDA call is made.  They complete the
+ * operator API; they are not a fallback of the device path.
+ * pts (n_pts,3), boxes3d (n_boxes,7) [x,y_bottom,z,h,w,l,ry] -> flags (n_boxes,n_pts) int64 0/1 */
+JMB_API int jmb_pts_in_boxes3d_host(int n_pts, int n_boxes, const float *pts, const float *boxes3d, int64_t *flags);
+/* first `sampled` in-box points per box in index order, wrap-around padding, empty flag; pooled arrays must be zeroed by the
+ * caller for empty boxes as in the reference (roipool3d_utils.py:63-65) */
+JMB_API int jmb_roipool3d_host(int n_pts, int n_boxes, int feat_len, int sampled, const float *pts, const float *boxes3d,
+                               const float *pts_feature, float *pooled_pts, float *pooled_features, int64_t *empty_flag);
+
 /* One whole single-scale set-abstraction layer (reference pointnet2_modules.py:20-63 with QueryAndGroup and a
  * 3-layer SharedMLP) in ONE kernel: grouped gather -> MLP -> max over nsample.  The first layer is linear up to its
  * ReLU and grouping only selects columns, so it is applied BEFORE the gather: the caller passes

@@ -1,7 +1,7 @@
 """Same call surface as the GPU entry points of the reference pybind module `roipool3d_cuda`
-(jmodt/ops/roipool3d/src/roipool3d.cpp:198-203).  The reference's two CPU helpers
-(`pts_in_boxes3d_cpu`, `roipool3d_cpu`) are host code outside the GPU hot path and are not
-provided: jmodt_b200 has no CPU path by design.
+(jmodt/ops/roipool3d/src/roipool3d.cpp:198-203), including its two HOST helpers `pts_in_boxes3d_cpu` /
+`roipool3d_cpu` (roipool3d.cpp:97-195), which the reference's dataset code calls on CPU tensors.  Those two run on the
+host by definition; no device op of this package ever routes through them (there is no CPU fallback).
 """
 from __future__ import annotations
 
@@ -29,6 +29,33 @@ def forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
 
 
 forward_slow = forward  # roipool3d.cpp:18-44 computes the same result with a slower kernel
+
+
+def _host(*tensors):
+    for t in tensors:
+        if t.is_cuda or not t.is_contiguous():
+            raise _lib.JmodtB200Error("host helper: tensors must be contiguous CPU tensors")
+
+
+def pts_in_boxes3d_cpu(pts_flag, pts, boxes3d):
+    """roipool3d.cpp:97-125: pts_flag (M, N) int64 <- 1 where point j lies in box i; pts (N, 3), boxes3d (M, 7) float32."""
+    _host(pts_flag, pts, boxes3d)
+    rc = _lib.lib().jmb_pts_in_boxes3d_host(pts.size(0), boxes3d.size(0), pts.data_ptr(), boxes3d.data_ptr(), pts_flag.data_ptr())
+    if rc:
+        raise _lib.JmodtB200Error("pts_in_boxes3d_cpu: bad arguments")
+    return 1
+
+
+def roipool3d_cpu(pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled_empty_flag):
+    """roipool3d.cpp:127-195 on CPU tensors: pts (N, 3), boxes3d (M, 7), pts_feature (N, C) ->
+    pooled_pts (M, S, 3), pooled_features (M, S, C), pooled_empty_flag (M) int64."""
+    _host(pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled_empty_flag)
+    rc = _lib.lib().jmb_roipool3d_host(pts.size(0), boxes3d.size(0), pts_feature.size(1), pooled_pts.size(1), pts.data_ptr(),
+                                       boxes3d.data_ptr(), pts_feature.data_ptr(), pooled_pts.data_ptr(),
+                                       pooled_features.data_ptr(), pooled_empty_flag.data_ptr())
+    if rc:
+        raise _lib.JmodtB200Error("roipool3d_cpu: bad arguments")
+    return 1
 
 
 def forward_canonical(xyz, boxes3d, pts_feature, pool_extra_width, pooled_features, pooled_empty_flag):
