@@ -225,6 +225,14 @@ JMB_API int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const
                          const int *idx, const float *xyz, const float *centres, float *out, int out_point_major,
                          void *stream);
 
+/* First SharedMLP layer of a set-abstraction level applied before the gather, for the layer-by-layer path (levels whose
+ * later layers are too wide for jmb_sa_fused): out (G, C1, npoint*nsample) channel-first
+ *   = relu(z[idx] + W1x . (xyz[idx] - centre)),  z (G, n_pts, C1) point-major = W1[:, 3:] . features + b1 (a dense layer over
+ * the POINTS), w1x (C1, 4) DEVICE rows [W1[k,0], W1[k,1], W1[k,2], b1[k]].  Replaces QueryAndGroup + the first Conv2d
+ * (pointnet2_utils.py:241-264, pytorch_utils.py:6-33) = a grouped GEMM over all npoint*nsample columns. */
+JMB_API int jmb_sa_first_layer(const float *z, const float *w1x, int C1, int G, int npoint, int nsample, int n_pts,
+                               const int *idx, const float *xyz, const float *centres, float *out, void *stream);
+
 /* Input stage of the per-proposal network (reference rcnn.py:172-186: xyz_up_layer 5->128->128, cat with the 128
  * RPN channels, merge_down_layer 256->128) in ONE kernel over consecutive rows of the pooled tensor in the
  * "head layout" written by jmb_roipool3d_canonical_head: in (rows, 136) = [128 channels | x,y,z,mask,depth | 0,0,0]

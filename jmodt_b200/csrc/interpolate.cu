@@ -281,3 +281,85 @@ extern "C" int jmb_group_points_grad(int b, int c, int n, int npoints, int nsamp
                                                                      grad_points);
     return check_launch("group_points_grad");
 }
+
+// ---- first SharedMLP layer of a set-abstraction level, applied BEFORE the gather -------------------------------
+// relu(W1 . [xyz_j - c ; f_j] + b1) = relu(Z_j + W1x . (xyz_j - c)),  Z = W1f . F + b1 over the level's n_pts points
+// (one small dense GEMM, jmb_tc_mlp_layer with point-major output).  This kernel finishes the layer for every grouped
+// neighbour and writes the (G, C1, npoint * nsample) channel-first activation the next dense layer reads — it replaces
+// the grouped-gather GEMM over all npoint * nsample columns (K = 3 + C_in, e.g. 259 x 262 144 columns at RPN level 2)
+// of the layer-by-layer path (reference pointnet2_utils.py:241-264 + the first Conv2d of the SharedMLP).
+// CTA = 32 consecutive columns of one group: the neighbours' Z rows are staged through shared memory with coalesced
+// 16-byte loads (a row is contiguous), then each warp emits whole channels as 128-byte stores.
+namespace jmb {
+
+__global__ void __launch_bounds__(256)
+sa_first_layer_kernel(int C1, int npoint, int nsample, int n_pts, const float *__restrict__ z,
+                      const float4 *__restrict__ w1x, const int *__restrict__ idx, const float *__restrict__ xyz,
+                      const float *__restrict__ centres, float *__restrict__ out) {
+    extern __shared__ __align__(16) float fl_smem[];   // C1 float4 weights, then [32][C1 + 1] rows
+    const int pitch = C1 + 1;
+    float4 *wx = reinterpret_cast<float4 *>(fl_smem);
+    float *rows = fl_smem + 4 * C1;
+    const int g = blockIdx.y;
+    const int N = npoint * nsample;
+    const int n0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < C1; k += blockDim.x) wx[k] = __ldg(w1x + k);
+    // stage: warp w loads rows w, w + 8, ...; a row of C1 floats = C1 / 4 16-byte pieces
+    const int pieces = C1 >> 2;
+    for (int r = warp; r < 32; r += 8) {
+        const int n = n0 + r;
+        if (n >= N) break;
+        const int pi = __ldg(idx + (size_t)g * N + n);
+        const float4 *src = reinterpret_cast<const float4 *>(z + ((size_t)g * n_pts + pi) * C1);
+        for (int c = lane; c < pieces; c += 32) {
+            const float4 v = __ldg(src + c);
+            float *dst = rows + r * pitch + c * 4;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+    }
+    // this lane's column: relative coordinates (pointnet2_utils.py:252)
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    const int n = n0 + lane;
+    if (n < N) {
+        const int pi = __ldg(idx + (size_t)g * N + n);
+        const float *pt = xyz + ((size_t)g * n_pts + pi) * 3;
+        const float *cen = centres + ((size_t)g * npoint + n / nsample) * 3;
+        dx = __fsub_rn(__ldg(pt), __ldg(cen));
+        dy = __fsub_rn(__ldg(pt + 1), __ldg(cen + 1));
+        dz = __fsub_rn(__ldg(pt + 2), __ldg(cen + 2));
+    }
+    __syncthreads();
+    if (n < N) {
+        float *o = out + (size_t)g * C1 * N + n;
+        for (int k = warp; k < C1; k += 8) {
+            const float4 w = wx[k];
+            const float base = z ? rows[lane * pitch + k] : w.w;
+            o[(size_t)k * N] = fmaxf(fmaf(w.x, dx, fmaf(w.y, dy, fmaf(w.z, dz, base))), 0.f);
+        }
+    }
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_sa_first_layer(const float *z, const float *w1x, int C1, int G, int npoint, int nsample, int n_pts,
+                                  const int *idx, const float *xyz, const float *centres, float *out, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(G >= 0 && C1 > 0 && npoint > 0 && nsample > 0 && n_pts > 0, "sa_first_layer: bad sizes");
+    if (G == 0) return JMB_OK;
+    JMB_REQUIRE(z && w1x && idx && xyz && centres && out, "sa_first_layer: null pointer");
+    JMB_REQUIRE(C1 % 4 == 0 && C1 <= 1024, "sa_first_layer: width %d must be a multiple of 4, <= 1024", C1);
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w1x) & 15u) == 0,
+                "sa_first_layer: z and w1x must be 16-byte aligned");
+    JMB_REQUIRE(G <= 65535, "sa_first_layer: too many groups");
+    const long long N = (long long)npoint * nsample;
+    JMB_REQUIRE(N < (1LL << 31), "sa_first_layer: too many columns");
+    const size_t smem = ((size_t)32 * (C1 + 1) + 4) * sizeof(float) + (size_t)C1 * sizeof(float4);
+    if (smem > 48 * 1024)
+        JMB_CUDA(cudaFuncSetAttribute(sa_first_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)G);
+    sa_first_layer_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(C1, npoint, nsample, n_pts, z,
+                                                                    reinterpret_cast<const float4 *>(w1x), idx, xyz,
+                                                                    centres, out);
+    return check_launch("sa_first_layer");
+}

@@ -134,8 +134,14 @@ class _PointnetSAModuleBase(nn.Module):
                 pool = grouper.nsample
                 if one_kernel[gi]:
                     return tc.sa_fused(layers, xyz, features, idx, new_xyz)   # first-layer GEMM over the points + one kernel
-                h = tc.grouped_first_layer(layers[0], xyz, features, idx, new_xyz, grouper.nsample,
-                                           pool=pool if len(layers) == 1 else 0)
+                l0 = layers[0]
+                if (features is not None and len(layers) > 1 and l0.relu and l0._w32 is not None and l0.M % 4 == 0
+                        and idx.shape[1] * idx.shape[2] > xyz.shape[1]):
+                    # wide levels: the first layer over the POINTS, then the per-neighbour finish (tc.hoisted_first_layer)
+                    h = tc.hoisted_first_layer(l0, xyz, features, idx, new_xyz)
+                else:
+                    h = tc.grouped_first_layer(l0, xyz, features, idx, new_xyz, grouper.nsample,
+                                               pool=pool if len(layers) == 1 else 0)
             else:  # GroupAll
                 pool = xyz.shape[1]
                 assert pool <= 128 and 128 % pool == 0, "GroupAll fused path: point count must divide 128"

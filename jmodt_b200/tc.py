@@ -149,6 +149,30 @@ def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tens
     return y
 
 
+def hoisted_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tensor, idx: torch.Tensor,
+                        centres: torch.Tensor) -> torch.Tensor:
+    """First SharedMLP layer of a set-abstraction scale, applied BEFORE the gather (it is linear up to its ReLU and
+    grouping only selects columns): Z = W1[:, 3:] . feats + b1 over the n_pts POINTS (tc_gemm_kernel), then
+    csrc/interpolate.cu:sa_first_layer_kernel emits relu(Z[idx] + W1[:, :3] . (xyz[idx] - centre)) for every grouped
+    neighbour.  xyz (G, n_pts, 3), feats (G, C, n_pts), idx (G, npoint, nsample), centres (G, npoint, 3) ->
+    (G, C1, npoint * nsample), what `grouped_first_layer` computes with a gathered GEMM over all npoint * nsample columns."""
+    G, n_pts, _ = xyz.shape
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    cache = getattr(layer, "_hoist", None)
+    if cache is None:
+        w1 = layer._w32
+        cache = layer._hoist = (PackedLayer(w1[:, 3:].contiguous(), layer.bias[: layer.M], relu=False),
+                                torch.cat((w1[:, :3], layer.bias[: layer.M, None]), dim=1).contiguous())
+    w1f, w1x = cache
+    z = mlp_layer(w1f, feats.contiguous(), point_major_out=True)               # (G, n_pts, C1)
+    out = torch.empty((G, layer.M, npoint * nsample), dtype=torch.float32, device=xyz.device)
+    st = _lib.stream_and_device(xyz)
+    _lib.check(_lib.lib().jmb_sa_first_layer(z.data_ptr(), w1x.data_ptr(), layer.M, G, npoint, nsample, n_pts,
+                                             idx.data_ptr(), xyz.data_ptr(), centres.contiguous().data_ptr(),
+                                             out.data_ptr(), st), "sa_first_layer")
+    return out
+
+
 def sa_fused_supported(layers, n_feat_channels: int, npoint: int, nsample: int) -> bool:
     """Shapes the single-kernel set-abstraction path handles (see csrc/sa_fused.cu): three ReLU layers of widths
     C1, C2 <= 128 (C1 a multiple of 8) and C3 <= 256 (narrower layers run zero-padded to the 128-row MMA tile); any

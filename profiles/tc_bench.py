@@ -31,6 +31,7 @@ SHAPES = [
     ("dense", 256, 256, 1024, 32, 0), ("pool", 512, 256, 1024, 32, 32),
     ("dense", 512, 512, 1, 1024, 0), ("dense", 512, 512, 4, 16384, 0), ("dense", 1, 512, 4, 16384, 0),
     ("dense", 512, 512, 4, 128, 0),
+    ("pm", 128, 128, 1024, 512, 0), ("pm", 128, 128, 1024, 128, 0), ("pm", 64, 96, 8, 4096, 0),     # first-layer GEMMs over the points (sa_fused Z)
 ]
 
 

@@ -282,3 +282,24 @@ def test_fp_module_interpolating_after_the_first_layer_is_equivalent(cuda):
     assert a2.shape == want2.shape == (2, 256, 4096)
     assert _rel(a2.cpu().numpy(), want2.cpu().numpy()) < 1e-4 and _rel(b2.cpu().numpy(), want2.cpu().numpy()) < 1e-4
     assert _rel(a2.cpu().numpy(), b2.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.gpu
+def test_wide_sa_level_first_layer_applied_before_the_gather(cuda):
+    """RPN level 2 / 3 shapes (widths beyond the one-kernel path): the first SharedMLP layer runs over the POINTS and
+    csrc/interpolate.cu:sa_first_layer_kernel finishes it per grouped neighbour — vs the reference composition
+    ball_query -> group -> SharedMLP (cuDNN fp32) -> max_pool of the same module."""
+    from jmodt_b200.pointnet2.pointnet2_modules import PointnetSAModuleMSG
+    from jmodt_b200.synth import fill_deterministic, make_batch
+    pts = torch.from_numpy(make_batch(21, 2, with_image=False)["pts"][:, :1024]).to(cuda).contiguous()
+    for c_in, npoint, mlps in ((256, 256, [[256, 128, 196, 256], [256, 128, 196, 256]]),
+                               (512, 64, [[512, 256, 256, 512], [512, 256, 384, 512]])):
+        feats = torch.randn(2, c_in, 1024, device=cuda)
+        sa = fill_deterministic(PointnetSAModuleMSG(npoint=npoint, radii=[1.0, 2.0], nsamples=[16, 32], mlps=mlps,
+                                                    bn=True)).to(cuda).eval()
+        with torch.no_grad():
+            new_xyz, fused, idx = sa(pts, feats)
+            sa.fused = False
+            new_xyz2, unfused, idx2 = sa(pts, feats)
+        assert torch.equal(idx, idx2) and fused.shape == unfused.shape
+        assert _rel(fused.cpu().numpy(), unfused.cpu().numpy()) < 1e-4
