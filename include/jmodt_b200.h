@@ -225,6 +225,16 @@ JMB_API int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const
                          const int *idx, const float *xyz, const float *centres, float *out, int out_point_major,
                          void *stream);
 
+/* Deterministic accumulation for the three backward ops (the reference uses float atomicAdd: group_points_gpu.cu:8-25,
+ * sampling_gpu.cu:46-63, interpolate_gpu.cu:120-142, so its gradients differ in the last bits from run to run).
+ * order (B, Lq): positions of the batch-local flat index list sorted (stably) by target; seg_off (B, n_tgt+1): start of each
+ * target's run; out[b][c][t] = sum over the run, in order, of src[b][c][q / rep] * (weight ? weight[b][q] : 1).
+ * group_points_grad: Lq = npoint*nsample, rep 1; gather_points_grad: Lq = npoint, rep 1; three_interpolate_grad: Lq = 3n,
+ * rep 3, weight = the interpolation weights.  out is fully written. */
+JMB_API int jmb_segmented_scatter_add(int B, int C, int L_src, int Lq, int n_tgt, int rep, const float *src,
+                                      const int *order, const int *seg_off, const float *weight, float *out,
+                                      void *stream);
+
 /* First SharedMLP layer of a set-abstraction level applied before the gather, for the layer-by-layer path (levels whose
  * later layers are too wide for jmb_sa_fused): out (G, C1, npoint*nsample) channel-first
  *   = relu(z[idx] + W1x . (xyz[idx] - centre)),  z (G, n_pts, C1) point-major = W1[:, 3:] . features + b1 (a dense layer over

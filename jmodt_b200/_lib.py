@@ -49,6 +49,7 @@ SIGNATURES = {
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_pts_in_boxes3d_host": [_i, _i, _vp, _vp, _vp],
     "jmb_roipool3d_host": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "jmb_segmented_scatter_add": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_sa_first_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],

@@ -363,3 +363,52 @@ extern "C" int jmb_sa_first_layer(const float *z, const float *w1x, int C1, int 
                                                                     centres, out);
     return check_launch("sa_first_layer");
 }
+
+// ---- deterministic scatter-add for the three backward ops ---------------------------------------------------------
+// The reference accumulates its gradients with float atomicAdd (group_points_gpu.cu:8-25, sampling_gpu.cu:46-63,
+// interpolate_gpu.cu:120-142): the summation order, and with it the last bits of the result, change from run to run.
+// Here the contributions to every target are summed in a FIXED order.  The caller sorts the (batch-local) flat index
+// list once (stable sort: positions of equal targets stay ascending) and passes
+//     order   (B, Lq)          positions q of the flat index list, sorted by target
+//     seg_off (B, n_tgt + 1)   start of every target's run in `order`
+// contribution of position q: src[b][c][q / rep] * (weight ? weight[b][q] : 1)
+//     group_points_grad        Lq = npoint * nsample, rep = 1
+//     gather_points_grad       Lq = npoint,           rep = 1
+//     three_interpolate_grad   Lq = 3 n,              rep = 3, weight = interpolation weights
+namespace jmb {
+
+__global__ void __launch_bounds__(128)
+segmented_scatter_kernel(int C, int L_src, int Lq, int n_tgt, int rep, const float *__restrict__ src,
+                         const int *__restrict__ order, const int *__restrict__ seg_off,
+                         const float *__restrict__ weight, float *__restrict__ out) {
+    const int b = blockIdx.z, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tgt) return;
+    const int q0 = __ldg(seg_off + (size_t)b * (n_tgt + 1) + t), q1 = __ldg(seg_off + (size_t)b * (n_tgt + 1) + t + 1);
+    const int *ord = order + (size_t)b * Lq;
+    const float *w = weight ? weight + (size_t)b * Lq : nullptr;
+    for (int c = blockIdx.y; c < C; c += gridDim.y) {
+        const float *s = src + ((size_t)b * C + c) * L_src;
+        float acc = 0.f;
+        for (int q = q0; q < q1; ++q) {
+            const int pos = __ldg(ord + q);
+            const float v = __ldg(s + pos / rep);
+            acc = __fadd_rn(acc, w ? __fmul_rn(v, __ldg(w + pos)) : v);     // product rounded, then added: the reference's atomicAdd(p, g * w)
+        }
+        out[((size_t)b * C + c) * n_tgt + t] = acc;
+    }
+}
+
+}  // namespace jmb
+
+extern "C" int jmb_segmented_scatter_add(int B, int C, int L_src, int Lq, int n_tgt, int rep, const float *src,
+                                         const int *order, const int *seg_off, const float *weight, float *out,
+                                         void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(B >= 0 && C >= 0 && L_src >= 0 && Lq >= 0 && n_tgt >= 0 && rep >= 1, "segmented_scatter_add: bad sizes");
+    if (B == 0 || C == 0 || n_tgt == 0) return JMB_OK;
+    JMB_REQUIRE(src && order && seg_off && out, "segmented_scatter_add: null pointer");
+    JMB_REQUIRE(B <= 65535, "segmented_scatter_add: batch too large");
+    dim3 grid(div_up(n_tgt, 128), C < 64 ? C : 64, B);
+    segmented_scatter_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(C, L_src, Lq, n_tgt, rep, src, order, seg_off, weight, out);
+    return check_launch("segmented_scatter_add");
+}

@@ -14,6 +14,30 @@ import torch
 import torch.nn as nn
 from torch.autograd import Function
 
+from .. import _lib
+
+
+def _scatter_add_sorted(src: torch.Tensor, idx_flat: torch.Tensor, n_targets: int, rep: int = 1,
+                        weight: torch.Tensor = None) -> torch.Tensor:
+    """out[b, c, t] = sum over the positions q with idx_flat[b, q] == t, in ascending q, of
+    src[b, c, q // rep] * (weight[b, q] if weight is given).  The backward of gather / grouping / interpolation with a
+    FIXED summation order (the reference's atomicAdd kernels are order-nondeterministic): the index list is sorted
+    once (stable), the runs are summed sequentially by csrc/interpolate.cu:segmented_scatter_kernel."""
+    B, C, L_src = src.shape
+    Lq = idx_flat.shape[1]
+    sorted_idx, order = torch.sort(idx_flat.long(), dim=1, stable=True)
+    bounds = torch.arange(n_targets + 1, device=src.device, dtype=torch.long).unsqueeze(0).expand(B, -1).contiguous()
+    seg_off = torch.searchsorted(sorted_idx.contiguous(), bounds).to(torch.int32).contiguous()
+    order = order.to(torch.int32).contiguous()
+    out = torch.empty((B, C, n_targets), dtype=torch.float32, device=src.device)
+    src = src.contiguous()
+    w = None if weight is None else weight.reshape(B, Lq).contiguous()
+    st = _lib.stream_and_device(src)
+    _lib.check(_lib.lib().jmb_segmented_scatter_add(B, C, L_src, Lq, n_targets, rep, src.data_ptr(), order.data_ptr(),
+                                                    seg_off.data_ptr(), _lib.ptr(w), out.data_ptr(), st),
+               "segmented_scatter_add")
+    return out
+
 from . import pointnet2_cuda
 
 
@@ -60,8 +84,7 @@ class GatherOperation(Function):
     def backward(ctx, grad_out):
         idx, C, N = ctx.for_backwards
         B, npoint = idx.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2_cuda.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
+        grad_features = _scatter_add_sorted(grad_out, idx.view(B, npoint), N)      # fixed summation order
         return grad_features, None
 
 
@@ -110,9 +133,7 @@ class ThreeInterpolate(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, weight, m = ctx.three_interpolate_for_backward
         B, c, n = grad_out.size()
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-        pointnet2_cuda.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight,
-                                                      grad_features)
+        grad_features = _scatter_add_sorted(grad_out, idx.view(B, n * 3), m, rep=3, weight=weight)   # fixed summation order
         return grad_features, None, None
 
 
@@ -137,9 +158,7 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2_cuda.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx,
-                                                 grad_features)
+        grad_features = _scatter_add_sorted(grad_out.reshape(B, C, npoint * nsample), idx.view(B, npoint * nsample), N)
         return grad_features, None
 
 
