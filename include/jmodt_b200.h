@@ -66,6 +66,15 @@ JMB_API int jmb_ball_query(int b, int n, int m, float radius, int nsample, const
 JMB_API int jmb_ball_query_msg2(int b, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
                                 const float *new_xyz, const float *xyz, int *idx_a, int *idx_b, void *stream);
 
+/* Same contract through a hashed cell list built per call (for large clouds and radii small against their extent, e.g.
+ * RPN level 0): a centre visits the 27 neighbouring cells instead of the whole cloud; hits are put in ascending index
+ * order before they are written, so the result is IDENTICAL to jmb_ball_query / jmb_ball_query_msg2.  radius_b /
+ * nsample_b / idx_b may be 0 / 0 / NULL.  workspace: jmb_ball_query_grid_workspace_bytes(b, n) bytes of device memory. */
+JMB_API size_t jmb_ball_query_grid_workspace_bytes(int b, int n);
+JMB_API int jmb_ball_query_msg2_grid(int b, int n, int m, float radius_a, int nsample_a, float radius_b, int nsample_b,
+                                     const float *new_xyz, const float *xyz, int *idx_a, int *idx_b, void *workspace,
+                                     size_t workspace_bytes, void *stream);
+
 /* replaces group_points_wrapper_fast (group_points.cpp:24-35) -> group_points_gpu.cu:47-86.
  * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
 JMB_API int jmb_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
@@ -224,6 +233,12 @@ JMB_API int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const
                          const float *b3, int C1, int C2, int C3, int G, int npoint, int nsample, int n_pts,
                          const int *idx, const float *xyz, const float *centres, float *out, int out_point_major,
                          void *stream);
+
+/* LI-Fusion attention weight (reference backbone.py:33-58, IALayer: three Linear layers, tanh, sigmoid) as one fp32 kernel:
+ * att[b,n] = sigmoid(w3 . tanh(W1 . img[b,:,n] + W2 . pt[b,:,n] + b12) + b3).  img (B, ic, N), pt (B, pc, N) channel-first;
+ * w12 (rc, ic+pc) = [W1 | W2] row-major, b12 (rc) = b1 + b2, w3 (rc); rc <= 256.  att (B, N). */
+JMB_API int jmb_ia_attention(int B, int ic, int pc, int rc, int N, const float *img, const float *pt, const float *w12,
+                             const float *b12, const float *w3, float b3, float *att, void *stream);
 
 /* Deterministic accumulation for the three backward ops (the reference uses float atomicAdd: group_points_gpu.cu:8-25,
  * sampling_gpu.cu:46-63, interpolate_gpu.cu:120-142, so its gradients differ in the last bits from run to run).

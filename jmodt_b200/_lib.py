@@ -25,6 +25,8 @@ SIGNATURES = {
     "jmb_sm_count": [],
     "jmb_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
     "jmb_ball_query_msg2": [_i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp],
+    "jmb_ball_query_grid_workspace_bytes": [_i, _i],
+    "jmb_ball_query_msg2_grid": [_i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "jmb_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -49,6 +51,7 @@ SIGNATURES = {
     "jmb_nms_normal": [_i, _vp, _f, _vp, _vp, _i, _vp, _sz, _vp],
     "jmb_pts_in_boxes3d_host": [_i, _i, _vp, _vp, _vp],
     "jmb_roipool3d_host": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "jmb_ia_attention": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "jmb_segmented_scatter_add": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_sa_first_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "jmb_sa_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -57,7 +60,8 @@ SIGNATURES = {
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _vp],
 }
-_RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz, "jmb_proposal_workspace_bytes": _sz}
+_RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz, "jmb_proposal_workspace_bytes": _sz,
+             "jmb_ball_query_grid_workspace_bytes": _sz}
 
 
 class JmodtB200Error(RuntimeError):

@@ -25,7 +25,11 @@ struct ProposalWs {
     int *nkeep;                   // [sets]
 };
 
-__global__ void __launch_bounds__(256)
+// 1 024 threads: every iteration of the ordered compaction is two dependent L2 round trips (sorted index, then the box's
+// depth), so the scan of 16 384 scored boxes is latency-bound — 16 iterations instead of 64 (104 -> ~30 us per batch).
+constexpr int PS_THREADS = 1024, PS_WARPS = PS_THREADS / 32;
+
+__global__ void __launch_bounds__(PS_THREADS)
 proposal_select_kernel(ProposalParams p, const float *__restrict__ proposals, const long long *__restrict__ order,
                        ProposalWs ws) {
     const int bin = blockIdx.x, b = blockIdx.y, set = b * 2 + bin;
@@ -33,7 +37,7 @@ proposal_select_kernel(ProposalParams p, const float *__restrict__ proposals, co
     const long long *ord = order + (size_t)b * p.N;
     int *sel_idx = ws.sel_idx + (size_t)set * p.max_pre;
     float *sel_bev = ws.sel_bev + (size_t)set * p.max_pre * 5;
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[PS_WARPS];
     __shared__ int s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -44,7 +48,7 @@ proposal_select_kernel(ProposalParams p, const float *__restrict__ proposals, co
         const int skip = pass == 0 ? 0 : p.pre[0];
         const int want = p.pre[bin];
         int seen = 0;  // matches so far (block-uniform)
-        for (int i0 = 0; i0 < p.N && seen < skip + want; i0 += 256) {
+        for (int i0 = 0; i0 < p.N && seen < skip + want; i0 += PS_THREADS) {
             const int i = i0 + threadIdx.x;
             bool hit = false;
             int e = 0;
@@ -58,7 +62,7 @@ proposal_select_kernel(ProposalParams p, const float *__restrict__ proposals, co
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < PS_WARPS; ++w) {
                 if (w < warp) before += s_warp[w];
                 total += s_warp[w];
             }
@@ -234,7 +238,7 @@ extern "C" int jmb_proposal_layer(int B, int N, const float *proposals, const fl
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)p.max_post * 5 * sizeof(float);
     JMB_REQUIRE(smem <= 40 * 1024, "proposal_layer: post_nms_top_n too large");
-    proposal_select_kernel<<<dim3(2, B), 256, 0, st>>>(p, proposals, order, ws);
+    proposal_select_kernel<<<dim3(2, B), PS_THREADS, 0, st>>>(p, proposals, order, ws);
     int rc = check_launch("proposal_layer(select)");
     if (rc != JMB_OK) return rc;
     if (rotated) nms_greedy_batched_kernel<true><<<B * 2, 256, smem, st>>>(p, nms_thresh, ws);

@@ -115,13 +115,33 @@ class IALayer(nn.Module):
         return {"conv1": tc.PackedLayer(w, b, True),
                 "fc1": tc.PackedLayer(self.fc1.weight, self.fc1.bias, False),
                 "fc2": tc.PackedLayer(self.fc2.weight, self.fc2.bias, False),
-                "fc3": tc.PackedLayer(self.fc3.weight, self.fc3.bias, False)}
+                "fc3": tc.PackedLayer(self.fc3.weight, self.fc3.bias, False),
+                # the attention weight's three Linear layers as one fp32 kernel (csrc/feature_gather.cu:ia_attention_kernel)
+                "w12": torch.cat((self.fc1.weight, self.fc2.weight), dim=1).detach().float().contiguous(),
+                "b12": (self.fc1.bias + self.fc2.bias).detach().float().contiguous(),
+                "w3": self.fc3.weight.detach().float().reshape(-1).contiguous(),
+                "b3": float(self.fc3.bias.detach().float().item())}
 
     @torch.no_grad()
     def forward(self, img_feas, point_feas):
         P = tc.packed_for(self, self.pack)
         img_feas, point_feas = img_feas.contiguous(), point_feas.contiguous()
-        # three independent projections of the inputs: forked streams (runtime.parallel)
+        B, ic, N = img_feas.shape
+        pc = point_feas.shape[1]
+
+        def attention():
+            att = torch.empty((B, 1, N), dtype=torch.float32, device=img_feas.device)
+            st = _lib.stream_and_device(img_feas)
+            _lib.check(_lib.lib().jmb_ia_attention(B, ic, pc, P["w3"].numel(), N, img_feas.data_ptr(), point_feas.data_ptr(),
+                                                   P["w12"].data_ptr(), P["b12"].data_ptr(), P["w3"].data_ptr(), P["b3"],
+                                                   att.data_ptr(), st), "ia_attention")
+            return att
+        if B * N >= 8192 and P["w3"].numel() <= 64:
+            # many points, few reduced channels (levels 0, 1 and the final fusion): the attention weight as ONE fp32 SIMT
+            # kernel next to the image projection, on forked streams (runtime.parallel)
+            att, conv = runtime.parallel(attention, lambda: tc.mlp_layer(P["conv1"], img_feas))
+            return conv * att
+        # few points, wide layers (levels 2, 3): three independent projections on the tensor cores
         ri, rp, conv = runtime.parallel(lambda: tc.mlp_layer(P["fc1"], img_feas),      # (B, rc, N)
                                         lambda: tc.mlp_layer(P["fc2"], point_feas),
                                         lambda: tc.mlp_layer(P["conv1"], img_feas))

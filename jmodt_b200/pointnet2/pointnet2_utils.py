@@ -198,10 +198,23 @@ def ball_query_msg2(radius_a: float, nsample_a: int, radius_b: float, nsample_b:
     idx_a = _new(xyz, (B, npoint, nsample_a), torch.int32)
     idx_b = _new(xyz, (B, npoint, nsample_b), torch.int32)
     st = _lib.stream_and_device(xyz)
-    _lib.check(_lib.lib().jmb_ball_query_msg2(B, N, npoint, radius_a, nsample_a, radius_b, nsample_b,
-                                              new_xyz.data_ptr(), xyz.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr(),
-                                              st), "ball_query_msg2")
+    L = _lib.lib()
+    if N >= GRID_MIN_POINTS:
+        # large cloud: hashed cell list, a centre visits 27 cells instead of all N points (identical result)
+        ws_bytes = L.jmb_ball_query_grid_workspace_bytes(B, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+        _lib.check(L.jmb_ball_query_msg2_grid(B, N, npoint, radius_a, nsample_a, radius_b, nsample_b, new_xyz.data_ptr(),
+                                              xyz.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr(), ws.data_ptr(), ws_bytes,
+                                              st), "ball_query_msg2_grid")
+        _lib.launch_count += 1
+        return idx_a, idx_b
+    _lib.check(L.jmb_ball_query_msg2(B, N, npoint, radius_a, nsample_a, radius_b, nsample_b,
+                                     new_xyz.data_ptr(), xyz.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr(),
+                                     st), "ball_query_msg2")
     return idx_a, idx_b
+
+
+GRID_MIN_POINTS = 8192      # clouds at least this large go through the cell-list ball query (RPN level 0)
 
 
 class QueryAndGroup(nn.Module):

@@ -428,3 +428,31 @@ def test_ball_query_msg2_equals_two_queries(cuda, cref):
         ia, ib = pu.ball_query_msg2(ra, na, rb, nb, T(xyz, cuda), T(new_xyz, cuda))
         np.testing.assert_array_equal(ia.cpu().numpy(), cref.ball_query(ra, na, xyz, new_xyz))
         np.testing.assert_array_equal(ib.cpu().numpy(), cref.ball_query(rb, nb, xyz, new_xyz))
+
+
+def test_ball_query_cell_list_equals_oracle_and_reference_cuda(cuda, cref, ref_ext):
+    """Large clouds go through the hashed cell list (csrc/ball_query.cu: ball_query_grid_kernel): identical rows to the
+    oracle / the reference kernel on (i) a KITTI-shaped synthetic frame at the RPN level-0 shape, (ii) a cloud so dense that
+    balls hold more than the 256 buffered hits (ordered-scan fallback), (iii) negative coordinates and far-away centres
+    without any hit."""
+    from jmodt_b200 import synth
+    from jmodt_b200.pointnet2 import pointnet2_utils as pu
+    rng = np.random.default_rng(5)
+    batch = synth.make_batch(31, 2, with_image=False)["pts"]
+    cases = [(batch, 4096, 0.1, 16, 0.5, 32),
+             ((rng.normal(0, 0.35, (1, 8192, 3))).astype(np.float32), 512, 0.3, 16, 0.6, 32),
+             ((rng.uniform(-30, 30, (2, 9000, 3))).astype(np.float32), 300, 1.0, 8, 2.5, 64)]
+    for xyz, m, ra, na, rb, nb in cases:
+        b, n, _ = xyz.shape
+        new_xyz = np.ascontiguousarray(xyz[:, rng.permutation(n)[:m]])
+        new_xyz[:, -1] += 500.0                                # a centre with no neighbour at all
+        x, c = T(xyz, cuda), T(new_xyz, cuda)
+        ia, ib = pu.ball_query_msg2(ra, na, rb, nb, x, c)
+        np.testing.assert_array_equal(ia.cpu().numpy(), cref.ball_query(ra, na, xyz, new_xyz))
+        np.testing.assert_array_equal(ib.cpu().numpy(), cref.ball_query(rb, nb, xyz, new_xyz))
+        for r, ns, got in ((ra, na, ia), (rb, nb, ib)):
+            ref = torch.zeros(b, m, ns, dtype=torch.int32, device=cuda)
+            ref_ext.pointnet2_cuda.ball_query_wrapper(b, n, m, r, ns, c, x, ref)
+            assert torch.equal(got, ref)
+    dense_hits = (np.linalg.norm(cases[1][0][0][None] - cases[1][0][0][:64, None], axis=2) < 0.6).sum(1)
+    assert dense_hits.max() > 256                              # the fallback path was exercised
