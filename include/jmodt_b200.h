@@ -112,6 +112,7 @@ JMB_API int jmb_wait_indices(const int *idx, int b, int row_stride, int k0, int 
 JMB_API int jmb_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                  int *idx, void *stream);
 
+
 /* replaces three_interpolate_wrapper_fast (interpolate.cpp:28-40) -> interpolate_gpu.cu:77-117. */
 JMB_API int jmb_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
                           const float *weight, float *out, void *stream);

@@ -152,6 +152,7 @@ static int launch_ball_query(int b, int n, int m, const BallQueryScales &sc, con
 constexpr int BG_BUCKETS = 16384;          // per frame (power of two)
 constexpr int BG_CAP = 256;                // hits buffered per (centre, radius)
 constexpr int BG_WARPS = 8;
+constexpr int BG_START_PITCH = (BG_BUCKETS + 4) & ~3;   // ints per frame of the bucket-start table (16-byte multiple)
 
 __device__ __forceinline__ unsigned bg_hash(int cx, int cy, int cz) {
     return ((unsigned)cx * 73856093u ^ (unsigned)cy * 19349663u ^ (unsigned)cz * 83492791u) & (BG_BUCKETS - 1);
@@ -160,13 +161,13 @@ __device__ __forceinline__ int bg_cell(float v, float inv_cs) { return (int)floo
 
 // one CTA per frame: histogram -> exclusive scan -> scatter (order inside a bucket is arbitrary: hits are sorted later)
 __global__ void __launch_bounds__(1024)
-bq_build_grid_kernel(int n, float inv_cs, const float *__restrict__ xyz, int *__restrict__ start, int *__restrict__ list) {
+bq_build_grid_kernel(int n, float inv_cs, const float *__restrict__ xyz, int *__restrict__ start, float4 *__restrict__ list) {
     extern __shared__ int bg_hist[];            // [BG_BUCKETS]
     __shared__ int s_warp_sum[32];
     const int b = blockIdx.x;
     const float *pts = xyz + (size_t)b * n * 3;
-    int *st = start + (size_t)b * (BG_BUCKETS + 1);
-    int *ls = list + (size_t)b * n;
+    int *st = start + (size_t)b * BG_START_PITCH;
+    float4 *ls = list + (size_t)b * n;       // bucket-ordered copies (x, y, z, index): a candidate is ONE 16-byte load
     for (int i = threadIdx.x; i < BG_BUCKETS; i += 1024) bg_hist[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += 1024)
@@ -207,16 +208,16 @@ bq_build_grid_kernel(int n, float inv_cs, const float *__restrict__ xyz, int *__
     if (threadIdx.x == 1023) st[BG_BUCKETS] = run;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += 1024) {
-        const int pos = atomicAdd(&bg_hist[bg_hash(bg_cell(__ldg(pts + 3 * i), inv_cs), bg_cell(__ldg(pts + 3 * i + 1), inv_cs),
-                                                   bg_cell(__ldg(pts + 3 * i + 2), inv_cs))], 1);
-        ls[pos] = i;
+        const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+        const int pos = atomicAdd(&bg_hist[bg_hash(bg_cell(x, inv_cs), bg_cell(y, inv_cs), bg_cell(z, inv_cs))], 1);
+        ls[pos] = make_float4(x, y, z, __int_as_float(i));
     }
 }
 
 template <int NR>
 __global__ void __launch_bounds__(BG_WARPS * 32)
 ball_query_grid_kernel(int n, int m, float inv_cs, BallQueryScales sc, const float *__restrict__ new_xyz,
-                       const float *__restrict__ xyz, const int *__restrict__ start, const int *__restrict__ list) {
+                       const float *__restrict__ xyz, const int *__restrict__ start, const float4 *__restrict__ list) {
     __shared__ int s_hits[BG_WARPS][NR][BG_CAP];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5;
@@ -225,8 +226,8 @@ ball_query_grid_kernel(int n, int m, float inv_cs, BallQueryScales sc, const flo
     const int c = blockIdx.x * BG_WARPS + warp;
     if (c >= m) return;                                   // whole warp
     const float *pts = xyz + (size_t)b * n * 3;
-    const int *st = start + (size_t)b * (BG_BUCKETS + 1);
-    const int *ls = list + (size_t)b * n;
+    const int *st = start + (size_t)b * BG_START_PITCH;
+    const float4 *ls = list + (size_t)b * n;
     const float *cp = new_xyz + ((size_t)b * m + c) * 3;
     const float cx = __ldg(cp), cy = __ldg(cp + 1), cz = __ldg(cp + 2);
     // the 27 neighbouring cells -> distinct buckets (hash collisions among them are visited once)
@@ -248,9 +249,9 @@ ball_query_grid_kernel(int n, int m, float inv_cs, BallQueryScales sc, const flo
             int k = 0;
             float d2 = 3.0e38f;
             if (valid) {
-                k = __ldg(ls + q + lane);
-                const float *p = pts + (size_t)k * 3;
-                d2 = dist2_ref(cx - __ldg(p), cy - __ldg(p + 1), cz - __ldg(p + 2));
+                const float4 e = __ldg(ls + q + lane);
+                k = __float_as_int(e.w);
+                d2 = dist2_ref(cx - e.x, cy - e.y, cz - e.z);
             }
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
@@ -305,6 +306,7 @@ ball_query_grid_kernel(int n, int m, float inv_cs, BallQueryScales sc, const flo
     }
 }
 
+
 }  // namespace jmb
 
 extern "C" int jmb_ball_query(int b, int n, int m, float radius, int nsample,
@@ -336,7 +338,8 @@ extern "C" int jmb_ball_query_msg2(int b, int n, int m, float radius_a, int nsam
 
 extern "C" size_t jmb_ball_query_grid_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 0;
-    return (size_t)b * ((size_t)jmb::BG_BUCKETS + 1 + (size_t)n) * sizeof(int);
+    // per frame: bucket starts (BG_BUCKETS + 1 ints, padded to 16 bytes) + one float4 per point
+    return (size_t)b * ((((size_t)jmb::BG_BUCKETS + 4) & ~(size_t)3) * sizeof(int) + (size_t)n * sizeof(float4));
 }
 
 // Same contract as jmb_ball_query_msg2 (radius_b / nsample_b / idx_b may be 0 / 0 / NULL for a single radius), through a
@@ -359,8 +362,9 @@ extern "C" int jmb_ball_query_msg2_grid(int b, int n, int m, float radius_a, int
     JMB_REQUIRE(rmax > 0.f, "ball_query_grid: radius must be positive");
     const float inv_cs = 1.0f / (rmax * 1.001f);       // cell a little larger than the largest radius: rounding of v * inv_cs
                                                        // can then never put two points within the radius two cells apart
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "ball_query_grid: workspace must be 16-byte aligned");
     int *start = static_cast<int *>(workspace);
-    int *list = start + (size_t)b * (BG_BUCKETS + 1);
+    float4 *list = reinterpret_cast<float4 *>(start + (size_t)b * BG_START_PITCH);
     cudaStream_t st = (cudaStream_t)stream;
     const int hist_bytes = BG_BUCKETS * (int)sizeof(int);
     {

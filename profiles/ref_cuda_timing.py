@@ -83,6 +83,19 @@ def main(out_path):
         out_r.zero_(); theirs()
         add("ball_query", f"B={B} N={n} m={m} r={r} ns={ns}", lambda: pu.ball_query(r, ns, src, ctr), theirs,
             bool(torch.equal(got, out_r)))
+    # both radii of RPN level 0 in one call (what PointnetSAModuleMSG issues): cell list here, two scans in the reference
+    src, ctr = lv[0], lv[1]
+    ra, na, rb, nb = 0.1, 16, 0.5, 32
+    oa = torch.zeros(B, 4096, na, dtype=torch.int32, device=dev)
+    ob = torch.zeros(B, 4096, nb, dtype=torch.int32, device=dev)
+
+    def both_ref():
+        ref.pointnet2_cuda.ball_query_wrapper(B, 16384, 4096, ra, na, ctr, src, oa)
+        ref.pointnet2_cuda.ball_query_wrapper(B, 16384, 4096, rb, nb, ctr, src, ob)
+    ga, gb = pu.ball_query_msg2(ra, na, rb, nb, src, ctr)
+    both_ref()
+    add("ball_query x2 radii", f"B={B} N=16384 m=4096 r=0.1/0.5 ns=16/32 (cell list)",
+        lambda: pu.ball_query_msg2(ra, na, rb, nb, src, ctr), both_ref, bool(torch.equal(ga, oa) and torch.equal(gb, ob)))
     G = 1024
     pooled_xyz = torch.rand(G, 512, 3, device=dev)
     fidx = pu.farthest_point_sample(pooled_xyz, 128)
