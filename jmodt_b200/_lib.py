@@ -58,10 +58,13 @@ SIGNATURES = {
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "jmb_feature_gather_nhwc": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "jmb_decode_workspace_bytes": [_i, _i],
+    "jmb_decode_gather": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "jmb_tc_mlp_layer": [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.c_longlong, _vp],
 }
 _RESTYPES = {"jmb_last_error": C.c_char_p, "jmb_nms_workspace_bytes": _sz, "jmb_proposal_workspace_bytes": _sz,
-             "jmb_ball_query_grid_workspace_bytes": _sz}
+             "jmb_ball_query_grid_workspace_bytes": _sz, "jmb_decode_workspace_bytes": C.c_longlong}
 
 
 class JmodtB200Error(RuntimeError):
@@ -107,7 +110,7 @@ launch_count = 0  # kernels enqueued through the C ABI (bench.py reports it as g
 
 def check(rc: int, what: str) -> None:
     global launch_count
-    launch_count += {"nms": 2, "proposal_layer": 3}.get(what, 1)   # nms = mask + sweep kernels, proposal = 3
+    launch_count += {"nms": 2, "proposal_layer": 3, "decode_gather": 5}.get(what, 1)   # nms = mask + sweep kernels, proposal = 3
     if rc != 0:
         msg = lib().jmb_last_error().decode(errors="replace")
         raise JmodtB200Error(f"{what} failed (code {rc}): {msg}")

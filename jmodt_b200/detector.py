@@ -68,12 +68,18 @@ class RpnConfig:
 
 
 def feature_gather(feature_map: torch.Tensor, xy: torch.Tensor) -> torch.Tensor:
-    """backbone.py:79-89 on the sm_100a kernel: feature_map (B,C,H,W), xy (B,N,2) in [-1,1] -> (B,C,N)."""
+    """backbone.py:79-89 on the sm_100a kernels: feature_map (B,C,H,W), xy (B,N,2) in [-1,1] -> (B,C,N).  A
+    channels-last map (what the image convolutions emit, `image_features(dense=False)`) is read as it lies."""
     B, C, H, W = feature_map.shape
     N = xy.shape[1]
-    fm, g = feature_map.float().contiguous(), xy.contiguous()
+    fm, g = feature_map.float(), xy.contiguous()
     out = torch.empty((B, C, N), dtype=torch.float32, device=fm.device)
     st = _lib.stream_and_device(fm)
+    if not fm.is_contiguous() and fm.is_contiguous(memory_format=torch.channels_last) and C % 2 == 0:
+        _lib.check(_lib.lib().jmb_feature_gather_nhwc(B, C, H, W, N, fm.data_ptr(), g.data_ptr(), out.data_ptr(), st),
+                   "feature_gather")
+        return out
+    fm = fm.contiguous()
     _lib.check(_lib.lib().jmb_feature_gather(B, C, H, W, N, fm.data_ptr(), g.data_ptr(), out.data_ptr(), st),
                "feature_gather")
     return out
@@ -234,16 +240,71 @@ class PointNet2MSG(nn.Module):
         return xyz, features
 
     @torch.no_grad()
-    def image_features(self, image):
-        """The cuDNN image stack: the four Img_Block maps and the fused de-convolved map
-        (backbone.py:170,187-193).  Out of the hot-path scope."""
+    def image_features(self, image, dense: bool = True):
+        """The image stack (backbone.py:170,187-193): the four Img_Block maps (3x3 convolutions: cuDNN) and, with
+        `dense`, the de-convolved + fused full-resolution map as the reference materialises it.  dense=False returns
+        `(channels-last maps, None)`: forward() then evaluates the decoder only at the sampled pixels (decode_gather)."""
         maps, x = [], image
+        if not dense:
+            x = x.contiguous(memory_format=torch.channels_last)
         for blk in self.Img_Block:
             x = blk(x)
             maps.append(x)
+        if not dense:
+            return maps, None
         de = torch.cat([dc(m) for dc, m in zip(self.DeConv, maps)], dim=1)
         fused = F.relu(self.image_fusion_bn(self.image_fusion_conv(de)))
         return maps, fused
+
+    def _decoder_pack(self):
+        """Weights of csrc/image_decode.cu: the DeConv slices of each of the 16 x 16 pixel phases in 32-channel chunks (hi / lo planes), and
+        image_fusion_conv with the BatchNorm (eval) affine and the DeConv biases folded in.  Rebuilt when the modules'
+        parameters change."""
+        mods = list(self.DeConv) + [self.image_fusion_conv, self.image_fusion_bn]
+        tok = tuple(t for m in mods for t in tc.weights_token(m))
+        d = self.__dict__
+        if d.get("_dec_pack") is None or d.get("_dec_token") != tok:
+            assert len(self.DeConv) == 4 and self.image_fusion_conv.out_channels == 32, \
+                "decode_gather is built for four decoder levels and 32 fused channels"
+            ph = torch.arange(16)
+            chunks, biases = [], []
+            for l, dc in enumerate(self.DeConv):
+                s = 2 << l
+                assert dc.kernel_size == (s, s) and dc.stride == (s, s) and dc.out_channels == 16 and \
+                    dc.in_channels % 64 == 0, "decode_gather needs kernel = stride = 2^(level+1), 16 outputs"
+                w = dc.weight.detach().float().permute(2, 3, 1, 0)            # (s, s, 16, C)
+                w = w[ph % s][:, ph % s]                                       # (16, 16, 16, C): phase (py, px)
+                C = w.shape[-1]
+                chunks.append(w.reshape(256, 16, C // 32, 32).permute(0, 2, 1, 3))
+                biases.append(dc.bias.detach().float() if dc.bias is not None else torch.zeros(16, device=w.device))
+            w1, b1 = tc.fold_conv_bn(self.image_fusion_conv, self.image_fusion_bn)
+            b1 = b1 + w1 @ torch.cat(biases)
+            w = torch.cat(chunks, dim=1).contiguous()                         # (256, chunks, 16, 32)
+            # the kernel multiplies on TF32 tensor-core instructions with an exact hi + lo split of both operands:
+            # hi = the 19 bits the hardware reads, lo = the rest (w = hi + lo exactly)
+            hi = (w.view(torch.int32) & -8192).view(torch.float32)
+            d["_dec_pack"] = (torch.stack([hi, w - hi], dim=2).contiguous(), w1.contiguous(), b1.contiguous())
+            d["_dec_token"] = tok
+        return d["_dec_pack"]
+
+    @torch.no_grad()
+    def decode_gather(self, maps, xy, image_hw=None):
+        """backbone.py:187-194 without the full-resolution maps: grid_sample(relu(bn(conv1x1(cat DeConv_i(maps_i)))), xy)
+        evaluated at the four bilinear taps of every point only.  maps: the four Img_Block outputs, xy (B,N,2)."""
+        wexp, w1, b1 = self._decoder_pack()
+        ms = [m.float().contiguous(memory_format=torch.channels_last) for m in maps]
+        B, N = xy.shape[0], xy.shape[1]
+        H, W = image_hw if image_hw is not None else (ms[0].shape[2] * 2, ms[0].shape[3] * 2)
+        for l, m in enumerate(ms):
+            assert m.shape[2] == H >> (l + 1) and m.shape[3] == W >> (l + 1), "image maps must halve level by level"
+        g = xy.contiguous()
+        out = torch.empty((B, 32, N), dtype=torch.float32, device=g.device)
+        ws = torch.empty(int(_lib.lib().jmb_decode_workspace_bytes(B, N)), dtype=torch.uint8, device=g.device)
+        st = _lib.stream_and_device(g)
+        _lib.check(_lib.lib().jmb_decode_gather(B, N, H, W, g.data_ptr(), *[m.data_ptr() for m in ms],
+                                                *[m.shape[1] for m in ms], wexp.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                                                ws.data_ptr(), out.data_ptr(), st), "decode_gather")
+        return out
 
     def geometry(self, xyz: torch.Tensor) -> "GeometryPlan":
         """The coordinate-only stage of the whole backbone on the CURRENT stream: FPS + centres + both ball-query
@@ -332,12 +393,13 @@ class PointNet2MSG(nn.Module):
 
     @torch.no_grad()
     def forward(self, pc, image=None, xy=None, image_maps=None, geometry=None):
-        """image_maps = (maps, fused) from image_features() may be passed to skip the image stack; geometry = the
+        """image_maps = (maps, fused) from image_features() may be passed to skip the image stack (fused None: the
+        decoder is evaluated at the sampled pixels only, image_decode.cu); geometry = the
         result of geometry(xyz) computed earlier (in stream order before this call) to skip the coordinate stage."""
         xyz, features = self._break_up_pc(pc)
         l_xyz, l_features, l_xy = [xyz], [features], [xy]
         if self.cfg.li_fusion and image_maps is None:
-            image_maps = self.image_features(image)
+            image_maps = self.image_features(image, dense=False)
         if geometry is not None:
             sa_plans = [(pl, None) for pl in geometry.sa]
             fp_plans = {i: (pl, None) for i, pl in geometry.fp.items()}
@@ -373,7 +435,9 @@ class PointNet2MSG(nn.Module):
             l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i],
                                                    plan=plan_i)
         if self.cfg.li_fusion:
-            l_features[0] = self.final_fusion_img_point(l_features[0], feature_gather(image_maps[1], xy))
+            fused = (feature_gather(image_maps[1], xy) if image_maps[1] is not None
+                     else self.decode_gather(image_maps[0], xy))
+            l_features[0] = self.final_fusion_img_point(l_features[0], fused)
         return l_xyz[0], l_features[0]
 
 
