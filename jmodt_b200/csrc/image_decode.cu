@@ -25,7 +25,8 @@ constexpr int DG_LEVELS = 4;
 constexpr int DG_PH = 16;                 // largest stride: 16 x 16 phases
 constexpr int DG_BINS = DG_PH * DG_PH;
 constexpr int DG_TILE = 512;              // samples per CTA
-constexpr int DG_THREADS = 256;
+constexpr int DG_THREADS = 512;
+constexpr int DG_MT = DG_TILE / (DG_THREADS / 32) / 16;      // 16-sample tiles per warp
 constexpr int DG_KC = 32;                 // channels per staged chunk
 constexpr int DG_R = 16;                  // decoder outputs per level (cfg.LI_FUSION.DeConv_Reduce)
 constexpr int DG_CAT = DG_LEVELS * DG_R;  // concatenated decoder channels
@@ -166,7 +167,9 @@ __device__ __forceinline__ void dg_split(float x, uint32_t &hi, uint32_t &lo) {
 // When a level is done its accumulator fragments ARE the A fragments of the folded 1x1 convolution (K = that level's 16
 // channels in the order the accumulator columns come in), so the concatenated 64-channel vector never leaves registers.
 // The first versions ran this on FFMA (4 x 4, then 16 x 2 register tiles, then packed fma.f32x2): 921 / 730 / 722 us for
-// 8 frames, bound by shared-memory wavefronts plus FFMA issue with two warps per scheduler.
+// 8 frames, bound by shared-memory wavefronts plus FFMA issue with two warps per scheduler; this one takes 503 us.
+// Measured apart (8 frames): the source-row gathers alone 342 us (2.0 GB of 128-byte L2 reads = 5.9 TB/s), the MMAs alone
+// 342 us (legacy HMMA pipe ~ 1/9 of the tcgen05 TF32 rate); a 4-stage ring of 16-channel chunks was slower (624 us).
 __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_constant__ DgParams p) {
     extern __shared__ __align__(16) float dg_smem[];
     float *s_src = dg_smem;                                        // [2][512][36]
@@ -219,14 +222,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
 #pragma unroll 4
         for (int r = t >> 3; r < DG_TILE; r += DG_THREADS / 8)
             dg_cp16(dst + r * DG_ROW + part * 4, base + s_off[l * DG_TILE + r] + part * 4);
-        dg_cp16(s_w + buf * DG_W_FLOATS + (t >> 3) * DG_WP + part * 4, wbin + (size_t)c * (2 * DG_R * DG_KC) + t * 4);
+        if (t < 2 * DG_R * DG_KC / 4)
+            dg_cp16(s_w + buf * DG_W_FLOATS + (t >> 3) * DG_WP + part * 4, wbin + (size_t)c * (2 * DG_R * DG_KC) + t * 4);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
-    float acc[4][2][4], h[4][4][4];         // [16-sample tile][8-output tile][fragment]
+    float acc[DG_MT][2][4], h[DG_MT][4][4];         // [16-sample tile][8-output tile][fragment]
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mt = 0; mt < DG_MT; ++mt) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const float *src = s_src + buf * DG_SRC_FLOATS + (warp * 64 + g) * DG_ROW + q;
+        const float *src = s_src + buf * DG_SRC_FLOATS + (warp * (16 * DG_MT) + g) * DG_ROW + q;
         const uint32_t *wh = reinterpret_cast<const uint32_t *>(s_w + buf * DG_W_FLOATS) + g * DG_WP + q;
         const uint32_t *wl = wh + DG_R * DG_WP;
 #pragma unroll
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
                 bl[nt][0] = wl[nt * 8 * DG_WP + k]; bl[nt][1] = wl[nt * 8 * DG_WP + k + 4];
             }
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
+            for (int mt = 0; mt < DG_MT; ++mt) {
                 const float *r0 = src + mt * 16 * DG_ROW + k;
                 uint32_t ah[4], al[4];
                 dg_split(r0[0], ah[0], al[0]);
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
                     bl[nt][0] = w1l[(8 * j) * DG_W1P + nt * 8]; bl[nt][1] = w1l[(8 * j + 1) * DG_W1P + nt * 8];
                 }
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
+                for (int mt = 0; mt < DG_MT; ++mt) {
                     uint32_t ah[4], al[4];
                     dg_split(acc[mt][j][0], ah[0], al[0]);
                     dg_split(acc[mt][j][2], ah[1], al[1]);
@@ -313,10 +317,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
     for (int nt = 0; nt < 4; ++nt) {
         const float2 bias = __ldg(reinterpret_cast<const float2 *>(p.b1 + nt * 8 + 2 * q));
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < DG_MT; ++mt) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int s = warp * 64 + mt * 16 + g + 8 * half;
+                const int s = warp * (16 * DG_MT) + mt * 16 + g + 8 * half;
                 if (s < cnt)
                     *reinterpret_cast<float2 *>(p.taps + (size_t)s_item[s] * DG_OUT + nt * 8 + 2 * q) =
                         make_float2(fmaxf(h[mt][nt][2 * half] + bias.x, 0.f), fmaxf(h[mt][nt][2 * half + 1] + bias.y, 0.f));
