@@ -77,6 +77,13 @@ def parse():
     ap.add_argument("--rois", default="synthetic", choices=["synthetic", "proposal"],
                     help="e2e workload: RoIs the per-proposal stage consumes (synthetic cluster boxes, or the proposal layer's output)")
     ap.add_argument("--pairs", type=int, default=1, help="affinity-sharded workload: 128x128 frame pairs per step")
+    ap.add_argument("--image-map", default="sparse", choices=["sparse", "dense"],
+                    help="e2e workload: sparse = the image decoder (deconv x4 + 1x1 + BN + ReLU + sampling) runs inside the "
+                         "timed step, evaluated at the sampled pixels (image_decode.cu); dense = the fused full-resolution "
+                         "map is precomputed outside the timed region (the round-1 configuration)")
+    ap.add_argument("--image-stack", action="store_true",
+                    help="e2e workload: also run the 3x3 image convolution stack (cuDNN, channels-last, TF32 as the "
+                         "reference's default) inside the timed step; the image is then an uploaded input")
     return ap.parse_args()
 
 
@@ -187,7 +194,7 @@ class FusionE2E:
     stages, and is handed over at the end of the step.  Every step therefore does one batch's complete work; the
     step's input is the current batch's pixel coordinates / RoIs and the next batch's points."""
 
-    def __init__(self, dev, frames, host_np, pipeline=True, rois_from="synthetic"):
+    def __init__(self, dev, frames, host_np, pipeline=True, rois_from="synthetic", image_map="sparse", image_stack=False):
         import torch
         from jmodt_b200 import tc
         from jmodt_b200.detector import PointRCNN, RpnConfig
@@ -196,10 +203,14 @@ class FusionE2E:
         self.pipeline, self.rois_from, self.ahead = pipeline, rois_from, None
         torch.manual_seed(0)
         self.model = fill_deterministic(PointRCNN(rpn_cfg=RpnConfig(post_nms_top_n=N_ROI))).to(dev).eval()
+        self.image_map, self.image_stack = image_map, image_stack
         with torch.no_grad():
             img = torch.from_numpy(host_np["img"]).to(dev)
-            maps, fused = self.model.rpn.backbone_net.image_features(img)
-            self.image_maps = ([m.contiguous() for m in maps], fused.contiguous())
+            if image_map == "dense":
+                maps, fused = self.model.rpn.backbone_net.image_features(img)
+                self.image_maps = ([m.contiguous() for m in maps], fused.contiguous())
+            else:       # channels-last maps as the convolutions emit them; the decoder runs per step at the sampled pixels
+                self.image_maps = self.model.rpn.backbone_net.image_features(img, dense=False)
         del img
         from jmodt_b200.runtime import EventLog
         self.log = EventLog()
@@ -221,7 +232,17 @@ class FusionE2E:
     def _main(self, d, geometry):
         torch, m = self.torch, self.model
         inp = {"pts_input": d["pts"], "pts_xy": d["pts_xy"]}
-        rpn = self._t("rpn_point_path", lambda: m.rpn(inp, image_maps=self.image_maps, geometry=geometry))
+        image_maps = self.image_maps
+        if self.image_stack:
+            def conv_stack():
+                tf32 = torch.backends.cudnn.allow_tf32
+                torch.backends.cudnn.allow_tf32 = True      # the reference's default for cuDNN convolutions
+                try:
+                    return m.rpn.backbone_net.image_features(d["img"], dense=self.image_map == "dense")
+                finally:
+                    torch.backends.cudnn.allow_tf32 = tf32
+            image_maps = self._t("image_conv_stack_cudnn", conv_stack)
+        rpn = self._t("rpn_point_path", lambda: m.rpn(inp, image_maps=image_maps, geometry=geometry))
         scores = rpn["rpn_cls"][:, :, 0]
         seg_mask = (torch.sigmoid(scores) > m.rpn.cfg.score_thresh).float()
         depth = torch.norm(rpn["backbone_xyz"], p=2, dim=2)
@@ -246,7 +267,7 @@ def make_inputs_e2e(first_frame, frames):
 
 
 def to_device_e2e(host, dev, torch, non_blocking=True):
-    d = {k: host[k].to(dev, non_blocking=non_blocking) for k in ("next_pts", "pts_xy", "rois")}
+    d = {k: host[k].to(dev, non_blocking=non_blocking) for k in ("next_pts", "pts_xy", "rois", "img") if k in host}
     d["pts"] = d["next_pts"].clone()      # steady state of the stream: the batch uploaded one step earlier
     return d
 
@@ -335,8 +356,10 @@ def run_b200(args):
     # no data-path collective is needed (affinity pairs (2k, 2k+1) never straddle a shard because B is even)
     host_np = make_inputs_e2e(rank * B, B) if e2e_mode else make_inputs(rank * B, B)
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    host = {k: ([pin(x) for x in v] if isinstance(v, list) else pin(v)) for k, v in host_np.items() if k != "img"}
-    suite = (FusionE2E(dev, B, host_np, pipeline=not args.no_pipeline, rois_from=args.rois) if e2e_mode
+    host = {k: ([pin(x) for x in v] if isinstance(v, list) else pin(v)) for k, v in host_np.items()
+            if k != "img" or (e2e_mode and args.image_stack)}
+    suite = (FusionE2E(dev, B, host_np, pipeline=not args.no_pipeline, rois_from=args.rois, image_map=args.image_map,
+                       image_stack=args.image_stack) if e2e_mode
              else OpsSuite(dev, B))
     upload = to_device_e2e if e2e_mode else to_device
     d = upload(host, dev, torch)
@@ -518,9 +541,13 @@ def run_b200(args):
                                 "2-3 on the tensor cores and finishes layer 1 (applied to the points by a separate small GEMM) "
                                 "in its gather, see executed_flops in `launch`"}
             workload = ("end-to-end region-proposal fusion + link/start-end affinity (BASELINE config 3): RPN point path "
-                        "with LI-Fusion on precomputed image maps, proposal layer, roipool3d+canonical, per-proposal "
-                        "RCNN, pair affinity; image 3x3 conv stack outside the timed region (SURVEY 8f.1); RCNN on "
-                        "synthetic cluster RoIs")
+                        "with LI-Fusion, " +
+                        ("image decoder (deconv x4 + 1x1 conv + BN + ReLU) evaluated at the sampled pixels inside the step, "
+                         if args.image_map == "sparse" else "fused image map precomputed outside the timed region, ") +
+                        "proposal layer, roipool3d+canonical, per-proposal RCNN, pair affinity; image 3x3 conv stack " +
+                        ("inside the timed region (cuDNN, channels-last, TF32)" if args.image_stack
+                         else "outside the timed region (cuDNN; SURVEY 8f.1)") +
+                        "; RCNN on " + ("the proposal layer's RoIs" if args.rois == "proposal" else "synthetic cluster RoIs"))
         else:
             hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
             rp_ms = kernel_ms.get("roipool3d", float("nan"))
@@ -558,7 +585,8 @@ def run_b200(args):
             "wall_s_timed_region": wall_s,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = (cpu_reference_e2e(threads=os.cpu_count() or 1) if e2e_mode
+            out["cpu_baseline"] = (cpu_reference_e2e(threads=os.cpu_count() or 1, image_map=args.image_map,
+                                                     image_stack=args.image_stack) if e2e_mode
                                    else cpu_reference(min(args.cpu_sample_frames, B), threads=1))
     if world > 1:
         dist.barrier()
@@ -648,7 +676,7 @@ def cpu_reference(frames, threads):
 _CPU_E2E_CACHE = {}
 
 
-def cpu_reference_e2e(threads, rcnn_sample=N_ROI, pair_sample=N_ROI):
+def cpu_reference_e2e(threads, rcnn_sample=N_ROI, pair_sample=N_ROI, image_map="sparse", image_stack=False):
     """Host-CPU time of the same end-to-end path on ONE full frame (no extrapolation): the reference forward restated
     in oracle/modules_ref.py (torch-CPU layers with `threads` intra-op threads; FPS / ball-query / three_nn / NMS through
     the C oracle; RoI pooling through the REFERENCE's own `roipool3d_cpu` (roipool3d.cpp:97-195) when oracle/_ref is
@@ -673,6 +701,22 @@ def cpu_reference_e2e(threads, rcnn_sample=N_ROI, pair_sample=N_ROI):
     model, f, maps = _CPU_E2E_CACHE["setup"]
     xyz, xy = torch.from_numpy(f["pts"]), torch.from_numpy(f["pts_xy"])
     with torch.no_grad():
+        # the image stages the B200 arm has inside its timed step, as the reference runs them (backbone.py:170,187-193)
+        net = model.rpn.backbone_net
+        t_img = 0.0
+        if image_stack:
+            t0 = time.perf_counter()
+            x, conv_maps = torch.from_numpy(f["img"]), []
+            for blk in net.Img_Block:
+                x = blk(x)
+                conv_maps.append(x)
+            t_img += time.perf_counter() - t0
+        if image_map == "sparse":
+            t0 = time.perf_counter()
+            de = torch.cat([dc(m) for dc, m in zip(net.DeConv, maps[0])], dim=1)
+            torch.relu(net.image_fusion_bn(net.image_fusion_conv(de)))
+            del de
+            t_img += time.perf_counter() - t0
         t0 = time.perf_counter()
         bxyz, feats = modules_ref.backbone_forward(model.rpn.backbone_net, xyz, xy, maps, cref)
         rpn_cls = modules_ref.shared_mlp(model.rpn.rpn_cls_layer, feats).transpose(1, 2)
@@ -716,14 +760,17 @@ def cpu_reference_e2e(threads, rcnn_sample=N_ROI, pair_sample=N_ROI):
         pf, df = torch.rand(pair_sample, 512, generator=g), torch.rand(pair_sample, 512, generator=g)
         modules_ref.affinity(model.rcnn_net.link_layer, model.rcnn_net.se_layer, pf, df)
         t_aff = time.perf_counter() - t0
-    per_frame = t_rpn + t_prop + t_rcnn * (N_ROI / rcnn_sample) + 0.5 * t_aff * (N_ROI / pair_sample) ** 2
+    per_frame = t_img + t_rpn + t_prop + t_rcnn * (N_ROI / rcnn_sample) + 0.5 * t_aff * (N_ROI / pair_sample) ** 2
     return {"value": N_ROI / per_frame, "unit": "proposals/s", "cores": threads,
             "kind": "port",
             "sample": ("" if ref_rp is None else "RoI pooling through the reference's own roipool3d_cpu (oracle/_ref); ") +
-                      f"one full frame: RPN point path ({t_rpn:.1f} s), proposal layer ({t_prop:.1f} s), {rcnn_sample} of 128 "
+                      f"one full frame: " + (f"image stages ({'3x3 conv stack + ' if image_stack else ''}"
+                                             f"{'dense decoder' if image_map == 'sparse' else ''}: {t_img:.1f} s), "
+                                             if t_img > 0 else "") +
+                      f"RPN point path ({t_rpn:.1f} s), proposal layer ({t_prop:.1f} s), {rcnn_sample} of 128 "
                       f"proposals through RoI pooling + the per-proposal network ({t_rcnn:.1f} s), one {pair_sample}x{pair_sample} "
                       f"affinity pair ({t_aff:.1f} s, half of it is this frame's share) = {per_frame:.1f} s per frame",
-            "seconds": t_rpn + t_prop + t_rcnn + t_aff}
+            "seconds": t_img + t_rpn + t_prop + t_rcnn + t_aff}
 
 
 def run_reference(args):
@@ -740,7 +787,7 @@ def run_reference(args):
         # one step = one full frame on all host threads; K steps unless the projected run would exceed ~150 s
         runs, t_start = [], time.perf_counter()
         for i in range(max(1, args.steps)):
-            runs.append(cpu_reference_e2e(threads))
+            runs.append(cpu_reference_e2e(threads, image_map=args.image_map, image_stack=args.image_stack))
             if (time.perf_counter() - t_start) / (i + 1) * (i + 2) > 150.0:
                 break
         base = dict(runs[-1])
