@@ -9,9 +9,9 @@ names / state_dict keys:
     PointRCNN                                                            jmodt/detection/modeling/point_rcnn.py
 
 Inference only.  Point-cloud ops and every 1x1-conv / Linear layer on the point path run on this package's
-sm_100a kernels.  The 3x3 image conv / deconv stack (backbone.py:15-30,130-139,187-193) stays on cuDNN: it is
-row (f)1 of SURVEY §8 ("next"), outside the hot-path scope of this round.
-"""
+sm_100a kernels, and so does the image decoder (backbone.py:187-196: deconvolutions + 1x1 conv + BatchNorm + ReLU +
+sampling, evaluated at the sampled pixels only: csrc/image_decode.cu).  The 3x3 image convolutions
+(backbone.py:15-30,170) stay on cuDNN: row (f)1 of SURVEY §8 ("next")."""
 from __future__ import annotations
 
 import os
@@ -86,7 +86,7 @@ def feature_gather(feature_map: torch.Tensor, xy: torch.Tensor) -> torch.Tensor:
 
 
 class BasicBlock(nn.Module):
-    """backbone.py:15-30 (cuDNN; image stack is out of this round's scope)."""
+    """backbone.py:15-30 (cuDNN)."""
 
     def __init__(self, in_channels, out_channels, stride=1):
         super().__init__()
