@@ -257,7 +257,7 @@ JMB_API int jmb_sa_fused(const float *z, const float *w1x, const void *w2, const
 
 /* LI-Fusion attention weight (reference backbone.py:33-58, IALayer: three Linear layers, tanh, sigmoid) as one fp32 kernel:
  * att[b,n] = sigmoid(w3 . tanh(W1 . img[b,:,n] + W2 . pt[b,:,n] + b12) + b3).  img (B, ic, N), pt (B, pc, N) channel-first;
- * w12 (rc, ic+pc) = [W1 | W2] row-major, b12 (rc) = b1 + b2, w3 (rc); rc <= 256.  att (B, N). */
+ * w12 (rc, ic+pc) = [W1 | W2] row-major, b12 (rc) = b1 + b2, w3 (rc); rc <= 64, (ic+pc) * rc_padded * 4 <= 200 KB.  att (B, N). */
 JMB_API int jmb_ia_attention(int B, int ic, int pc, int rc, int N, const float *img, const float *pt, const float *w12,
                              const float *b12, const float *w3, float b3, float *att, void *stream);
 

@@ -10,7 +10,7 @@ agg = collections.OrderedDict()
 for r in rows[start:]:
     if len(r) <= vi:
         continue
-    name = r[ki].split('(')[0][:70]
+    name = r[ki].split("(")[0][:70] if "elementwise" not in r[ki] else r[ki][:230]
     v = float(r[vi].replace(',', '')); u = r[ui]
     us = v / 1000 if u.startswith('ns') else (v if u.startswith('us') else v * 1000)
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += us

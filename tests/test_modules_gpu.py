@@ -303,3 +303,25 @@ def test_wide_sa_level_first_layer_applied_before_the_gather(cuda):
             new_xyz2, unfused, idx2 = sa(pts, feats)
         assert torch.equal(idx, idx2) and fused.shape == unfused.shape
         assert _rel(fused.cpu().numpy(), unfused.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ic,pc,B,N", [(64, 96, 2, 4096), (128, 256, 2, 4100), (32, 128, 1, 8192), (32, 40, 3, 2731)])
+def test_ia_attention_kernel_matches_the_reference_layer(cuda, ic, pc, B, N):
+    """IALayer (backbone.py:33-58) through jmb_ia_attention (thread per point, all reduced channels in registers) against
+    the three Linear layers + tanh + sigmoid in torch on the CPU; ragged N and rc = 10 ... 64."""
+    from jmodt_b200.detector import IALayer
+    from jmodt_b200.synth import fill_deterministic
+    torch.manual_seed(3)
+    layer = fill_deterministic(IALayer([ic, pc])).eval()
+    g = torch.Generator().manual_seed(4)
+    img, pts = torch.randn(B, ic, N, generator=g), torch.randn(B, pc, N, generator=g)
+    with torch.no_grad():
+        ri = layer.fc1(img.transpose(1, 2).reshape(-1, ic))
+        rp = layer.fc2(pts.transpose(1, 2).reshape(-1, pc))
+        att = torch.sigmoid(layer.fc3(torch.tanh(ri + rp))).view(B, 1, N)
+        want = layer.conv1(img) * att
+    layer = layer.to(cuda)
+    assert B * N >= 8192 and pc // 4 <= 64          # the SIMT kernel's gate in IALayer.forward
+    got = layer(img.to(cuda), pts.to(cuda)).cpu()
+    assert (got - want).abs().max().item() <= 1e-4 * want.abs().max().item()      # fp32 logits within 1e-4 of the scale
