@@ -200,6 +200,14 @@ JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K,
                              const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
                              int pool, int relu, float *y, long long y_group_stride, void *stream);
 
+/* replaces the `conv3x3` layers of BasicBlock (jmodt/detection/modeling/backbone.py:9-30; cuDNN there): 3x3 convolution,
+ * padding 1, stride 1 or 2, + bias (eval-mode BatchNorm folded in) + optional ReLU, as an implicit GEMM on the same tcgen05
+ * kernel as jmb_tc_mlp_layer (fp32-grade three-term bf16 products).  Channels-last in and out: x (B, H, W, C) with C = 4
+ * (RGB + one zero channel) or a power of two >= 32; wpack = the packed (Cout, 9 * C) matrix [cout][3 dy + dx][c] in the
+ * layout of jmb_tc_mlp_layer's wpack; bias (ceil(Cout / 128) * 128) or null; y (B, OH, OW, Cout), OH = (H - 1) / stride + 1. */
+JMB_API int jmb_tc_conv3x3(const void *wpack, const float *bias, int Cout, int C, int B, int H, int W, int stride,
+                           const float *x, int relu, float *y, void *stream);
+
 /* ---- LI-Fusion image feature sampling ---------------------------------------------------- */
 
 /* replaces feature_gather (jmodt/detection/modeling/backbone.py:79-89): bilinear grid_sample with

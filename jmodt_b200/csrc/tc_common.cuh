@@ -71,6 +71,19 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
 }
+// the same with an explicit instruction descriptor (TC_IDESC_KK: both operands K-major)
+constexpr uint32_t TC_IDESC_KK = TC_IDESC & ~(1u << 16);
+__device__ __forceinline__ void umma_ss_i(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // One lane of a converged warp (elect.sync).  tcgen05.mma / tcgen05.commit take uniform-register operands; issued under
 // a `lane == 0` test the compiler cannot prove the region single-threaded and wraps EVERY such instruction in an
 // ELECT / BRA.U.ANY serialisation loop (~60 issue cycles per MMA measured: profiles/r02/sa_fused_timeline_v5b.txt).

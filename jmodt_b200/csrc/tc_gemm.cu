@@ -66,7 +66,7 @@ struct TcGemmParams {
     int G, N;                     // groups, columns per group
     int P, Nt, Nshift;            // groups per tile (1 unless N < 128 divides 128), column tiles per group, log2(N) if P > 1
     long long col_tiles;          // G * Nt (P == 1) or ceil(G / P)
-    int mode;                     // 0 dense, 1 grouped gather
+    int mode;                     // 0 dense, 1 grouped gather, 2 3x3 convolution (channels-last rows, K-major X images)
     int use_raw;                  // dense X staged by bulk copies (needs 16-byte aligned rows)
     int bulk_out;                 // dense Y staged in shared memory and written as 16-byte pieces (needs 16-byte aligned rows)
     const float *x;               // dense: (G, K, N)   gather: feats (G, K-3, n_pts)
@@ -76,6 +76,10 @@ struct TcGemmParams {
     const float *xyz;             // gather: (G, n_pts, 3)
     const float *centres;         // gather: (G, N / nsample, 3) or null (GroupAll: no centring)
     int nsample, n_pts;
+    // mode 2, 3x3 convolution (padding 1) as an implicit GEMM over a channels-last input: x (G, cv_H, cv_W, C) with
+    // C = 1 << cv_cshift channels per pixel, column n of group g = output pixel (n / cv_OW, n % cv_OW), K index
+    // k = tap * C + channel, tap = 3 dy + dx reading input pixel (oy * cv_stride + dy - 1, ox * cv_stride + dx - 1)
+    int cv_cshift, cv_H, cv_W, cv_OW, cv_stride;
     int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool),
                                   // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store
     int pool, relu;
@@ -254,12 +258,46 @@ tc_gemm_kernel(const TcGemmParams p) {
                 if (c.tile >= 0) tc_col(p, c.tile / p.Mt, 0, c.g0, c.n0);
                 norm(c, release);
             };
+            // mode 2: window origin (iy0, ix0) of this thread's eight pixels of the tile being STAGED (pixel rows
+            // (tl >> 3) + 16 j of the raw stage; 0x7fffffff: column beyond N)
+            int cv_tile = -2, cv_origin[8];
             // this thread's eight 16-byte pieces of raw chunk number ci -> stage ci % RSTAGES
             auto issue_raw = [&](const Cur &c, uint32_t ci) {
                 const int s = ci % TC_RSTAGES;
                 mbar_wait(&s_rempty[s], ((ci / TC_RSTAGES) & 1) ^ 1);       // the group's four warps have read the stage
                 TC_STAMP(cdbg, cdi, 15);
                 uint8_t *stage = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE;
+                if (p.mode == 2) {
+                    // raw stage = [128 pixels][32 channels]: a pixel row is 128 contiguous bytes of the channels-last input
+                    // (eight lanes per row, four rows per warp access); its 16-byte pieces are XOR-swizzled by the row so
+                    // that the converter's per-pixel reads are conflict-free
+                    if (cv_tile != c.tile) {
+                        cv_tile = c.tile;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int n = c.n0 + (tl >> 3) + 16 * j;
+                            const int oy = n / p.cv_OW, ox = n - oy * p.cv_OW;
+                            cv_origin[j] = n < p.N ? (((oy * p.cv_stride - 1) * 65536) | ((ox * p.cv_stride - 1) & 0xffff)) : 0x7fffffff;
+                        }
+                    }
+                    const int c8 = tl & 7;
+                    const int k = c.kc * TC_BK + c8 * 4;
+                    const int tap = k >> p.cv_cshift, ch = k & ((1 << p.cv_cshift) - 1);
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    const float *xg = p.x + (size_t)c.g0 * p.x_group_stride + ch;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = (tl >> 3) + 16 * j;
+                        const int iy = (cv_origin[j] >> 16) + dy, ix = (int)(short)(cv_origin[j] & 0xffff) + dx;
+                        const bool ok = tap < 9 && cv_origin[j] != 0x7fffffff && iy >= 0 && iy < p.cv_H && ix >= 0 && ix < p.cv_W;
+                        const float *src = ok ? xg + (((size_t)iy * p.cv_W + ix) << p.cv_cshift) : p.x;
+                        const uint32_t dst = smem_u32(stage + (size_t)r * 128 + (size_t)((c8 ^ (r & 7)) * 16));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                    }
+                    TC_STAMP(cdbg, cdi, 16);
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_rfull[s])) : "memory");
+                    return;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int piece = tl + j * 128;
@@ -290,13 +328,25 @@ tc_gemm_kernel(const TcGemmParams p) {
                 mbar_wait(&s_rfull[s], (c / TC_RSTAGES) & 1);
                 TC_STAMP(cdbg, cdi, 11);
                 float v[4][8];
+                if (p.mode == 2) {
+                    // pixel tl of the tile: its 32 channels -> four 8-channel runs, each one row of a K-major core matrix
+                    const uint8_t *row = tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)tl * 128;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 *src = reinterpret_cast<const float4 *>(
-                        tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)(q * 8 + rk) * TC_RAW_ROW + rg * 32);
-                    const float4 a4 = src[0], b4 = src[1];      // rows >= K and columns >= N were zero-filled by the copy
-                    v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
-                    v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a4 = *reinterpret_cast<const float4 *>(row + (((2 * q) ^ (tl & 7)) * 16));
+                        const float4 b4 = *reinterpret_cast<const float4 *>(row + (((2 * q + 1) ^ (tl & 7)) * 16));
+                        v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                        v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 *src = reinterpret_cast<const float4 *>(
+                            tc_smem + TC_OFF_RAW + (size_t)s * TC_RAW_STAGE + (size_t)(q * 8 + rk) * TC_RAW_ROW + rg * 32);
+                        const float4 a4 = src[0], b4 = src[1];      // rows >= K and columns >= N were zero-filled by the copy
+                        v[q][0] = a4.x; v[q][1] = a4.y; v[q][2] = a4.z; v[q][3] = a4.w;
+                        v[q][4] = b4.x; v[q][5] = b4.y; v[q][6] = b4.z; v[q][7] = b4.w;
+                    }
                 }
                 {   // image stage c % 2 (this group's own): wait until the MMAs of chunk c - 2 have read it
                     const int sx = c % TC_XSTAGES;
@@ -310,7 +360,10 @@ tc_gemm_kernel(const TcGemmParams p) {
                         split2(v[q][2], v[q][3], h.y, l.y);
                         split2(v[q][4], v[q][5], h.z, l.z);
                         split2(v[q][6], v[q][7], h.w, l.w);
-                        const uint32_t off = (uint32_t)rg * TC_SBO + (uint32_t)q * TC_LBO + (uint32_t)rk * 16;
+                        // MN-major image: core matrix = 8 k rows x 8 columns; K-major image (mode 2): 8 columns x 8 k
+                        const uint32_t off = p.mode == 2
+                            ? (uint32_t)(tl >> 3) * TC_SBO + (uint32_t)q * TC_LBO + (uint32_t)(tl & 7) * 16
+                            : (uint32_t)rg * TC_SBO + (uint32_t)q * TC_LBO + (uint32_t)rk * 16;
                         *reinterpret_cast<uint4 *>(xhi + off) = h;
                         *reinterpret_cast<uint4 *>(xlo + off) = l;
                     }
@@ -563,6 +616,7 @@ tc_gemm_kernel(const TcGemmParams p) {
     } else if (warp == W_MMA) {
         // =============================== MMA issuer ===============================
         constexpr uint64_t D_IMG = TC_IMG >> 4, D_K16 = (2 * TC_LBO) >> 4;
+        const uint32_t idesc = p.mode == 2 ? TC_IDESC_KK : TC_IDESC;      // convolution: X images are K-major like W's
         uint32_t xctr = 0, wctr = 0, tile_ctr = 0;
         long long *mdbg = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
         int mdi = 0;
@@ -587,12 +641,12 @@ tc_gemm_kernel(const TcGemmParams p) {
                 if (elect_one()) {
                     const uint64_t xd = make_smem_desc(smem_u32(tc_smem + TC_OFF_X + (size_t)sx * TC_CHUNK));
                     const uint64_t wd = make_smem_desc(smem_u32(tc_smem + TC_OFF_W + (size_t)sw * TC_CHUNK));
-                    umma_ss(acc, wd, xd, kc != 0);
-                    umma_ss(acc, wd + D_IMG, xd, 1);
-                    umma_ss(acc, wd, xd + D_IMG, 1);
-                    umma_ss(acc, wd + D_K16, xd + D_K16, 1);
-                    umma_ss(acc, wd + D_K16 + D_IMG, xd + D_K16, 1);
-                    umma_ss(acc, wd + D_K16, xd + D_K16 + D_IMG, 1);
+                    umma_ss_i(acc, wd, xd, idesc, kc != 0);
+                    umma_ss_i(acc, wd + D_IMG, xd, idesc, 1);
+                    umma_ss_i(acc, wd, xd + D_IMG, idesc, 1);
+                    umma_ss_i(acc, wd + D_K16, xd + D_K16, idesc, 1);
+                    umma_ss_i(acc, wd + D_K16 + D_IMG, xd + D_K16, idesc, 1);
+                    umma_ss_i(acc, wd + D_K16, xd + D_K16 + D_IMG, idesc, 1);
                     umma_commit(&s_xempty[sx]);
                     umma_commit(&s_wempty[sw]);
                     if (kc == p.Kc - 1) umma_commit(&s_acc_full[buf]);
@@ -664,6 +718,10 @@ int tc_sched_slot(int dev, int **counter, int **done) {
 
 }  // namespace jmb
 
+namespace jmb {
+int tc_gemm_launch(TcGemmParams &p, long long tiles, void *stream);
+}
+
 extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K, int G, int N, int mode,
                                         const float *x, long long x_group_stride, int x_row_stride, const int *idx,
                                         const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
@@ -699,6 +757,12 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     p.use_raw = (mode == 0 && al16(x) && N % 4 == 0 && x_row_stride % 4 == 0 && x_group_stride % 4 == 0) ? 1 : 0;
     p.bulk_out = (out_mode == 0 && al16(y) && N % 4 == 0 && p.y_group_stride % 4 == 0) ? 1 : 0;
 
+    return tc_gemm_launch(p, tiles, stream);
+}
+
+namespace jmb {
+int tc_gemm_launch(TcGemmParams &p, long long tiles, void *stream) {
+    const int M = p.M, K = p.K, N = p.N;
     int dev = 0, sms = 0;
     {
         const int rc = device_info(&dev, &sms);
@@ -734,4 +798,38 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
         cudaMemset(dbg_buf, 0, 1024 * sizeof(long long));
     }
     return check_launch("tc_mlp_layer");
+}
+}  // namespace jmb
+
+// 3x3 convolution, padding 1, stride 1 or 2, bias + optional ReLU, channels-last in and out, on the same kernel: an implicit
+// GEMM whose X operand rows are the 128-byte channel runs of the input pixels under the nine taps (zero-filled outside the
+// image), converted to bf16 hi / lo K-major images by the same converter warps; replaces the `conv3x3` layers of
+// BasicBlock (reference jmodt/detection/modeling/backbone.py:9-30; cuDNN there).  x (B, H, W, C) with C a power of two >= 4,
+// wpack = tc.pack_weights of the (Cout, 9 * C) matrix [cout][3 dy + dx][c]; y (B, OH, OW, Cout), OH = (H - 1) / stride + 1.
+extern "C" int jmb_tc_conv3x3(const void *wpack, const float *bias, int Cout, int C, int B, int H, int W, int stride,
+                              const float *x, int relu, float *y, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(Cout > 0 && C >= 4 && (C & (C - 1)) == 0 && B >= 0 && H > 0 && W > 0, "tc_conv3x3: bad sizes");
+    JMB_REQUIRE(C == 4 || C % TC_BK == 0, "tc_conv3x3: channels per pixel must be 4 or a multiple of 32");
+    JMB_REQUIRE(stride == 1 || stride == 2, "tc_conv3x3: stride must be 1 or 2");
+    JMB_REQUIRE(H < 32768 && W < 32768, "tc_conv3x3: image too large");
+    if (B == 0) return JMB_OK;
+    JMB_REQUIRE(wpack && x && y, "tc_conv3x3: null pointer");
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "tc_conv3x3: input must be 16-byte aligned");
+    const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    JMB_REQUIRE((long long)OH * OW < (1LL << 30), "tc_conv3x3: too many pixels");
+    TcGemmParams p{};
+    p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
+    p.M = Cout; p.K = 9 * C; p.Mt = div_up(p.M, TC_BM); p.Kc = div_up(p.K, TC_BK);
+    p.G = B; p.N = OH * OW; p.mode = 2; p.x = x; p.x_group_stride = (long long)H * W * C; p.x_row_stride = 0;
+    p.cv_cshift = 0;
+    while ((1 << p.cv_cshift) < C) ++p.cv_cshift;
+    p.cv_H = H; p.cv_W = W; p.cv_OW = OW; p.cv_stride = stride;
+    p.out_mode = 2; p.pool = 0; p.relu = relu; p.y = y; p.y_group_stride = (long long)p.N * Cout;
+    p.P = 1; p.Nshift = 0; p.Nt = div_up(p.N, TC_BN);
+    p.col_tiles = (long long)B * p.Nt;
+    const long long tiles = p.col_tiles * p.Mt;
+    JMB_REQUIRE(tiles < (1LL << 30), "tc_conv3x3: too many tiles");
+    p.use_raw = 1; p.bulk_out = 0;
+    return tc_gemm_launch(p, tiles, stream);
 }

@@ -11,7 +11,8 @@ names / state_dict keys:
 Inference only.  Point-cloud ops and every 1x1-conv / Linear layer on the point path run on this package's
 sm_100a kernels, and so does the image decoder (backbone.py:187-196: deconvolutions + 1x1 conv + BatchNorm + ReLU +
 sampling, evaluated at the sampled pixels only: csrc/image_decode.cu).  The 3x3 image convolutions
-(backbone.py:15-30,170) stay on cuDNN: row (f)1 of SURVEY §8 ("next")."""
+(backbone.py:15-30,170) run as implicit GEMMs on the same tcgen05 kernel as the 1x1 layers (BasicBlock._forward_tc;
+`pt_utils.torch_layers()` selects cuDNN)."""
 from __future__ import annotations
 
 import os
@@ -86,7 +87,7 @@ def feature_gather(feature_map: torch.Tensor, xy: torch.Tensor) -> torch.Tensor:
 
 
 class BasicBlock(nn.Module):
-    """backbone.py:15-30 (cuDNN)."""
+    """backbone.py:15-30.  Training / CPU: cuDNN / torch.  Inference on the device: tcgen05 implicit GEMMs."""
 
     def __init__(self, in_channels, out_channels, stride=1):
         super().__init__()
@@ -96,7 +97,20 @@ class BasicBlock(nn.Module):
         self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=2 * stride, padding=1, bias=False)
 
     def forward(self, x):
+        if pt_utils._on_tensor_cores(self, x) and x.dim() == 4:
+            return self._forward_tc(x)
         return self.conv2(self.relu(self.bn1(self.conv1(x))))
+
+    def _forward_tc(self, x):
+        """Inference on the device: both 3x3 convolutions as implicit GEMMs on the tcgen05 kernel (csrc/tc_gemm.cu,
+        convolution mode: fp32-grade three-term bf16 products, BatchNorm folded into conv1, ReLU in its epilogue),
+        channels-last in and out.  Returns a (B, C, H/2, W/2) tensor in torch.channels_last memory format."""
+        P = tc.packed_for(self, lambda: (tc.pack_conv3x3(self.conv1, self.bn1, relu=True), tc.pack_conv3x3(self.conv2)))
+        xn = x.permute(0, 2, 3, 1)                       # a view when x is channels-last
+        if xn.shape[3] < P[0].cpad:                      # RGB input: one zero channel makes a pixel one 16-byte piece
+            xn = F.pad(xn, (0, P[0].cpad - xn.shape[3]))
+        y = tc.conv3x3(P[1], tc.conv3x3(P[0], xn.contiguous()))
+        return y.permute(0, 3, 1, 2)
 
 
 class IALayer(nn.Module):
@@ -406,6 +420,11 @@ class PointNet2MSG(nn.Module):
         else:
             sa_plans, fp_plans = self._geometry(xyz)
         main = torch.cuda.current_stream() if xyz.is_cuda else None
+        decoded = None
+        if self.cfg.li_fusion and image_maps[1] is None:
+            # the decoder needs only the image maps and the pixel coordinates and is consumed by the last fusion layer:
+            # it runs on a background stream under the chain of small set-abstraction / propagation launches
+            decoded = runtime.spawn(lambda: self.decode_gather(image_maps[0], xy))
         for i, sa in enumerate(self.SA_modules):
             if sa_plans is not None:
                 plan_i, ev = sa_plans[i]
@@ -435,8 +454,7 @@ class PointNet2MSG(nn.Module):
             l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i],
                                                    plan=plan_i)
         if self.cfg.li_fusion:
-            fused = (feature_gather(image_maps[1], xy) if image_maps[1] is not None
-                     else self.decode_gather(image_maps[0], xy))
+            fused = feature_gather(image_maps[1], xy) if decoded is None else decoded.join()
             l_features[0] = self.final_fusion_img_point(l_features[0], fused)
         return l_xyz[0], l_features[0]
 

@@ -187,3 +187,50 @@ def parallel(*fns):
     for o in outs[1:]:
         hand_over(o)
     return outs
+
+
+_background_streams: dict = {}
+
+
+class Spawned:
+    """Result of spawn(): join() orders the caller's stream behind the background work and returns its output."""
+
+    def __init__(self, out, done):
+        self._out, self._done = out, done
+
+    def join(self):
+        if self._done is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(self._done)
+
+            def hand_over(o):
+                if isinstance(o, torch.Tensor):
+                    o.record_stream(main)
+                elif isinstance(o, (list, tuple)):
+                    for x in o:
+                        hand_over(x)
+            hand_over(self._out)
+            self._done = None
+        return self._out
+
+
+def spawn(fn) -> Spawned:
+    """Start `fn` on a background stream of its own (not one of parallel()'s sibling streams, which the caller keeps
+    using meanwhile) behind everything queued so far; the caller continues and join()s where it needs the result.  For a
+    long launch whose inputs are ready early and whose output is needed late — the image decoder next to the chain of
+    small set-abstraction / feature-propagation launches.  Inside a CUDA-graph capture the fork / join become graph edges."""
+    if not branch_parallel or not torch.cuda.is_available():
+        return Spawned(fn(), None)
+    main = torch.cuda.current_stream()
+    dev = main.device
+    s = _background_streams.get(dev)
+    if s is None:
+        s = _background_streams[dev] = torch.cuda.Stream(device=dev)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    s.wait_event(fork)
+    with torch.cuda.stream(s):
+        out = fn()
+        done = torch.cuda.Event()
+        done.record(s)
+    return Spawned(out, done)

@@ -95,6 +95,42 @@ def fold_conv_bn(conv, bn=None):
     return w, b
 
 
+def pack_conv3x3(conv, bn=None, relu: bool = False) -> PackedLayer:
+    """3x3 Conv2d (+ eval-mode BatchNorm folded in) as the (Cout, 9 * Cpad) matrix [cout][3 dy + dx][c] that
+    csrc/tc_gemm.cu's convolution mode multiplies; Cpad = 4 for the RGB input, the channel count otherwise."""
+    w = conv.weight.detach().float()                                   # (Cout, Cin, 3, 3)
+    cout, cin = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (3, 3) and conv.padding == (1, 1) and conv.stride[0] == conv.stride[1] and conv.stride[0] in (1, 2)
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None, None, None]
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    cpad = 4 if cin <= 4 else cin
+    assert cpad & (cpad - 1) == 0 and (cpad == 4 or cpad % 32 == 0), "conv3x3: channels must be <= 4 or a power of two >= 32"
+    wk = torch.zeros(cout, 3, 3, cpad, dtype=torch.float32, device=w.device)
+    wk[..., :cin] = w.permute(0, 2, 3, 1)
+    layer = PackedLayer(wk.reshape(cout, 9 * cpad), b, relu)
+    layer.cpad, layer.stride = cpad, conv.stride[0]
+    return layer
+
+
+def conv3x3(layer: PackedLayer, x: torch.Tensor) -> torch.Tensor:
+    """x (B, H, W, Cpad) channels-last fp32 -> (B, OH, OW, Cout) on the tcgen05 kernel (implicit GEMM, 9 taps x channels)."""
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype == torch.float32 and x.shape[3] == layer.cpad
+    B, H, W, C = x.shape
+    s = layer.stride
+    OH, OW = (H - 1) // s + 1, (W - 1) // s + 1
+    y = torch.empty((B, OH, OW, layer.M), dtype=torch.float32, device=x.device)
+    st = _lib.stream_and_device(x)
+    flops = 2.0 * B * OH * OW * layer.M * 9 * C
+    desc = f"conv3x3 Cout={layer.M} C={C} B={B} {H}x{W} stride={s}"
+    profiler.launch(flops, lambda: _lib.check(
+        _lib.lib().jmb_tc_conv3x3(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, C, B, H, W, s, x.data_ptr(),
+                                  int(layer.relu), y.data_ptr(), st), "tc_conv3x3"), desc=desc)
+    return y
+
+
 def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None = None,
               pool: int = 0, point_major_out: bool = False) -> torch.Tensor:
     """Dense layer: x (G, K, N) channel-first fp32 -> (G, M, N), or (G, M, N / pool) with pool > 0, or the

@@ -8,6 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jmodt_b200.detector import PointNet2MSG, RpnConfig  # noqa: E402
+from jmodt_b200.pointnet2 import pytorch_utils as pt_utils  # noqa: E402
 from jmodt_b200.synth import fill_deterministic, make_batch  # noqa: E402
 
 
@@ -33,7 +34,8 @@ def main():
     res = {}
     with torch.no_grad():
         maps_cl, _ = net.image_features(img, dense=False)
-        maps, _ = net.image_features(img, dense=True)[0], None
+        with pt_utils.torch_layers():
+            maps, _ = net.image_features(img, dense=True)[0], None
         res["decode_gather_sparse_us"] = timed(lambda: net.decode_gather(maps_cl, xy))
 
         def dense():
@@ -41,6 +43,18 @@ def main():
             fused = torch.relu(net.image_fusion_bn(net.image_fusion_conv(de)))
             return torch.nn.functional.grid_sample(fused, xy.unsqueeze(1), align_corners=True).squeeze(2)
         res["decode_dense_cudnn_tf32_us"] = timed(dense, n=3, warm=1)
+        def own_stack():
+            y = img
+            for blk in net.Img_Block:
+                y = blk(y)
+            return y
+        res["conv_stack_tcgen05_fp32_grade_us"] = timed(own_stack, n=5, warm=2)
+        y = img
+        for i, blk in enumerate(net.Img_Block):
+            res["conv_block%d_tcgen05_us" % (i + 1)] = timed(lambda: blk(y), n=5, warm=1)
+            y = blk(y)
+        ctx = pt_utils.torch_layers()
+        ctx.__enter__()
         for name, tf32, cl in (("nchw_tf32", True, False), ("nhwc_tf32", True, True), ("nchw_fp32", False, False),
                                ("nhwc_fp32", False, True)):
             torch.backends.cudnn.allow_tf32 = tf32
@@ -71,6 +85,7 @@ def main():
                 y = blk(y)
             return y
         res["conv_stack_cudnn_nhwc_bf16_autotuned_us"] = timed(stackb, n=3, warm=3)
+        ctx.__exit__(None, None, None)
     res["conv_stack_gflop"] = 92.3 * B
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/decode_bench.json", "w") as f:

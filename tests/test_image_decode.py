@@ -132,3 +132,30 @@ def test_backbone_with_sparse_decoder_matches_dense_maps(cuda):
     scale = want.abs().max().item()
     assert (got - want).abs().max().item() <= 1e-4 * scale
     assert (cl - want).abs().max().item() <= 1e-4 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,B,H,W", [(3, 64, 2, 32, 64), (64, 128, 1, 24, 40), (128, 128, 2, 17, 23),
+                                             (256, 512, 1, 12, 20), (3, 64, 1, 384, 1280)])
+def test_basic_block_on_tensor_cores_matches_torch_fp32(cuda, cin, cout, B, H, W):
+    """BasicBlock (backbone.py:15-30: conv3x3 -> BN -> ReLU -> conv3x3 stride 2) through the tcgen05 implicit-GEMM
+    convolution against torch on the CPU in fp32; odd sizes exercise the zero padding and the ragged last tile."""
+    from jmodt_b200.detector import BasicBlock
+    from jmodt_b200.synth import fill_deterministic
+    torch.manual_seed(1)
+    blk = fill_deterministic(BasicBlock(cin, cout)).eval()
+    with torch.no_grad():
+        blk.bn1.running_mean.copy_(torch.linspace(-0.3, 0.2, cout))
+        blk.bn1.running_var.copy_(torch.linspace(0.6, 1.7, cout))
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, cin, H, W, generator=g)
+    with torch.no_grad():
+        want = blk(x)
+    blk = blk.to(cuda)
+    with torch.no_grad():
+        got = blk(x.to(cuda))
+        got_cl = blk(x.to(cuda).contiguous(memory_format=torch.channels_last))
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, got_cl)
+    scale = want.abs().max().item()
+    assert (got.cpu() - want).abs().max().item() <= 1e-4 * scale
