@@ -82,8 +82,8 @@ def parse():
                          "timed step, evaluated at the sampled pixels (image_decode.cu); dense = the fused full-resolution "
                          "map is precomputed outside the timed region (the round-1 configuration)")
     ap.add_argument("--image-stack", action="store_true",
-                    help="e2e workload: also run the 3x3 image convolution stack (cuDNN, channels-last, TF32 as the "
-                         "reference's default) inside the timed step; the image is then an uploaded input")
+                    help="e2e workload: also run the 3x3 image convolution stack (tcgen05 implicit GEMMs, fp32-grade) inside "
+                         "the timed step; the image is then an uploaded input")
     return ap.parse_args()
 
 
@@ -234,14 +234,8 @@ class FusionE2E:
         inp = {"pts_input": d["pts"], "pts_xy": d["pts_xy"]}
         image_maps = self.image_maps
         if self.image_stack:
-            def conv_stack():
-                tf32 = torch.backends.cudnn.allow_tf32
-                torch.backends.cudnn.allow_tf32 = True      # the reference's default for cuDNN convolutions
-                try:
-                    return m.rpn.backbone_net.image_features(d["img"], dense=self.image_map == "dense")
-                finally:
-                    torch.backends.cudnn.allow_tf32 = tf32
-            image_maps = self._t("image_conv_stack_cudnn", conv_stack)
+            image_maps = self._t("image_conv_stack", lambda: m.rpn.backbone_net.image_features(
+                d["img"], dense=self.image_map == "dense"))
         rpn = self._t("rpn_point_path", lambda: m.rpn(inp, image_maps=image_maps, geometry=geometry))
         scores = rpn["rpn_cls"][:, :, 0]
         seg_mask = (torch.sigmoid(scores) > m.rpn.cfg.score_thresh).float()
@@ -545,8 +539,8 @@ def run_b200(args):
                         ("image decoder (deconv x4 + 1x1 conv + BN + ReLU) evaluated at the sampled pixels inside the step, "
                          if args.image_map == "sparse" else "fused image map precomputed outside the timed region, ") +
                         "proposal layer, roipool3d+canonical, per-proposal RCNN, pair affinity; image 3x3 conv stack " +
-                        ("inside the timed region (cuDNN, channels-last, TF32)" if args.image_stack
-                         else "outside the timed region (cuDNN; SURVEY 8f.1)") +
+                        ("inside the timed region (tcgen05 implicit GEMMs)" if args.image_stack
+                         else "outside the timed region (SURVEY 8f.1: excluded from the hot-path numerator)") +
                         "; RCNN on " + ("the proposal layer's RoIs" if args.rois == "proposal" else "synthetic cluster RoIs"))
         else:
             hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
