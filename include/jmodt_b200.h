@@ -200,6 +200,17 @@ JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K,
                              const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
                              int pool, int relu, float *y, long long y_group_stride, void *stream);
 
+/* two pointwise layers in one launch when the second has ONE output channel (the heads end in a C -> 1 layer: rpn.py:40-47,
+ * rcnn.py:91-111, tracker.py:86-109): layer 1 as jmb_tc_mlp_layer (dense x), its activated rows multiplied by dot_w
+ * (ceil(M / 128) * 128 floats, zero padded: the second layer's weights) and reduced per 32-row block in fp32.
+ * partial (G, 4 * ceil(M / 128), N): sum over dim 1 + the second layer's bias = the second layer's output. */
+JMB_API int jmb_tc_mlp_layer_dot(const void *wpack, const float *bias, int M, int K, int G, int N, const float *x,
+                                 long long x_group_stride, int x_row_stride, int relu, const float *dot_w,
+                                 float *partial, void *stream);
+
+/* out (G, N) = act(bias + sum over dim 1 of partial (G, rows, N)), rows added in index order (shape-independent result) */
+JMB_API int jmb_tc_dot_finish(int G, int rows, int N, const float *partial, float bias, int relu, float *out, void *stream);
+
 /* replaces the `conv3x3` layers of BasicBlock (jmodt/detection/modeling/backbone.py:9-30; cuDNN there): 3x3 convolution,
  * padding 1, stride 1 or 2, + bias (eval-mode BatchNorm folded in) + optional ReLU, as an implicit GEMM on the same tcgen05
  * kernel as jmb_tc_mlp_layer (fp32-grade three-term bf16 products).  Channels-last in and out: x (B, H, W, C) with C = 4

@@ -81,7 +81,10 @@ struct TcGemmParams {
     // k = tap * C + channel, tap = 3 dy + dx reading input pixel (oy * cv_stride + dy - 1, ox * cv_stride + dx - 1)
     int cv_cshift, cv_H, cv_W, cv_OW, cv_stride;
     int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool),
-                                  // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store
+                                  // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store,
+                                  // 3 dot: the NEXT layer when it has one output channel, y (G, 4 Mt, N) = per 32-row
+                                  //   block the partial sums  sum_m dot_w[m] * act(W x + b)[m]  (added up by the caller)
+    const float *dot_w;           // out_mode 3: (Mt * 128) weights of the single-output layer that follows, zero padded
     int pool, relu;
     float *y;
     long long y_group_stride;     // elements between consecutive groups of y
@@ -487,6 +490,7 @@ tc_gemm_kernel(const TcGemmParams p) {
             const int buf = tile_ctr % TC_ACC_BUFS;
             const int m = mt * TC_BM + r;
             const float bias = (p.bias && m < p.M) ? __ldg(p.bias + m) : 0.f;
+            const float dot_w = (p.out_mode == 3 && m < p.M) ? __ldg(p.dot_w + m) : 0.f;
             // pool windows of 128 columns are reduced by the half-0 warps alone
             const bool whole = (p.out_mode == 1 && p.pool > 64);
             const int c_begin = whole ? 0 : half * 64;
@@ -510,7 +514,26 @@ tc_gemm_kernel(const TcGemmParams p) {
                     const float o = v[j] + bias;
                     v[j] = p.relu ? fmaxf(o, 0.f) : o;
                 }
-                if (p.out_mode == 0) {
+                if (p.out_mode == 3) {
+                    // the 32 rows of this warp times the following layer's weights, summed over the rows with a fixed
+                    // butterfly (lane l ends up with column c0 + l): deterministic, independent of how columns are tiled
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= dot_w;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = up ? v[i] : v[i + off];
+                            const float keep = up ? v[i + off] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    int g, n;
+                    tc_col(p, ct, c0 + lane, g, n);
+                    if (g < p.G && n < p.N)
+                        p.y[(size_t)g * p.y_group_stride + (size_t)(mt * 4 + quad) * p.N + n] = v[0];
+                } else if (p.out_mode == 0) {
                     if (p.bulk_out) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -736,7 +759,7 @@ extern "C" int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int
     JMB_REQUIRE(out_mode >= 0 && out_mode <= 2, "tc_mlp_layer: bad out_mode");
     JMB_REQUIRE(out_mode != 1 || (pool > 0 && pool <= TC_BN && TC_BN % pool == 0 && N % pool == 0),
                 "tc_mlp_layer: pool must divide 128 and N");
-    TcGemmParams p;
+    TcGemmParams p{};
     p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
     p.M = M; p.K = K; p.Mt = div_up(M, TC_BM); p.Kc = div_up(K, TC_BK);
     p.G = G; p.N = N; p.mode = mode; p.x = x; p.x_group_stride = x_group_stride; p.x_row_stride = x_row_stride;
@@ -800,6 +823,67 @@ int tc_gemm_launch(TcGemmParams &p, long long tiles, void *stream) {
     return check_launch("tc_mlp_layer");
 }
 }  // namespace jmb
+
+// Two layers in one launch when the second has ONE output channel (the cls / link / start-end heads end in a C -> 1 layer:
+// reference rpn.py:40-47, rcnn.py:91-111): the epilogue of layer 1 multiplies its activated rows by the second layer's
+// weights and reduces over the rows in fp32.  partial (G, 4 * ceil(M / 128), N): the caller adds the rows and the bias.
+extern "C" int jmb_tc_mlp_layer_dot(const void *wpack, const float *bias, int M, int K, int G, int N, const float *x,
+                                    long long x_group_stride, int x_row_stride, int relu, const float *dot_w,
+                                    float *partial, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(M > 0 && K > 0 && G >= 0 && N >= 0, "tc_mlp_layer_dot: bad sizes");
+    if (G == 0 || N == 0) return JMB_OK;
+    JMB_REQUIRE(wpack && x && dot_w && partial, "tc_mlp_layer_dot: null pointer");
+    TcGemmParams p{};
+    p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
+    p.M = M; p.K = K; p.Mt = div_up(M, TC_BM); p.Kc = div_up(K, TC_BK);
+    p.G = G; p.N = N; p.mode = 0; p.x = x; p.x_group_stride = x_group_stride; p.x_row_stride = x_row_stride;
+    p.out_mode = 3; p.pool = 0; p.relu = relu; p.y = partial; p.dot_w = dot_w;
+    p.y_group_stride = (long long)4 * p.Mt * N;
+    p.P = 1; p.Nshift = 0;
+    if (N >= 8 && N < TC_BN && (N & (N - 1)) == 0 && G > 1) {
+        p.P = TC_BN / N;
+        while ((1 << p.Nshift) < N) ++p.Nshift;
+    }
+    p.Nt = p.P == 1 ? div_up(N, TC_BN) : 1;
+    p.col_tiles = p.P == 1 ? (long long)G * p.Nt : (long long)div_up(G, p.P);
+    const long long tiles = p.col_tiles * p.Mt;
+    JMB_REQUIRE(tiles < (1LL << 30), "tc_mlp_layer_dot: too many tiles");
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    p.use_raw = (al16(x) && N % 4 == 0 && x_row_stride % 4 == 0 && x_group_stride % 4 == 0) ? 1 : 0;
+    p.bulk_out = 0;
+    return tc_gemm_launch(p, tiles, stream);
+}
+
+namespace jmb {
+// out[g][n] = act(bias + partial[g][0][n] + partial[g][1][n] + ...): the rows are added one after the other, so the result
+// does not depend on the shape (a library reduction picks its order by layout)
+__global__ void __launch_bounds__(256)
+tc_dot_finish_kernel(int rows, int N, long long total, float bias, int relu, const float *__restrict__ partial,
+                     float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long g = i / N;
+    const int n = (int)(i - g * N);
+    const float *src = partial + (size_t)g * rows * N + n;
+    float acc = __ldg(src);
+    for (int r = 1; r < rows; ++r) acc = __fadd_rn(acc, __ldg(src + (size_t)r * N));
+    acc = __fadd_rn(acc, bias);
+    out[i] = relu ? fmaxf(acc, 0.f) : acc;
+}
+}  // namespace jmb
+
+extern "C" int jmb_tc_dot_finish(int G, int rows, int N, const float *partial, float bias, int relu, float *out,
+                                 void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(G >= 0 && rows > 0 && N >= 0, "tc_dot_finish: bad sizes");
+    if (G == 0 || N == 0) return JMB_OK;
+    JMB_REQUIRE(partial && out, "tc_dot_finish: null pointer");
+    const long long total = (long long)G * N;
+    JMB_REQUIRE(total < (1LL << 40), "tc_dot_finish: too many columns");
+    tc_dot_finish_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(rows, N, total, bias, relu, partial, out);
+    return check_launch("tc_dot_finish");
+}
 
 // 3x3 convolution, padding 1, stride 1 or 2, bias + optional ReLU, channels-last in and out, on the same kernel: an implicit
 // GEMM whose X operand rows are the 128-byte channel runs of the input pixels under the nine taps (zero-filled outside the

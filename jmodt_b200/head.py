@@ -79,8 +79,12 @@ def _pack_stack(seq) -> List[tc.PackedLayer]:
 def run_stack(packed: List[tc.PackedLayer], x: torch.Tensor, pool: int = 0, point_major_out: bool = False) -> torch.Tensor:
     """x (G, K, N) through the layers; the last one max-pools over `pool` columns, or (point_major_out) writes
     (G, N, M) directly — the `.transpose(1, 2).contiguous()` of the reference heads (rpn.py:76-77) for free."""
+    fold = len(packed) >= 2 and packed[-1].M == 1 and not pool      # C -> 1 tail: folded into the previous layer's epilogue
     for i, layer in enumerate(packed):
         last = i == len(packed) - 1
+        if fold and i == len(packed) - 2:
+            x = tc.mlp_layer_dot(layer, packed[-1], x)
+            break
         pm = point_major_out and last and layer.M > 1
         x = tc.mlp_layer(layer, x, pool=pool if last else 0, point_major_out=pm)
     if point_major_out and packed[-1].M == 1:

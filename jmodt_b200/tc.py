@@ -162,6 +162,34 @@ def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None =
     return y
 
 
+def mlp_layer_dot(layer: PackedLayer, last: PackedLayer, x: torch.Tensor) -> torch.Tensor:
+    """last(layer(x)) in ONE launch when `last` has a single output channel: x (G, K, N) -> (G, 1, N).  The epilogue of
+    `layer` multiplies its activated rows by `last`'s weights and reduces them per 32-row block in fp32 (deterministic
+    order); the 4 * ceil(M / 128) partial rows and `last`'s bias are added here.  Saves the (G, M, N) activation and a
+    launch whose 128-row tile would hold one useful row."""
+    assert x.dim() == 3 and x.is_contiguous() and x.dtype == torch.float32
+    assert last.M == 1 and last.K == layer.M and last._w32 is not None
+    G, K, N = x.shape
+    assert K == layer.K
+    Mt = -(-layer.M // BM)
+    if getattr(last, "_dot_vec", None) is None:
+        v = torch.zeros(Mt * BM, dtype=torch.float32, device=last._w32.device)
+        v[: layer.M] = last._w32.reshape(-1)
+        last._dot_vec = v
+    partial = torch.empty((G, 4 * Mt, N), dtype=torch.float32, device=x.device)
+    st = _lib.stream_and_device(x)
+    profiler.launch(2.0 * (layer.M + 1) * K * G * N, lambda: _lib.check(
+        _lib.lib().jmb_tc_mlp_layer_dot(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, K, G, N, x.data_ptr(),
+                                        K * N, N, int(layer.relu), last._dot_vec.data_ptr(), partial.data_ptr(), st),
+        "tc_mlp_layer_dot"), desc=f"dense M={layer.M} K={K} G={G} N={N} dot")
+    if getattr(last, "_dot_bias", None) is None:
+        last._dot_bias = float(last.bias[0].item())      # host copy, made once (not during a graph capture)
+    y = torch.empty((G, 1, N), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().jmb_tc_dot_finish(G, 4 * Mt, N, partial.data_ptr(), last._dot_bias, int(last.relu), y.data_ptr(), st),
+               "tc_dot_finish")
+    return y
+
+
 def grouped_first_layer(layer: PackedLayer, xyz: torch.Tensor, feats: torch.Tensor | None,
                         idx: torch.Tensor | None, centres: torch.Tensor | None, nsample: int,
                         *, pool: int = 0) -> torch.Tensor:

@@ -153,3 +153,30 @@ def test_sa_fused_single_kernel_matches_layerwise_and_torch(cuda, C, npoint, ns,
     for w, b in ws:
         x = (torch.einsum("mk,gkps->gmps", w.double(), x) + b.double()[None, :, None, None]).clamp_min(0)
     _check(got.double(), x.max(dim=3)[0], tol=5e-5)
+
+
+@pytest.mark.parametrize("G,K,N,M,relu", [(4, 512, 16384, 512, True), (8, 128, 4096, 128, True), (1, 512, 1024, 256, True),
+                                          (3, 96, 100, 46, False), (8, 64, 32, 128, True), (2, 256, 37, 200, True)])
+def test_single_output_tail_folded_into_the_previous_epilogue(cuda, G, K, N, M, relu):
+    """tc.mlp_layer_dot: layer (K -> M, bias, ReLU) followed by a M -> 1 layer in one launch (the C -> 1 tails of the cls /
+    link / start-end heads) against fp64; ragged N, several M tiles, narrow groups packed into one tile; bit-identical
+    when the columns are split differently (the sharded affinity relies on it)."""
+    from jmodt_b200 import tc
+    g = torch.Generator(device="cpu").manual_seed(K * 7 + N)
+    w1, b1 = torch.randn(M, K, generator=g) / K ** 0.5, torch.randn(M, generator=g)
+    w2, b2 = torch.randn(1, M, generator=g) / M ** 0.5, torch.randn(1, generator=g)
+    x = torch.randn(G, K, N, generator=g)
+    l1 = tc.PackedLayer(w1.to(cuda), b1.to(cuda), relu)
+    l2 = tc.PackedLayer(w2.to(cuda), b2.to(cuda), False)
+    xd = x.to(cuda).contiguous()
+    got = tc.mlp_layer_dot(l1, l2, xd)
+    h = torch.einsum("mk,gkn->gmn", w1.double(), x.double()) + b1.double()[None, :, None]
+    if relu:
+        h = h.clamp_min(0)
+    want = torch.einsum("om,gmn->gon", w2.double(), h) + b2.double()
+    assert got.shape == (G, 1, N)
+    _check(got.cpu().double(), want)
+    assert torch.equal(tc.mlp_layer_dot(l1, l2, xd), got)
+    if N % 8 == 0 and N >= 256:       # the same columns as one group of half the width twice over
+        half = tc.mlp_layer_dot(l1, l2, xd[:, :, : N // 2].contiguous())
+        assert torch.equal(half, got[:, :, : N // 2])
