@@ -235,15 +235,16 @@ JMB_API int jmb_feature_gather_nhwc(int b, int c, int h, int w, int n, const flo
  *   grid_sample(relu(image_fusion_bn(image_fusion_conv(cat_i DeConv_i(img_i)))), xy)   -> out (b, 32, n)
  * evaluated only at the four bilinear taps of every point, so neither full-resolution map is written.
  * m0..m3: channels-last source maps (b, h >> (i+1), w >> (i+1), c_i), c_i multiples of 64, sum <= 1024; h, w multiples
- * of 16 (the padded image, 384 x 1280).  wexp (256, sum c_i / 32, 2, 16, 32): for phase (y mod 16) * 16 + (x mod 16) and
- * 32-channel chunk k of the concatenated levels, the (16 out, 32 in) slice DeConv_i.weight[chunk, :, y mod s_i, x mod s_i]^T
- * as two planes hi + lo (hi = the value with the low 13 mantissa bits cleared, lo = the exact remainder: the products run
- * on TF32 tensor-core instructions as xh wh + xl wh + xh wl);
+ * of 16 (the padded image, 384 x 1280).  wexp (256, sum c_i / 32, 2, 16, 16) 32-bit words: for phase
+ * (y mod 16) * 16 + (x mod 16) and 32-channel chunk k of the concatenated levels, the (16 out, 32 in) slice
+ * DeConv_i.weight[chunk, :, y mod s_i, x mod s_i]^T as two planes hi + lo of bf16 PAIRS along the input channel (even
+ * channel in the low half; hi = bf16(w), lo = bf16(w - hi): the products run on bf16 tensor-core instructions as
+ * xh wh + xl wh + xh wl, fp32 accumulate);
  * w1 (32, 64) / b1 (32): image_fusion_conv with the BatchNorm (eval) affine and the DeConv biases folded in.
  * workspace: jmb_decode_workspace_bytes(b, n) bytes, 16-byte aligned.  Six launches on `stream`. */
 JMB_API long long jmb_decode_workspace_bytes(int b, int n);
 JMB_API int jmb_decode_gather(int b, int n, int h, int w, const float *xy, const float *m0, const float *m1,
-                              const float *m2, const float *m3, int c0, int c1, int c2, int c3, const float *wexp,
+                              const float *m2, const float *m3, int c0, int c1, int c2, int c3, const void *wexp,
                               const float *w1, const float *b1, void *workspace, float *out, void *stream);
 
 /* HOST helpers of the reference's roipool3d module (roipool3d.cpp:97-195 `pts_in_boxes3d_cpu`, `roipool3d_cpu`; called by

@@ -17,7 +17,7 @@
 //   3. combine  a thread per point blends its four samples with the bilinear weights in the reference's nw, ne, sw, se
 //               order and writes the channel-first (B, 32, N) result the fusion layer consumes.
 // Work drops from 17.1 GFLOP per frame (dense) to <= 2.3 GFLOP, and nothing of full resolution is ever written.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace jmb {
 
@@ -31,7 +31,7 @@ constexpr int DG_KC = 32;                 // channels per staged chunk
 constexpr int DG_R = 16;                  // decoder outputs per level (cfg.LI_FUSION.DeConv_Reduce)
 constexpr int DG_CAT = DG_LEVELS * DG_R;  // concatenated decoder channels
 constexpr int DG_OUT = 32;                // fused channels (cfg.LI_FUSION.IMG_FEATURES_CHANNEL / 4)
-constexpr int DG_ROW = DG_KC + 4;         // padded shared-memory row, floats (conflict-free 128-bit reads)
+constexpr int DG_ROW = DG_KC + 8;         // padded shared-memory row, floats (conflict-free 64-bit fragment reads)
 constexpr int DG_MAX_CHUNKS = 32;
 // bins workspace (ints): histogram, first sample of a bin, first tile of a bin, fill cursor
 constexpr int DG_OFF_HIST = 0, DG_OFF_BIN = 256, DG_OFF_TILE = 256 + 257, DG_OFF_CUR = 256 + 2 * 257;
@@ -125,18 +125,18 @@ struct DgParams {
     int n_chunks;
     int B, N, H, W;
     const float *xy;
-    const float *wexp;               // (256 phases, n_chunks, [hi, lo], 16, 32)
+    const uint32_t *wexp;            // (256 phases, n_chunks, [hi, lo], 16, 16) packed bf16 pairs (k even in the low half)
     const float *w1;                 // (32, 64): 1x1 convolution with the BatchNorm scale folded in
     const float *b1;                 // (32): its bias with BatchNorm shift and the decoder biases folded in
     const int *bins, *items;
     float *taps;                     // (B * N * 4, 32)
 };
 
-constexpr int DG_WP = DG_KC + 4;          // padded weight row: conflict-free fragment reads
-constexpr int DG_SRC_FLOATS = DG_TILE * DG_ROW, DG_W_FLOATS = 2 * DG_R * DG_WP;      // hi and lo planes
-constexpr int DG_W1P = DG_OUT + 4;        // padded row of the transposed 1x1 weights
-constexpr int DG_W1_FLOATS = 2 * DG_CAT * DG_W1P;
-constexpr size_t DG_SMEM = (size_t)(2 * (DG_SRC_FLOATS + DG_W_FLOATS) + DG_W1_FLOATS) * 4 +
+constexpr int DG_WP = DG_KC / 2 + 4;      // padded weight row in 32-bit words (two bf16 each): conflict-free fragment reads
+constexpr int DG_SRC_FLOATS = DG_TILE * DG_ROW, DG_W_WORDS = 2 * DG_R * DG_WP;      // hi and lo planes
+constexpr int DG_W1P = DG_OUT + 8;        // padded row of the packed 1x1 weights
+constexpr int DG_W1_WORDS = 2 * (DG_CAT / 2) * DG_W1P;
+constexpr size_t DG_SMEM = (size_t)(2 * (DG_SRC_FLOATS + DG_W_WORDS) + DG_W1_WORDS) * 4 +
                            (size_t)DG_TILE * 4 + (size_t)DG_LEVELS * DG_TILE * 4;
 
 __device__ __forceinline__ void dg_cp16(void *dst, const void *src) {
@@ -144,39 +144,36 @@ __device__ __forceinline__ void dg_cp16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 
-// D (16 x 8) += A (16 x 8, row) * B (8 x 8, col) on the warp-level tensor-core path, TF32 operands (the hardware reads the
-// upper 19 bits of each fp32 operand), fp32 accumulation.  lane = 4 g + q:
-//   a0 (g, q)  a1 (g + 8, q)  a2 (g, q + 4)  a3 (g + 8, q + 4);   b0 (k = q, n = g)  b1 (k = q + 4, n = g);
+// D (16 x 8) += A (16 x 16, row) * B (16 x 8, col) on the warp-level tensor-core path, bf16 operands (two per register,
+// the lower k in the low half), fp32 accumulation.  lane = 4 g + q:
+//   a0 (g, 2q..2q+1)  a1 (g + 8, 2q..)  a2 (g, 2q + 8..)  a3 (g + 8, 2q + 8..);   b0 (k = 2q..2q+1, n = g)  b1 (k = 2q + 8.., n = g);
 //   c0 (g, 2q)  c1 (g, 2q + 1)  c2 (g + 8, 2q)  c3 (g + 8, 2q + 1)
 __device__ __forceinline__ void dg_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                  "{%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// x = hi + lo exactly, hi = the TF32 the tensor core sees for x, |lo| < 2^-10 |x|
-__device__ __forceinline__ void dg_split(float x, uint32_t &hi, uint32_t &lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
 
-// fp32-grade products from TF32 tensor-core instructions: x w = xh wh + xl wh + xh wl (+ xl wl < 2^-20 |x w|, dropped).
-// A warp owns 64 samples (four 16-row tiles) and all 16 decoder outputs of the level being accumulated (two 8-column
-// tiles); the samples' source rows are the A operand straight out of the staging buffer (pitch 36 floats: every fragment
-// read is conflict-free), split in registers; the phase's weights arrive pre-split (hi / lo planes) as the B operand.
-// When a level is done its accumulator fragments ARE the A fragments of the folded 1x1 convolution (K = that level's 16
-// channels in the order the accumulator columns come in), so the concatenated 64-channel vector never leaves registers.
-// The first versions ran this on FFMA (4 x 4, then 16 x 2 register tiles, then packed fma.f32x2): 921 / 730 / 722 us for
-// 8 frames, bound by shared-memory wavefronts plus FFMA issue with two warps per scheduler; this one takes 503 us.
-// Measured apart (8 frames): the source-row gathers alone 342 us (2.0 GB of 128-byte L2 reads = 5.9 TB/s), the MMAs alone
-// 342 us (legacy HMMA pipe ~ 1/9 of the tcgen05 TF32 rate); a 4-stage ring of 16-channel chunks was slower (624 us).
+// fp32-grade products from bf16 tensor-core instructions, as in tc_gemm.cu: x = xh + xl (two bf16, residual 2^-17),
+// x w = xh wh + xl wh + xh wl (+ xl wl <= 2^-16 |x w|, dropped).
+// A warp owns 32 samples (two 16-row tiles) and all 16 decoder outputs of the level being accumulated (two 8-column
+// tiles); the samples' source rows are the A operand straight out of the staging buffer (pitch 40 floats: every 64-bit
+// fragment read is conflict-free), split in registers; the phase's weights arrive pre-split and packed (hi / lo planes of
+// bf16 pairs) as the B operand.  When a level is done its accumulator fragments ARE the A fragments of the folded 1x1
+// convolution (K = that level's 16 channels: accumulator columns 2q, 2q + 1 are exactly the k pairs of an A register), so
+// the concatenated 64-channel vector never leaves registers.
+// History (8 frames): FFMA 4 x 4 / 16 x 2 register tiles / packed fma.f32x2: 921 / 730 / 722 us, bound by shared-memory
+// wavefronts plus FFMA issue; TF32 m16n8k8 with a hi / lo split: 503 us, with the source-row gathers alone at 342 us
+// (2.0 GB of 128-byte L2 reads = 5.9 TB/s) and the MMAs alone at 342 us (the legacy HMMA pipe runs at ~1/9 of the tcgen05
+// rate); a 4-stage ring of 16-channel chunks was slower (624 us).  bf16 m16n8k16 halves the MMA count.
 __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_constant__ DgParams p) {
     extern __shared__ __align__(16) float dg_smem[];
-    float *s_src = dg_smem;                                        // [2][512][36]
-    float *s_w = s_src + 2 * DG_SRC_FLOATS;                        // [2][hi, lo][16][36]
-    float *s_w1 = s_w + 2 * DG_W_FLOATS;                           // [hi, lo][64 concat channels][36]
-    int *s_item = reinterpret_cast<int *>(s_w1 + DG_W1_FLOATS);    // [512]
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(s_item + DG_TILE);   // [4][512]: element offset of the source row
+    float *s_src = dg_smem;                                                   // [2][512][40]
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_src + 2 * DG_SRC_FLOATS);   // [2][hi, lo][16][20]
+    uint32_t *s_w1 = s_w + 2 * DG_W_WORDS;                                     // [hi, lo][32 channel pairs][40]
+    int *s_item = reinterpret_cast<int *>(s_w1 + DG_W1_WORDS);                 // [512]
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(s_item + DG_TILE);          // [4][512]: element offset of the source row
 
     const int tile = blockIdx.x;
     const int *tile_start = p.bins + DG_OFF_TILE, *bin_start = p.bins + DG_OFF_BIN;
@@ -202,18 +199,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
             s_off[l * DG_TILE + s] = (uint32_t)((((size_t)b * hl + (y >> (l + 1))) * wl + (x >> (l + 1))) * p.C[l]);
         }
     }
-    for (int e = t; e < DG_OUT * DG_CAT; e += DG_THREADS) {       // w1 (32, 64) -> hi / lo planes of s_w1[k][o]
-        const int o = e / DG_CAT, k = e - o * DG_CAT;
+    for (int e = t; e < (DG_CAT / 2) * DG_OUT; e += DG_THREADS) {       // w1 (32, 64) -> hi / lo planes of s_w1[k pair][o]
+        const int kw = e / DG_OUT, o = e - kw * DG_OUT;
         uint32_t wh, wl;
-        dg_split(__ldg(p.w1 + e), wh, wl);
-        s_w1[k * DG_W1P + o] = __uint_as_float(wh);
-        s_w1[(DG_CAT + k) * DG_W1P + o] = __uint_as_float(wl);
+        split2(__ldg(p.w1 + o * DG_CAT + 2 * kw), __ldg(p.w1 + o * DG_CAT + 2 * kw + 1), wh, wl);
+        s_w1[kw * DG_W1P + o] = wh;
+        s_w1[(DG_CAT / 2 + kw) * DG_W1P + o] = wl;
     }
     __syncthreads();
 
-    const float *wbin = p.wexp + (size_t)bin * p.n_chunks * (2 * DG_R * DG_KC);
+    const uint32_t *wbin = p.wexp + (size_t)bin * p.n_chunks * (2 * DG_R * DG_KC / 2);
     // a chunk = 32 channels of one level: 512 source rows of 128 bytes (8 lanes per row, four rows per warp access) and the
-    // two 16 x 32 weight planes of the CTA's phase
+    // two 16 x 16-word weight planes of the CTA's phase
     auto stage = [&](int c, int buf) {
         const int l = p.chunk_level[c];
         const float *base = p.map[l] + p.chunk_ch[c];
@@ -222,8 +219,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
 #pragma unroll 4
         for (int r = t >> 3; r < DG_TILE; r += DG_THREADS / 8)
             dg_cp16(dst + r * DG_ROW + part * 4, base + s_off[l * DG_TILE + r] + part * 4);
-        if (t < 2 * DG_R * DG_KC / 4)
-            dg_cp16(s_w + buf * DG_W_FLOATS + (t >> 3) * DG_WP + part * 4, wbin + (size_t)c * (2 * DG_R * DG_KC) + t * 4);
+        if (t < 2 * DG_R * DG_KC / 8)
+            dg_cp16(s_w + buf * DG_W_WORDS + (t >> 2) * DG_WP + (t & 3) * 4, wbin + (size_t)c * (2 * DG_R * DG_KC / 2) + t * 4);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -250,63 +247,70 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const float *src = s_src + buf * DG_SRC_FLOATS + (warp * (16 * DG_MT) + g) * DG_ROW + q;
-        const uint32_t *wh = reinterpret_cast<const uint32_t *>(s_w + buf * DG_W_FLOATS) + g * DG_WP + q;
+        const float *src = s_src + buf * DG_SRC_FLOATS + (warp * (16 * DG_MT) + g) * DG_ROW + 2 * q;
+        const uint32_t *wh = s_w + buf * DG_W_WORDS + g * DG_WP + q;
         const uint32_t *wl = wh + DG_R * DG_WP;
 #pragma unroll
-        for (int k = 0; k < DG_KC; k += 8) {
+        for (int ks = 0; ks < DG_KC / 16; ++ks) {
             uint32_t bh[2][2], bl[2][2];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                bh[nt][0] = wh[nt * 8 * DG_WP + k]; bh[nt][1] = wh[nt * 8 * DG_WP + k + 4];
-                bl[nt][0] = wl[nt * 8 * DG_WP + k]; bl[nt][1] = wl[nt * 8 * DG_WP + k + 4];
+                bh[nt][0] = wh[nt * 8 * DG_WP + ks * 8]; bh[nt][1] = wh[nt * 8 * DG_WP + ks * 8 + 4];
+                bl[nt][0] = wl[nt * 8 * DG_WP + ks * 8]; bl[nt][1] = wl[nt * 8 * DG_WP + ks * 8 + 4];
             }
+            uint32_t ah[DG_MT][4], al[DG_MT][4];
 #pragma unroll
             for (int mt = 0; mt < DG_MT; ++mt) {
-                const float *r0 = src + mt * 16 * DG_ROW + k;
-                uint32_t ah[4], al[4];
-                dg_split(r0[0], ah[0], al[0]);
-                dg_split(r0[8 * DG_ROW], ah[1], al[1]);
-                dg_split(r0[4], ah[2], al[2]);
-                dg_split(r0[8 * DG_ROW + 4], ah[3], al[3]);
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    dg_mma(acc[mt][nt], al, bh[nt][0], bh[nt][1]);
-                    dg_mma(acc[mt][nt], ah, bl[nt][0], bl[nt][1]);
-                    dg_mma(acc[mt][nt], ah, bh[nt][0], bh[nt][1]);
-                }
+                const float *r0 = src + mt * 16 * DG_ROW + ks * 16;
+                const float2 x0 = *reinterpret_cast<const float2 *>(r0), x1 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW);
+                const float2 x2 = *reinterpret_cast<const float2 *>(r0 + 8), x3 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW + 8);
+                split2(x0.x, x0.y, ah[mt][0], al[mt][0]);
+                split2(x1.x, x1.y, ah[mt][1], al[mt][1]);
+                split2(x2.x, x2.y, ah[mt][2], al[mt][2]);
+                split2(x3.x, x3.y, ah[mt][3], al[mt][3]);
             }
+            // three passes over the accumulator tiles: the MMAs that update the same accumulator are several issues apart
+#pragma unroll
+            for (int mt = 0; mt < DG_MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+            for (int mt = 0; mt < DG_MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+            for (int mt = 0; mt < DG_MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
         }
         const int l = p.chunk_level[c];
         if (c + 1 == p.n_chunks || p.chunk_level[c + 1] != l) {
-            // level finished: folded 1x1 convolution with this level's 16 concat channels as K.  Accumulator columns 2q,
-            // 2q + 1 of output tile j are K slots q, q + 4 of step j, so the matching weight rows are 16 l + 8 j + 2q (+ 1).
-            const uint32_t *w1h = reinterpret_cast<const uint32_t *>(s_w1) + (l * DG_R + 2 * q) * DG_W1P + g;
-            const uint32_t *w1l = w1h + DG_CAT * DG_W1P;
+            // level finished: folded 1x1 convolution with this level's 16 concat channels as K (one k16 step)
+            const uint32_t *w1h = s_w1 + (l * (DG_R / 2) + q) * DG_W1P + g;
+            const uint32_t *w1l = w1h + (DG_CAT / 2) * DG_W1P;
+            uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint32_t bh[4][2], bl[4][2];
+            for (int nt = 0; nt < 4; ++nt) {
+                bh[nt][0] = w1h[nt * 8]; bh[nt][1] = w1h[4 * DG_W1P + nt * 8];
+                bl[nt][0] = w1l[nt * 8]; bl[nt][1] = w1l[4 * DG_W1P + nt * 8];
+            }
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    bh[nt][0] = w1h[(8 * j) * DG_W1P + nt * 8]; bh[nt][1] = w1h[(8 * j + 1) * DG_W1P + nt * 8];
-                    bl[nt][0] = w1l[(8 * j) * DG_W1P + nt * 8]; bl[nt][1] = w1l[(8 * j + 1) * DG_W1P + nt * 8];
-                }
+            for (int mt = 0; mt < DG_MT; ++mt) {
+                uint32_t ah[4], al[4];
+                split2(acc[mt][0][0], acc[mt][0][1], ah[0], al[0]);
+                split2(acc[mt][0][2], acc[mt][0][3], ah[1], al[1]);
+                split2(acc[mt][1][0], acc[mt][1][1], ah[2], al[2]);
+                split2(acc[mt][1][2], acc[mt][1][3], ah[3], al[3]);
 #pragma unroll
-                for (int mt = 0; mt < DG_MT; ++mt) {
-                    uint32_t ah[4], al[4];
-                    dg_split(acc[mt][j][0], ah[0], al[0]);
-                    dg_split(acc[mt][j][2], ah[1], al[1]);
-                    dg_split(acc[mt][j][1], ah[2], al[2]);
-                    dg_split(acc[mt][j][3], ah[3], al[3]);
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], al, bh[nt][0], bh[nt][1]);
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        dg_mma(h[mt][nt], al, bh[nt][0], bh[nt][1]);
-                        dg_mma(h[mt][nt], ah, bl[nt][0], bl[nt][1]);
-                        dg_mma(h[mt][nt], ah, bh[nt][0], bh[nt][1]);
-                    }
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], ah, bl[nt][0], bl[nt][1]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-                }
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], ah, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
             }
         }
         __syncthreads();       // buffer `buf` is refilled by the stage() of the next iteration
@@ -417,7 +421,7 @@ extern "C" int jmb_feature_gather_nhwc(int b, int c, int h, int w, int n, const 
 }
 
 extern "C" int jmb_decode_gather(int b, int n, int h, int w, const float *xy, const float *m0, const float *m1,
-                                 const float *m2, const float *m3, int c0, int c1, int c2, int c3, const float *wexp,
+                                 const float *m2, const float *m3, int c0, int c1, int c2, int c3, const void *wexp,
                                  const float *w1, const float *b1, void *workspace, float *out, void *stream) {
     using namespace jmb;
     JMB_REQUIRE(b >= 0 && n >= 0 && h > 0 && w > 0, "decode_gather: bad sizes");
@@ -445,7 +449,7 @@ extern "C" int jmb_decode_gather(int b, int n, int h, int w, const float *xy, co
     int *bins = static_cast<int *>(workspace);
     int *items = bins + ((DG_BINS_INTS + 3) / 4) * 4;
     float *taps = reinterpret_cast<float *>(items + ((samples + 3) / 4) * 4);
-    p.B = b; p.N = n; p.H = h; p.W = w; p.xy = xy; p.wexp = wexp; p.w1 = w1; p.b1 = b1;
+    p.B = b; p.N = n; p.H = h; p.W = w; p.xy = xy; p.wexp = static_cast<const uint32_t *>(wexp); p.w1 = w1; p.b1 = b1;
     p.bins = bins; p.items = items; p.taps = taps;
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;

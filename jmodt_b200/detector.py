@@ -294,10 +294,12 @@ class PointNet2MSG(nn.Module):
             w1, b1 = tc.fold_conv_bn(self.image_fusion_conv, self.image_fusion_bn)
             b1 = b1 + w1 @ torch.cat(biases)
             w = torch.cat(chunks, dim=1).contiguous()                         # (256, chunks, 16, 32)
-            # the kernel multiplies on TF32 tensor-core instructions with an exact hi + lo split of both operands:
-            # hi = the 19 bits the hardware reads, lo = the rest (w = hi + lo exactly)
-            hi = (w.view(torch.int32) & -8192).view(torch.float32)
-            d["_dec_pack"] = (torch.stack([hi, w - hi], dim=2).contiguous(), w1.contiguous(), b1.contiguous())
+            # the kernel multiplies on bf16 tensor-core instructions with a hi + lo split of both operands (fp32-grade, as
+            # the layer kernels): two planes of bf16 pairs along the input channel, packed into 32-bit words
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            wexp = torch.stack([hi, lo], dim=2).contiguous().view(torch.int32)      # (256, chunks, 2, 16, 16)
+            d["_dec_pack"] = (wexp, w1.contiguous(), b1.contiguous())
             d["_dec_token"] = tok
         return d["_dec_pack"]
 

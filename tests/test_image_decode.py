@@ -51,8 +51,8 @@ def test_decoder_pack_reproduces_dense_pixels_on_cpu():
     maps = _maps(1, 32, 64)
     _, fused = _dense(net, maps, torch.zeros(1, 1, 2))
     wexp, w1, b1 = net._decoder_pack()
-    assert wexp.shape == (256, 30, 2, 16, 32)
-    wexp = wexp.sum(dim=2)                 # hi + lo planes and w1.shape == (32, 64) and b1.shape == (32,)
+    assert wexp.shape == (256, 30, 2, 16, 16) and wexp.dtype == torch.int32 and w1.shape == (32, 64) and b1.shape == (32,)
+    wexp = wexp.view(torch.bfloat16).float().sum(dim=2)          # hi + lo planes of bf16 pairs -> (256, 30, 16, 32)
     rng = np.random.default_rng(0)
     for _ in range(40):
         y, x = int(rng.integers(0, 32)), int(rng.integers(0, 64))
