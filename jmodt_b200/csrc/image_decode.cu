@@ -24,9 +24,9 @@ namespace jmb {
 constexpr int DG_LEVELS = 4;
 constexpr int DG_PH = 16;                 // largest stride: 16 x 16 phases
 constexpr int DG_BINS = DG_PH * DG_PH;
-constexpr int DG_TILE = 512;              // samples per CTA
+constexpr int DG_PTS = 128;               // points per CTA
+constexpr int DG_TILE = 4 * DG_PTS;       // samples (point, tap) per CTA = staged source rows per level at most
 constexpr int DG_THREADS = 512;
-constexpr int DG_MT = DG_TILE / (DG_THREADS / 32) / 16;      // 16-sample tiles per warp
 constexpr int DG_KC = 32;                 // channels per staged chunk
 constexpr int DG_R = 16;                  // decoder outputs per level (cfg.LI_FUSION.DeConv_Reduce)
 constexpr int DG_CAT = DG_LEVELS * DG_R;  // concatenated decoder channels
@@ -64,7 +64,7 @@ __device__ __forceinline__ DgTaps dg_taps(float gx, float gy, int h, int w) {
 
 __device__ __forceinline__ int dg_phase(int x, int y) { return (y & (DG_PH - 1)) * DG_PH + (x & (DG_PH - 1)); }
 
-// ---- 1. plan: counting sort of the valid (point, tap) samples by phase ----------------------------------------------
+// ---- 1. plan: counting sort of the points (those with a tap inside the image) by the phase of their nw tap --------------
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 dg_bin_kernel(int total, int h, int w, const float *__restrict__ xy, int *__restrict__ bins, int *__restrict__ items) {
@@ -72,17 +72,14 @@ dg_bin_kernel(int total, int h, int w, const float *__restrict__ xy, int *__rest
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int ph[4], rank[4];
-    bool ok[4] = {false, false, false, false};
+    int ph = 0, rank = 0;
+    bool ok = false;
     if (p < total) {
         const DgTaps t = dg_taps(__ldg(xy + (size_t)p * 2), __ldg(xy + (size_t)p * 2 + 1), h, w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            ok[i] = t.valid[i];
-            if (ok[i]) {
-                ph[i] = dg_phase(t.x[i], t.y[i]);
-                rank[i] = atomicAdd(&s_cnt[ph[i]], 1);
-            }
+        ok = t.valid[0] || t.valid[1] || t.valid[2] || t.valid[3];
+        if (ok) {
+            ph = dg_phase(t.x[0], t.y[0]);
+            rank = atomicAdd(&s_cnt[ph], 1);
         }
     }
     __syncthreads();
@@ -93,9 +90,7 @@ dg_bin_kernel(int total, int h, int w, const float *__restrict__ xy, int *__rest
     }
     s_base[threadIdx.x] = c ? atomicAdd(bins + DG_OFF_CUR + threadIdx.x, c) : 0;
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (ok[i]) items[s_base[ph[i]] + rank[i]] = p * 4 + i;
+    if (ok) items[s_base[ph] + rank] = p;
 }
 
 __global__ void __launch_bounds__(DG_BINS) dg_scan_kernel(int *__restrict__ bins) {
@@ -103,7 +98,7 @@ __global__ void __launch_bounds__(DG_BINS) dg_scan_kernel(int *__restrict__ bins
     const int t = threadIdx.x;
     const int c = bins[DG_OFF_HIST + t];
     s_a[t] = c;
-    s_t[t] = (c + DG_TILE - 1) / DG_TILE;
+    s_t[t] = (c + DG_PTS - 1) / DG_PTS;
     __syncthreads();
     for (int d = 1; d < DG_BINS; d <<= 1) {       // inclusive Hillis-Steele scans
         const int a = t >= d ? s_a[t - d] : 0, b = t >= d ? s_t[t - d] : 0;
@@ -133,11 +128,11 @@ struct DgParams {
 };
 
 constexpr int DG_WP = DG_KC / 2 + 4;      // padded weight row in 32-bit words (two bf16 each): conflict-free fragment reads
-constexpr int DG_SRC_FLOATS = DG_TILE * DG_ROW, DG_W_WORDS = 2 * DG_R * DG_WP;      // hi and lo planes
+constexpr int DG_SRC_FLOATS = DG_TILE * DG_ROW, DG_W_WORDS = 4 * 2 * DG_R * DG_WP;      // four tap phases, hi and lo planes
 constexpr int DG_W1P = DG_OUT + 8;        // padded row of the packed 1x1 weights
 constexpr int DG_W1_WORDS = 2 * (DG_CAT / 2) * DG_W1P;
 constexpr size_t DG_SMEM = (size_t)(2 * (DG_SRC_FLOATS + DG_W_WORDS) + DG_W1_WORDS) * 4 +
-                           (size_t)DG_TILE * 4 + (size_t)DG_LEVELS * DG_TILE * 4;
+                           (size_t)3 * DG_PTS * 4 + (size_t)DG_TILE * 4;
 
 __device__ __forceinline__ void dg_cp16(void *dst, const void *src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
@@ -157,24 +152,31 @@ __device__ __forceinline__ void dg_mma(float (&c)[4], const uint32_t (&a)[4], ui
 
 // fp32-grade products from bf16 tensor-core instructions, as in tc_gemm.cu: x = xh + xl (two bf16, residual 2^-17),
 // x w = xh wh + xl wh + xh wl (+ xl wl <= 2^-16 |x w|, dropped).
-// A warp owns 32 samples (two 16-row tiles) and all 16 decoder outputs of the level being accumulated (two 8-column
-// tiles); the samples' source rows are the A operand straight out of the staging buffer (pitch 40 floats: every 64-bit
-// fragment read is conflict-free), split in registers; the phase's weights arrive pre-split and packed (hi / lo planes of
-// bf16 pairs) as the B operand.  When a level is done its accumulator fragments ARE the A fragments of the folded 1x1
-// convolution (K = that level's 16 channels: accumulator columns 2q, 2q + 1 are exactly the k pairs of an A register), so
-// the concatenated 64-channel vector never leaves registers.
+// A CTA takes 128 POINTS whose nw taps share one phase (py, px) — so the phases of their four taps, and which of the taps
+// fall into the neighbouring source pixel at each level, are the same for the whole tile.  Per level it stages the source
+// rows of the 1, 2 or 4 distinct source pixels a point's taps touch (at stride 16 / 8 the four taps nearly always share
+// one source pixel: 1 247 floats per point on average instead of 4 x 960) and the weight slices of the four tap phases.
+// Warp w owns the 16-point tile w & 7 and the taps 2 (w >> 3), 2 (w >> 3) + 1, all 16 decoder outputs of the level being
+// accumulated (two 8-column tiles): the source rows are the A operand straight out of the staging buffer (pitch 40 floats:
+// every 64-bit fragment read is conflict-free), split in registers and shared by both taps when they read the same source
+// pixel; the weights arrive pre-split and packed (hi / lo planes of bf16 pairs) as the B operand.  When a level is done
+// its accumulator fragments ARE the A fragments of the folded 1x1 convolution (K = that level's 16 channels: accumulator
+// columns 2q, 2q + 1 are exactly the k pairs of an A register), so the concatenated 64-channel vector never leaves
+// registers.
 // History (8 frames): FFMA 4 x 4 / 16 x 2 register tiles / packed fma.f32x2: 921 / 730 / 722 us, bound by shared-memory
-// wavefronts plus FFMA issue; TF32 m16n8k8 with a hi / lo split: 503 us, with the source-row gathers alone at 342 us
-// (2.0 GB of 128-byte L2 reads = 5.9 TB/s) and the MMAs alone at 342 us (the legacy HMMA pipe runs at ~1/9 of the tcgen05
-// rate); a 4-stage ring of 16-channel chunks was slower (624 us).  bf16 m16n8k16 halves the MMA count.
+// wavefronts plus FFMA issue; TF32 m16n8k8 with a hi / lo split, tiles of 512 (point, tap) samples of one phase: 503 us,
+// with the source-row gathers alone at 342 us (2.0 GB of 128-byte L2 reads = 5.9 TB/s) and the MMAs alone at 342 us (the
+// legacy HMMA pipe runs at ~1/9 of the tcgen05 rate); a 4-stage ring of 16-channel chunks was slower (624 us); bf16
+// m16n8k16 (half the MMAs): 375 us, gather-bound.
 __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_constant__ DgParams p) {
     extern __shared__ __align__(16) float dg_smem[];
-    float *s_src = dg_smem;                                                   // [2][512][40]
-    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_src + 2 * DG_SRC_FLOATS);   // [2][hi, lo][16][20]
+    float *s_src = dg_smem;                                                   // [2][4 source pixels][128 points][40]
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_src + 2 * DG_SRC_FLOATS);   // [2][4 taps][hi, lo][16][20]
     uint32_t *s_w1 = s_w + 2 * DG_W_WORDS;                                     // [hi, lo][32 channel pairs][40]
-    int *s_item = reinterpret_cast<int *>(s_w1 + DG_W1_WORDS);                 // [512]
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(s_item + DG_TILE);          // [4][512]: element offset of the source row
-
+    int *s_item = reinterpret_cast<int *>(s_w1 + DG_W1_WORDS);                 // [128] point
+    int *s_x0 = s_item + DG_PTS, *s_y0 = s_x0 + DG_PTS;                        // [128] nw tap
+    uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(s_y0 + DG_PTS);          // [4][128]: element offset of the source row
+                                                                               // of the level being staged (~0: not needed)
     const int tile = blockIdx.x;
     const int *tile_start = p.bins + DG_OFF_TILE, *bin_start = p.bins + DG_OFF_BIN;
     if (tile >= __ldg(tile_start + DG_BINS)) return;
@@ -183,21 +185,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
         const int mid = (lo + hi + 1) >> 1;
         if (__ldg(tile_start + mid) <= tile) lo = mid; else hi = mid - 1;
     }
-    const int bin = lo;
-    const int first = __ldg(bin_start + bin) + (tile - __ldg(tile_start + bin)) * DG_TILE;
-    const int cnt = min(DG_TILE, __ldg(bin_start + bin + 1) - first);
+    const int bin = lo, py = bin >> 4, px = bin & 15;
+    const int first = __ldg(bin_start + bin) + (tile - __ldg(tile_start + bin)) * DG_PTS;
+    const int cnt = min(DG_PTS, __ldg(bin_start + bin + 1) - first);
     const int t = threadIdx.x;
-    for (int s = t; s < DG_TILE; s += DG_THREADS) {
-        const int item = __ldg(p.items + first + min(s, cnt - 1));
-        s_item[s] = item;
-        const int pg = item >> 2, tap = item & 3, b = pg / p.N;
+    if (t < DG_PTS) {
+        const int pg = __ldg(p.items + first + min(t, cnt - 1));
+        s_item[t] = pg;
         const DgTaps tp = dg_taps(__ldg(p.xy + (size_t)pg * 2), __ldg(p.xy + (size_t)pg * 2 + 1), p.H, p.W);
-        const int x = tp.x[0] + (tap & 1), y = tp.y[0] + (tap >> 1);
-#pragma unroll
-        for (int l = 0; l < DG_LEVELS; ++l) {
-            const int hl = p.H >> (l + 1), wl = p.W >> (l + 1);
-            s_off[l * DG_TILE + s] = (uint32_t)((((size_t)b * hl + (y >> (l + 1))) * wl + (x >> (l + 1))) * p.C[l]);
-        }
+        s_x0[t] = tp.x[0]; s_y0[t] = tp.y[0];
     }
     for (int e = t; e < (DG_CAT / 2) * DG_OUT; e += DG_THREADS) {       // w1 (32, 64) -> hi / lo planes of s_w1[k pair][o]
         const int kw = e / DG_OUT, o = e - kw * DG_OUT;
@@ -208,82 +204,127 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
     }
     __syncthreads();
 
-    const uint32_t *wbin = p.wexp + (size_t)bin * p.n_chunks * (2 * DG_R * DG_KC / 2);
-    // a chunk = 32 channels of one level: 512 source rows of 128 bytes (8 lanes per row, four rows per warp access) and the
-    // two 16 x 16-word weight planes of the CTA's phase
+    // source rows of level l: slot (oy, ox) holds the rows of the source pixel (y0 >> (l+1)) + oy, (x0 >> (l+1)) + ox; a tap
+    // (dy, dx) reads slot (((py & (s-1)) + dy) >> (l+1), ((px & (s-1)) + dx) >> (l+1)).  Pixels outside the map belong to
+    // taps outside the image (their samples are ignored by the combine step): clamped.
+    auto level_rows = [&](int l) {
+        const int sh = l + 1, sm = (1 << sh) - 1;
+        const int need_ox = ((px & sm) + 1) >> sh, need_oy = ((py & sm) + 1) >> sh;
+        const int hl = p.H >> sh, wl = p.W >> sh;
+        if (t < DG_TILE) {
+            const int slot = t >> 7, i = t & (DG_PTS - 1);
+            const int ox = slot & 1, oy = slot >> 1;
+            uint32_t off = 0xffffffffu;
+            if (ox <= need_ox && oy <= need_oy) {
+                const int pg = s_item[i], b = pg / p.N;
+                const int X = min(max((s_x0[i] >> sh) + ox, 0), wl - 1), Y = min(max((s_y0[i] >> sh) + oy, 0), hl - 1);
+                off = (uint32_t)((((size_t)b * hl + Y) * wl + X) * p.C[l]);
+            }
+            s_rowoff[t] = off;
+        }
+    };
+    // a chunk = 32 channels of one level: up to 512 source rows of 128 bytes (8 lanes per row, four rows per warp access)
+    // and the two 16 x 16-word weight planes of each of the four tap phases
     auto stage = [&](int c, int buf) {
         const int l = p.chunk_level[c];
         const float *base = p.map[l] + p.chunk_ch[c];
         float *dst = s_src + buf * DG_SRC_FLOATS;
         const int part = t & 7;
 #pragma unroll 4
-        for (int r = t >> 3; r < DG_TILE; r += DG_THREADS / 8)
-            dg_cp16(dst + r * DG_ROW + part * 4, base + s_off[l * DG_TILE + r] + part * 4);
-        if (t < 2 * DG_R * DG_KC / 8)
-            dg_cp16(s_w + buf * DG_W_WORDS + (t >> 2) * DG_WP + (t & 3) * 4, wbin + (size_t)c * (2 * DG_R * DG_KC / 2) + t * 4);
+        for (int r = t >> 3; r < DG_TILE; r += DG_THREADS / 8) {
+            const uint32_t off = s_rowoff[r];
+            if (off != 0xffffffffu) dg_cp16(dst + r * DG_ROW + part * 4, base + off + part * 4);
+        }
+        {
+            const int tap = t >> 7, rem = t & 127;            // 4 taps x 128 pieces of 16 bytes
+            const int phase = ((py + (tap >> 1)) & (DG_PH - 1)) * DG_PH + ((px + (tap & 1)) & (DG_PH - 1));
+            dg_cp16(s_w + buf * DG_W_WORDS + tap * (2 * DG_R * DG_WP) + (rem >> 2) * DG_WP + (rem & 3) * 4,
+                    p.wexp + ((size_t)phase * p.n_chunks + c) * (2 * DG_R * DG_KC / 2) + rem * 4);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
-    float acc[DG_MT][2][4], h[DG_MT][4][4];         // [16-sample tile][8-output tile][fragment]
+    const int mt = warp & 7, tap0 = (warp >> 3) * 2;      // this warp: points mt * 16 .. + 15, taps tap0 and tap0 + 1
+    float acc[2][2][4], h[2][4][4];         // [tap][8-output tile][fragment]
 #pragma unroll
-    for (int mt = 0; mt < DG_MT; ++mt) {
+    for (int tt = 0; tt < 2; ++tt) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) acc[tt][nt][i] = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[mt][nt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) h[tt][nt][i] = 0.f;
     }
+    level_rows(p.chunk_level[0]);
+    __syncthreads();
     stage(0, 0);
     for (int c = 0; c < p.n_chunks; ++c) {
         const int buf = c & 1;
+        const int l = p.chunk_level[c];
         if (c + 1 < p.n_chunks) {
+            if (p.chunk_level[c + 1] != l) {          // the next chunk opens a level: its row table first
+                __syncthreads();                      // everyone has issued the copies that read the current table
+                level_rows(p.chunk_level[c + 1]);
+                __syncthreads();
+            }
             stage(c + 1, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const float *src = s_src + buf * DG_SRC_FLOATS + (warp * (16 * DG_MT) + g) * DG_ROW + 2 * q;
-        const uint32_t *wh = s_w + buf * DG_W_WORDS + g * DG_WP + q;
-        const uint32_t *wl = wh + DG_R * DG_WP;
+        const int sh = l + 1, sm = (1 << sh) - 1;
+        // source-pixel slot of each of this warp's two taps (dy = tap0 >> 1 for both, dx = 0 / 1)
+        const int oy = ((py & sm) + (tap0 >> 1)) >> sh;
+        const int slot0 = oy * 2 + ((px & sm) >> sh), slot1 = oy * 2 + (((px & sm) + 1) >> sh);       // (px & sm) >> sh == 0
+        const float *src0 = s_src + buf * DG_SRC_FLOATS + (slot0 * DG_PTS + mt * 16 + g) * DG_ROW + 2 * q;
+        const float *src1 = s_src + buf * DG_SRC_FLOATS + (slot1 * DG_PTS + mt * 16 + g) * DG_ROW + 2 * q;
+        const uint32_t *wbase = s_w + buf * DG_W_WORDS + tap0 * (2 * DG_R * DG_WP) + g * DG_WP + q;
 #pragma unroll
         for (int ks = 0; ks < DG_KC / 16; ++ks) {
-            uint32_t bh[2][2], bl[2][2];
+            uint32_t bh[2][2][2], bl[2][2][2];        // [tap][8-output tile][register]
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                bh[nt][0] = wh[nt * 8 * DG_WP + ks * 8]; bh[nt][1] = wh[nt * 8 * DG_WP + ks * 8 + 4];
-                bl[nt][0] = wl[nt * 8 * DG_WP + ks * 8]; bl[nt][1] = wl[nt * 8 * DG_WP + ks * 8 + 4];
+            for (int tt = 0; tt < 2; ++tt) {
+                const uint32_t *wh = wbase + tt * (2 * DG_R * DG_WP), *wl = wh + DG_R * DG_WP;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    bh[tt][nt][0] = wh[nt * 8 * DG_WP + ks * 8]; bh[tt][nt][1] = wh[nt * 8 * DG_WP + ks * 8 + 4];
+                    bl[tt][nt][0] = wl[nt * 8 * DG_WP + ks * 8]; bl[tt][nt][1] = wl[nt * 8 * DG_WP + ks * 8 + 4];
+                }
             }
-            uint32_t ah[DG_MT][4], al[DG_MT][4];
+            uint32_t ah[2][4], al[2][4];
 #pragma unroll
-            for (int mt = 0; mt < DG_MT; ++mt) {
-                const float *r0 = src + mt * 16 * DG_ROW + ks * 16;
-                const float2 x0 = *reinterpret_cast<const float2 *>(r0), x1 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW);
-                const float2 x2 = *reinterpret_cast<const float2 *>(r0 + 8), x3 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW + 8);
-                split2(x0.x, x0.y, ah[mt][0], al[mt][0]);
-                split2(x1.x, x1.y, ah[mt][1], al[mt][1]);
-                split2(x2.x, x2.y, ah[mt][2], al[mt][2]);
-                split2(x3.x, x3.y, ah[mt][3], al[mt][3]);
+            for (int tt = 0; tt < 2; ++tt) {
+                if (tt == 1 && slot1 == slot0) {      // both taps read the same source pixel (warp-uniform)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ah[1][i] = ah[0][i]; al[1][i] = al[0][i]; }
+                } else {
+                    const float *r0 = (tt ? src1 : src0) + ks * 16;
+                    const float2 x0 = *reinterpret_cast<const float2 *>(r0), x1 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW);
+                    const float2 x2 = *reinterpret_cast<const float2 *>(r0 + 8), x3 = *reinterpret_cast<const float2 *>(r0 + 8 * DG_ROW + 8);
+                    split2(x0.x, x0.y, ah[tt][0], al[tt][0]);
+                    split2(x1.x, x1.y, ah[tt][1], al[tt][1]);
+                    split2(x2.x, x2.y, ah[tt][2], al[tt][2]);
+                    split2(x3.x, x3.y, ah[tt][3], al[tt][3]);
+                }
             }
             // three passes over the accumulator tiles: the MMAs that update the same accumulator are several issues apart
 #pragma unroll
-            for (int mt = 0; mt < DG_MT; ++mt)
+            for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[tt][nt], al[tt], bh[tt][nt][0], bh[tt][nt][1]);
 #pragma unroll
-            for (int mt = 0; mt < DG_MT; ++mt)
+            for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[tt][nt], ah[tt], bl[tt][nt][0], bl[tt][nt][1]);
 #pragma unroll
-            for (int mt = 0; mt < DG_MT; ++mt)
+            for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
+                for (int nt = 0; nt < 2; ++nt) dg_mma(acc[tt][nt], ah[tt], bh[tt][nt][0], bh[tt][nt][1]);
         }
-        const int l = p.chunk_level[c];
         if (c + 1 == p.n_chunks || p.chunk_level[c + 1] != l) {
             // level finished: folded 1x1 convolution with this level's 16 concat channels as K (one k16 step)
             const uint32_t *w1h = s_w1 + (l * (DG_R / 2) + q) * DG_W1P + g;
@@ -295,39 +336,39 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_decode_kernel(const __grid_c
                 bl[nt][0] = w1l[nt * 8]; bl[nt][1] = w1l[4 * DG_W1P + nt * 8];
             }
 #pragma unroll
-            for (int mt = 0; mt < DG_MT; ++mt) {
+            for (int tt = 0; tt < 2; ++tt) {
                 uint32_t ah[4], al[4];
-                split2(acc[mt][0][0], acc[mt][0][1], ah[0], al[0]);
-                split2(acc[mt][0][2], acc[mt][0][3], ah[1], al[1]);
-                split2(acc[mt][1][0], acc[mt][1][1], ah[2], al[2]);
-                split2(acc[mt][1][2], acc[mt][1][3], ah[3], al[3]);
+                split2(acc[tt][0][0], acc[tt][0][1], ah[0], al[0]);
+                split2(acc[tt][0][2], acc[tt][0][3], ah[1], al[1]);
+                split2(acc[tt][1][0], acc[tt][1][1], ah[2], al[2]);
+                split2(acc[tt][1][2], acc[tt][1][3], ah[3], al[3]);
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], al, bh[nt][0], bh[nt][1]);
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[tt][nt], al, bh[nt][0], bh[nt][1]);
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], ah, bl[nt][0], bl[nt][1]);
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[tt][nt], ah, bl[nt][0], bl[nt][1]);
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dg_mma(h[mt][nt], ah, bh[nt][0], bh[nt][1]);
+                for (int nt = 0; nt < 4; ++nt) dg_mma(h[tt][nt], ah, bh[nt][0], bh[nt][1]);
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+                    for (int i = 0; i < 4; ++i) acc[tt][nt][i] = 0.f;
             }
         }
         __syncthreads();       // buffer `buf` is refilled by the stage() of the next iteration
     }
-    // bias (BatchNorm shift and decoder biases folded in) + ReLU; a thread holds fused channels 8 nt + 2q, + 1 of samples
-    // g and g + 8 of each 16-sample tile
+    // bias (BatchNorm shift and decoder biases folded in) + ReLU; a thread holds fused channels 8 nt + 2q, + 1 of points
+    // g and g + 8 of its 16-point tile, for its two taps
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
         const float2 bias = __ldg(reinterpret_cast<const float2 *>(p.b1 + nt * 8 + 2 * q));
 #pragma unroll
-        for (int mt = 0; mt < DG_MT; ++mt) {
+        for (int tt = 0; tt < 2; ++tt) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int s = warp * (16 * DG_MT) + mt * 16 + g + 8 * half;
-                if (s < cnt)
-                    *reinterpret_cast<float2 *>(p.taps + (size_t)s_item[s] * DG_OUT + nt * 8 + 2 * q) =
-                        make_float2(fmaxf(h[mt][nt][2 * half] + bias.x, 0.f), fmaxf(h[mt][nt][2 * half + 1] + bias.y, 0.f));
+                const int i = mt * 16 + g + 8 * half;
+                if (i < cnt)
+                    *reinterpret_cast<float2 *>(p.taps + ((size_t)s_item[i] * 4 + tap0 + tt) * DG_OUT + nt * 8 + 2 * q) =
+                        make_float2(fmaxf(h[tt][nt][2 * half] + bias.x, 0.f), fmaxf(h[tt][nt][2 * half + 1] + bias.y, 0.f));
             }
         }
     }
@@ -401,7 +442,7 @@ feature_gather_nhwc_kernel(int c, int h, int w, int n, const float *__restrict__
 }  // namespace jmb
 
 extern "C" long long jmb_decode_workspace_bytes(int b, int n) {
-    // bins | items (B N 4 ints) | taps (B N 4 x 32 floats)
+    // bins | items (B N ints, laid out for 4 B N) | taps (B N 4 x 32 floats)
     if (b < 0 || n < 0) return -1;
     const long long samples = (long long)b * n * 4;
     return (long long)jmb::DG_BINS_INTS * 4 + 16 + samples * 4 + 16 + samples * jmb::DG_OUT * 4;
@@ -475,7 +516,7 @@ extern "C" int jmb_decode_gather(int b, int n, int h, int w, const float *xy, co
         const int rc = check_launch("decode_gather (fill)");
         if (rc != JMB_OK) return rc;
     }
-    const int max_tiles = (int)(samples / DG_TILE) + DG_BINS;
+    const int max_tiles = total / DG_PTS + DG_BINS;
     dg_decode_kernel<<<max_tiles, DG_THREADS, DG_SMEM, st>>>(p);
     {
         const int rc = check_launch("decode_gather (decode)");
