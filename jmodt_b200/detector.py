@@ -195,8 +195,11 @@ class GeometryPlan:
     feature-propagation level.  `tensors()` lists them in a fixed order; `copy_from()` overwrites this plan's tensors
     with another plan's (same shapes) — the hand-over between two pipelined steps."""
 
-    def __init__(self, sa, fp):
+    def __init__(self, sa, fp, l0_features=None):
         self.sa, self.fp = sa, fp
+        # features of set-abstraction level 0 when the cloud carries coordinates only: that level's MLPs see nothing but
+        # relative coordinates, so it belongs to the coordinate-only stage and is computed with it, one step ahead
+        self.l0_features = l0_features
 
     def tensors(self):
         out = []
@@ -204,6 +207,8 @@ class GeometryPlan:
             out.extend(pl.tensors())
         for i in sorted(self.fp):
             out.extend(self.fp[i])
+        if self.l0_features is not None:
+            out.append(self.l0_features)
         return out
 
     def copy_from(self, other: "GeometryPlan"):
@@ -216,6 +221,7 @@ class PointNet2MSG(nn.Module):
     def __init__(self, input_channels=0, use_xyz=True, cfg: RpnConfig | None = None):
         super().__init__()
         self.cfg = cfg = cfg or RpnConfig()
+        self.input_channels = input_channels
         self.SA_modules = nn.ModuleList()
         channel_in = input_channels
         skip_channel_list = [input_channels]
@@ -335,7 +341,20 @@ class PointNet2MSG(nn.Module):
             xs.append(plan.new_xyz)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):
             fp[i] = self.FP_modules[i].plan(xs[i - 1], xs[i])
-        return GeometryPlan(sa, fp)
+        l0 = None
+        if self.level0_with_geometry and self.input_channels == 0 and sa[0].nbr is not None and not self.training:
+            # xyz-only input: no feature stage feeds this level.  Not event-timed: inside a captured graph the external
+            # event-record nodes of this (side-stream) launch would be ordered with the caller's stage events
+            was, tc.profiler.enabled = tc.profiler.enabled, False
+            try:
+                l0 = self.SA_modules[0](xs[0], None, plan=sa[0])[1]
+            finally:
+                tc.profiler.enabled = was
+        return GeometryPlan(sa, fp, l0)
+
+    # Opt-in (JMB_L0_WITH_GEOMETRY=1): measured 8.15-8.22 ms per step against 8.25 — the step is bound by total SM time, and
+    # the level's two launches then share the SMs with the per-proposal stage of the previous batch
+    level0_with_geometry = os.environ.get("JMB_L0_WITH_GEOMETRY", "0") == "1"
 
     overlap_geometry = True
     # Opt-in (JMB_L0_CHUNKS=8): consume the level-0 FPS output in prefixes while the sampler is still running.  The
@@ -428,7 +447,10 @@ class PointNet2MSG(nn.Module):
             # it runs on a background stream under the chain of small set-abstraction / propagation launches
             decoded = runtime.spawn(lambda: self.decode_gather(image_maps[0], xy))
         for i, sa in enumerate(self.SA_modules):
-            if sa_plans is not None:
+            if i == 0 and geometry is not None and geometry.l0_features is not None and features is None:
+                plan_i = geometry.sa[0]
+                li_xyz, li_features, li_index = plan_i.new_xyz, geometry.l0_features, plan_i.idx
+            elif sa_plans is not None:
                 plan_i, ev = sa_plans[i]
                 if plan_i.nbr is None:     # level 0, consumed in prefixes while FPS runs
                     li_features = self._sa0_chunked(sa, l_xyz[i], l_features[i], plan_i)

@@ -159,7 +159,9 @@ def parallel(*fns):
         return [f() for f in fns]
     main = torch.cuda.current_stream()
     dev = main.device
-    pool = _branch_streams.setdefault(dev, [])
+    # one pool per CALLING stream: two callers on different streams (the step and the coordinate stage of the next batch)
+    # must not queue their branches on the same side stream, or one caller's branch waits behind the other's whole chain
+    pool = _branch_streams.setdefault((dev, main.cuda_stream), [])
     while len(pool) < len(fns) - 1:
         pool.append(torch.cuda.Stream(device=dev))
     fork = torch.cuda.Event()
