@@ -470,11 +470,23 @@ extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dat
                 case 5: return launch_fps_cluster<16, 128, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 6: return launch_fps_cluster<4, 512, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 7: return launch_fps_cluster<16, 64, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 8: return launch_fps<1024, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 9: return launch_fps_cluster<2, 1024, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 10: return launch_fps_cluster<4, 1024, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 11: return launch_fps_cluster<2, 512, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 12: return launch_fps_cluster<2, 256, 32>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 13: return launch_fps_cluster<4, 256, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 14: return launch_fps<512, 32>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 15: return launch_fps_cluster<4, 128, 32>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 16: return launch_fps_cluster<8, 128, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+                case 17: return launch_fps_cluster<8, 64, 32>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 default: break;
             }
         }
-        if (cfg_override > 0 && slots == 4096) {
-            switch (cfg_override) {
+        static int cfg4k = -1;          // JMB_FPS_CFG4K: the same for 4 096-point clouds
+        if (cfg4k < 0) { const char *e = getenv("JMB_FPS_CFG4K"); cfg4k = e ? atoi(e) : 0; }
+        if (cfg4k > 0 && slots == 4096) {
+            switch (cfg4k) {
                 case 1: return launch_fps_cluster<4, 256, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 2: return launch_fps_cluster<8, 128, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
                 case 3: return launch_fps_cluster<4, 128, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
@@ -487,10 +499,13 @@ extern "C" int jmb_furthest_point_sampling(int b, int n, int m, const float *dat
                 default: break;
             }
         }
-        // measured on B200 (profiles/fps_tune.py): 16384 points: 8 CTAs x 256 threads x 8 points = 2.93 ms vs 6.0 ms
-        // for one CTA; at 4096 points the per-iteration exchange latency cancels the gain, so one CTA is kept.
+        // measured on B200: alone, 8 CTAs x 256 threads x 8 points is the fastest shape for 16384 points (2.93 ms vs 6.0 ms
+        // for one CTA, profiles/fps_tune.py) — but the sampler is pure dependency latency, and inside the pipelined step every
+        // SM it holds is an SM the tensor-core kernels of the other stream cannot use: 4 CTAs x 256 threads x 16 points
+        // (half the SMs, 3.15 ms alone) gives 7.62 ms per step against 8.25 (profiles/r02/fps_shapes_in_step.txt).
+        // JMB_FPS_CFG=2 selects the latency shape.
         if (slots > 8192 && slots <= 16384 && (long long)b * 8 <= 2LL * sms)
-            return launch_fps_cluster<8, 256, 8>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
+            return launch_fps_cluster<4, 256, 16>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
         if (slots > 4096 && slots <= 8192 && (long long)b * 8 <= 2LL * sms)
             return launch_fps_cluster<8, 256, 4>(b, n, m, bs, log2bs, S, dataset, temp, idxs, st);
     }
