@@ -200,6 +200,11 @@ JMB_API int jmb_tc_mlp_layer(const void *wpack, const float *bias, int M, int K,
                              const float *xyz, const float *centres, int nsample, int n_pts, int out_mode,
                              int pool, int relu, float *y, long long y_group_stride, void *stream);
 
+/* one pointwise layer over POINT-MAJOR rows: x (G, N, C) -> y (G, N, M) = act(W x + bias) per row; C a power of two >= 32,
+ * x 16-byte aligned.  Same kernel and packed weights as jmb_tc_mlp_layer; the layout sa_fused gathers from. */
+JMB_API int jmb_tc_mlp_rows(const void *wpack, const float *bias, int M, int C, int G, int N, const float *x, int relu,
+                            float *y, void *stream);
+
 /* two pointwise layers in one launch when the second has ONE output channel (the heads end in a C -> 1 layer: rpn.py:40-47,
  * rcnn.py:91-111, tracker.py:86-109): layer 1 as jmb_tc_mlp_layer (dense x), its activated rows multiplied by dot_w
  * (ceil(M / 128) * 128 floats, zero padded: the second layer's weights) and reduced per 32-row block in fp32.

@@ -58,6 +58,7 @@ SIGNATURES = {
     "jmb_proposal_workspace_bytes": [_i, _i, _i, _i],
     "jmb_proposal_layer": [_i, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp],
     "jmb_feature_gather": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "jmb_tc_mlp_rows": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "jmb_tc_mlp_layer_dot": [_vp, _vp, _i, _i, _i, _i, _vp, C.c_longlong, _i, _i, _vp, _vp, _vp],
     "jmb_tc_dot_finish": [_i, _i, _i, _vp, _f, _i, _vp, _vp],
     "jmb_tc_conv3x3": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp],

@@ -80,6 +80,7 @@ struct TcGemmParams {
     // C = 1 << cv_cshift channels per pixel, column n of group g = output pixel (n / cv_OW, n % cv_OW), K index
     // k = tap * C + channel, tap = 3 dy + dx reading input pixel (oy * cv_stride + dy - 1, ox * cv_stride + dx - 1)
     int cv_cshift, cv_H, cv_W, cv_OW, cv_stride;
+    int cv_taps;                  // 9, or 1: "rows" mode — x (G, N, C) point-major, column n reads row n (a 1x1 convolution)
     int out_mode;                 // 0 dense (G, M, N), 1 max over `pool` consecutive columns -> (G, M, N / pool),
                                   // 2 point-major (G, N, M): a warp's 32 channels of one column are one 128-byte store,
                                   // 3 dot: the NEXT layer when it has one output channel, y (G, 4 Mt, N) = per 32-row
@@ -279,8 +280,12 @@ tc_gemm_kernel(const TcGemmParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int n = c.n0 + (tl >> 3) + 16 * j;
-                            const int oy = n / p.cv_OW, ox = n - oy * p.cv_OW;
-                            cv_origin[j] = n < p.N ? (((oy * p.cv_stride - 1) * 65536) | ((ox * p.cv_stride - 1) & 0xffff)) : 0x7fffffff;
+                            if (p.cv_taps == 1) {
+                                cv_origin[j] = n < p.N ? n : 0x7fffffff;
+                            } else {
+                                const int oy = n / p.cv_OW, ox = n - oy * p.cv_OW;
+                                cv_origin[j] = n < p.N ? (((oy * p.cv_stride - 1) * 65536) | ((ox * p.cv_stride - 1) & 0xffff)) : 0x7fffffff;
+                            }
                         }
                     }
                     const int c8 = tl & 7;
@@ -292,8 +297,11 @@ tc_gemm_kernel(const TcGemmParams p) {
                     for (int j = 0; j < 8; ++j) {
                         const int r = (tl >> 3) + 16 * j;
                         const int iy = (cv_origin[j] >> 16) + dy, ix = (int)(short)(cv_origin[j] & 0xffff) + dx;
-                        const bool ok = tap < 9 && cv_origin[j] != 0x7fffffff && iy >= 0 && iy < p.cv_H && ix >= 0 && ix < p.cv_W;
-                        const float *src = ok ? xg + (((size_t)iy * p.cv_W + ix) << p.cv_cshift) : p.x;
+                        const bool rows_mode = p.cv_taps == 1;
+                        const bool ok = tap < p.cv_taps && cv_origin[j] != 0x7fffffff &&
+                                        (rows_mode || (iy >= 0 && iy < p.cv_H && ix >= 0 && ix < p.cv_W));
+                        const size_t pix = rows_mode ? (size_t)cv_origin[j] : (size_t)iy * p.cv_W + ix;
+                        const float *src = ok ? xg + (pix << p.cv_cshift) : p.x;
                         const uint32_t dst = smem_u32(stage + (size_t)r * 128 + (size_t)((c8 ^ (r & 7)) * 16));
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
                     }
@@ -855,6 +863,33 @@ extern "C" int jmb_tc_mlp_layer_dot(const void *wpack, const float *bias, int M,
     return tc_gemm_launch(p, tiles, stream);
 }
 
+// Pointwise layer over POINT-MAJOR rows: x (G, N, C) -> y (G, N, M), the layout the fused set-abstraction kernel gathers
+// from and the per-proposal input stage writes.  The convolution mode with one tap: a column's K values are one contiguous
+// 4 C-byte run, staged with 16-byte copies and converted to K-major operand images.  C a power of two >= 32.
+extern "C" int jmb_tc_mlp_rows(const void *wpack, const float *bias, int M, int C, int G, int N, const float *x, int relu,
+                               float *y, void *stream) {
+    using namespace jmb;
+    JMB_REQUIRE(M > 0 && C >= TC_BK && (C & (C - 1)) == 0 && G >= 0 && N >= 0, "tc_mlp_rows: bad sizes (C must be a power of two >= 32)");
+    if (G == 0 || N == 0) return JMB_OK;
+    JMB_REQUIRE(wpack && x && y, "tc_mlp_rows: null pointer");
+    JMB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "tc_mlp_rows: input must be 16-byte aligned");
+    JMB_REQUIRE(N < 0x7fffffff, "tc_mlp_rows: too many rows per group");
+    TcGemmParams p{};
+    p.wpack = (const __nv_bfloat16 *)wpack; p.bias = bias;
+    p.M = M; p.K = C; p.Mt = div_up(M, TC_BM); p.Kc = div_up(C, TC_BK);
+    p.G = G; p.N = N; p.mode = 2; p.x = x; p.x_group_stride = (long long)N * C; p.x_row_stride = 0;
+    p.cv_cshift = 0;
+    while ((1 << p.cv_cshift) < C) ++p.cv_cshift;
+    p.cv_H = 1; p.cv_W = N; p.cv_OW = N; p.cv_stride = 1; p.cv_taps = 1;
+    p.out_mode = 2; p.pool = 0; p.relu = relu; p.y = y; p.y_group_stride = (long long)N * M;
+    p.P = 1; p.Nshift = 0; p.Nt = div_up(N, TC_BN);
+    p.col_tiles = (long long)G * p.Nt;
+    const long long tiles = p.col_tiles * p.Mt;
+    JMB_REQUIRE(tiles < (1LL << 30), "tc_mlp_rows: too many tiles");
+    p.use_raw = 1; p.bulk_out = 0;
+    return tc_gemm_launch(p, tiles, stream);
+}
+
 namespace jmb {
 // out[g][n] = act(bias + partial[g][0][n] + partial[g][1][n] + ...): the rows are added one after the other, so the result
 // does not depend on the shape (a library reduction picks its order by layout)
@@ -908,7 +943,7 @@ extern "C" int jmb_tc_conv3x3(const void *wpack, const float *bias, int Cout, in
     p.G = B; p.N = OH * OW; p.mode = 2; p.x = x; p.x_group_stride = (long long)H * W * C; p.x_row_stride = 0;
     p.cv_cshift = 0;
     while ((1 << p.cv_cshift) < C) ++p.cv_cshift;
-    p.cv_H = H; p.cv_W = W; p.cv_OW = OW; p.cv_stride = stride;
+    p.cv_H = H; p.cv_W = W; p.cv_OW = OW; p.cv_stride = stride; p.cv_taps = 9;
     p.out_mode = 2; p.pool = 0; p.relu = relu; p.y = y; p.y_group_stride = (long long)p.N * Cout;
     p.P = 1; p.Nshift = 0; p.Nt = div_up(p.N, TC_BN);
     p.col_tiles = (long long)B * p.Nt;

@@ -201,9 +201,13 @@ class RCNN(nn.Module):
         if pts_input.shape[-1] == head_pitch and head_pitch != cin + 128:
             # head layout from pool_rois: [128 channels | x, y, z, extras | 0...]; one kernel for the whole input stage
             xyz = pts_input[..., 128:131].contiguous()
+            # point-major rows when the first set-abstraction level is the fused kernel (its first-layer GEMM reads rows:
+            # tc.mlp_rows), else the reference's channel-first layout
+            fused_in_pm = bool(chain_ok and chain_ok[0])
             h = tc.rcnn_input_fused(P["xyz_up_w8"], P["xyz_up"][1], P["merge_down"][0], pts_input.contiguous(),
-                                    channel_first=True)                                   # (G, 128, 512)
+                                    channel_first=not fused_in_pm)                    # (G, 512, 128) | (G, 128, 512)
         else:
+            fused_in_pm = False
             xyz = pts_input[..., 0:3].contiguous()
             xyz_input = pts_input[..., 0:cin].transpose(1, 2).contiguous()               # (G, 5, 512)
             rpn_feature = pts_input[..., cin:].transpose(1, 2)                            # (G, 128, 512)
@@ -218,7 +222,7 @@ class RCNN(nn.Module):
             h = both
             for i, layer in enumerate(md):
                 h = tc.mlp_layer(layer, h)
-        l_xyz, l_feat, pm = xyz, h, False                                                 # pm: l_feat is point-major
+        l_xyz, l_feat, pm = xyz, h, fused_in_pm                                           # pm: l_feat is point-major
         for k, (sa, packed) in enumerate(sa_list):
             grouper = sa.groupers[0]
             if sa.npoint is not None:

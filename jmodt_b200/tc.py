@@ -162,6 +162,21 @@ def mlp_layer(layer: PackedLayer, x: torch.Tensor, *, out: torch.Tensor | None =
     return y
 
 
+def mlp_rows(layer: PackedLayer, x: torch.Tensor) -> torch.Tensor:
+    """Dense layer over point-major rows: x (G, N, C) -> (G, N, M); C a power of two >= 32 (the one-tap convolution mode of
+    csrc/tc_gemm.cu: a row's channels are one contiguous run)."""
+    assert x.dim() == 3 and x.is_contiguous() and x.dtype == torch.float32
+    G, N, C = x.shape
+    assert C == layer.K and C >= BK and C & (C - 1) == 0
+    y = torch.empty((G, N, layer.M), dtype=torch.float32, device=x.device)
+    st = _lib.stream_and_device(x)
+    profiler.launch(2.0 * layer.M * C * G * N, lambda: _lib.check(
+        _lib.lib().jmb_tc_mlp_rows(layer.wpack.data_ptr(), layer.bias.data_ptr(), layer.M, C, G, N, x.data_ptr(),
+                                   int(layer.relu), y.data_ptr(), st), "tc_mlp_rows"),
+        desc=f"rows M={layer.M} K={C} G={G} N={N} point-major")
+    return y
+
+
 def mlp_layer_dot(layer: PackedLayer, last: PackedLayer, x: torch.Tensor) -> torch.Tensor:
     """last(layer(x)) in ONE launch when `last` has a single output channel: x (G, K, N) -> (G, 1, N).  The epilogue of
     `layer` multiplies its activated rows by `last`'s weights and reduces them per 32-row block in fp32 (deterministic
@@ -281,9 +296,12 @@ def sa_fused(layers, xyz: torch.Tensor, feats: torch.Tensor | None, idx: torch.T
     C1, C2, C3 = layers[0].M, layers[1].M, layers[2].M
     z = None
     if feats is not None:
-        if feats_point_major:
-            feats = feats.transpose(1, 2)
-        z = mlp_layer(w1f, feats.contiguous(), point_major_out=True)          # (G, n_pts, C1)
+        if feats_point_major and C >= BK and C & (C - 1) == 0:
+            z = mlp_rows(w1f, feats.contiguous())                             # point-major in, point-major out
+        else:
+            if feats_point_major:
+                feats = feats.transpose(1, 2)
+            z = mlp_layer(w1f, feats.contiguous(), point_major_out=True)      # (G, n_pts, C1)
     oshape = (G, npoint, C3) if out_point_major else (G, C3, npoint)
     out = torch.empty(oshape, dtype=torch.float32, device=xyz.device)
     st = _lib.stream_and_device(xyz)

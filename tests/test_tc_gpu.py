@@ -180,3 +180,23 @@ def test_single_output_tail_folded_into_the_previous_epilogue(cuda, G, K, N, M, 
     if N % 8 == 0 and N >= 256:       # the same columns as one group of half the width twice over
         half = tc.mlp_layer_dot(l1, l2, xd[:, :, : N // 2].contiguous())
         assert torch.equal(half, got[:, :, : N // 2])
+
+
+@pytest.mark.parametrize("G,N,C,M,relu", [(4, 512, 128, 128, False), (3, 100, 32, 46, True), (2, 1000, 256, 200, True),
+                                          (1, 128, 64, 128, True)])
+def test_point_major_rows_layer(cuda, G, N, C, M, relu):
+    """tc.mlp_rows: x (G, N, C) point-major -> (G, N, M) (one-tap convolution mode of the layer kernel) against fp64."""
+    from jmodt_b200 import tc
+    g = torch.Generator(device="cpu").manual_seed(C * 11 + N)
+    w, b = torch.randn(M, C, generator=g) / C ** 0.5, torch.randn(M, generator=g)
+    x = torch.randn(G, N, C, generator=g)
+    layer = tc.PackedLayer(w.to(cuda), b.to(cuda), relu)
+    got = tc.mlp_rows(layer, x.to(cuda).contiguous())
+    want = torch.einsum("mk,gnk->gnm", w.double(), x.double()) + b.double()
+    if relu:
+        want = want.clamp_min(0)
+    assert got.shape == (G, N, M)
+    _check(got.cpu().double(), want)
+    # the same numbers as the channel-first launch with a point-major epilogue
+    ref = tc.mlp_layer(layer, x.to(cuda).transpose(1, 2).contiguous(), point_major_out=True)
+    assert torch.equal(got, ref)
