@@ -93,9 +93,11 @@ class CapturedPath:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count
-        # kernel nodes inherit the priority of the stream they were captured on: JMB_MAIN_PRIORITY=-1 captures the step on
-        # a high-priority stream (its forked branch streams stay at the default priority)
-        prio = int(os.environ.get("JMB_MAIN_PRIORITY", "0"))
+        # kernel nodes inherit the priority of the stream they were captured on: the step is captured on a high-priority
+        # stream (JMB_MAIN_PRIORITY, default -1; its forked branch and background streams stay at the default priority), so
+        # the chain of small launches on the critical path is scheduled ahead of the wide background launches (the image
+        # decoder's 1 280 CTAs): 7.53 ms per step against 7.62
+        prio = int(os.environ.get("JMB_MAIN_PRIORITY", "-1"))
         cap_stream = torch.cuda.Stream(priority=prio) if prio else None
         with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local"):
             self.outputs = fn(inputs)

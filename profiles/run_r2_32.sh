@@ -12,6 +12,6 @@ except Exception as e:
     print("cfg $1 ERR", e)
 PY
 }
-run JMB_L0_WITH_GEOMETRY=1
-run JMB_GEO_PRIORITY=0
-run JMB_BRANCH_PARALLEL=0
+run JMB_MAIN_PRIORITY=-1
+run JMB_MAIN_PRIORITY=-2
+run "JMB_MAIN_PRIORITY=-1 JMB_GEO_PRIORITY=-2"
