@@ -12,6 +12,7 @@ except Exception as e:
     print("cfg $1 ERR", e)
 PY
 }
-run JMB_MAIN_PRIORITY=-1
-run JMB_MAIN_PRIORITY=-2
-run "JMB_MAIN_PRIORITY=-1 JMB_GEO_PRIORITY=-2"
+run JMB_DECODE_SPAWN_LEVEL=0
+run JMB_DECODE_SPAWN_LEVEL=1
+run JMB_DECODE_SPAWN_LEVEL=2
+run JMB_DECODE_SPAWN_LEVEL=3
