@@ -1,18 +1,13 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-run() {
-env $1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_x.json 2> gpurun_out/bench_x.err; echo "$1 rc=$?"
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_golden_gpu.py -m gpu -q -x --timeout 300 2>&1 | tail -2
+timeout 600 python profiles/ref_cuda_timing.py > gpurun_out/ref_cuda_timing.log 2>&1; grep -i "furthest" gpurun_out/ref_cuda_timing.log
+for i in 1 2; do
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_x$i.json 2> gpurun_out/bench_x$i.err
 python - <<PY
 import json
-try:
-    d = json.loads(open("gpurun_out/bench_x.json").read().strip().splitlines()[-1])
-    print("cfg $1", d["value"], d["ms_per_step"], d.get("stage_ms_per_call"), d["roofline"]["frac"])
-except Exception as e:
-    print("cfg $1 ERR", e)
+d = json.loads(open("gpurun_out/bench_x$i.json").read().strip().splitlines()[-1])
+print("bench", d["value"], d["ms_per_step"], d["e2e"]["value"], d.get("stage_ms_per_call"), d["roofline"]["frac"])
 PY
-}
-run JMB_DECODE_SPAWN_LEVEL=0
-run JMB_DECODE_SPAWN_LEVEL=1
-run JMB_DECODE_SPAWN_LEVEL=2
-run JMB_DECODE_SPAWN_LEVEL=3
+done
