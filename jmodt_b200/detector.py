@@ -359,7 +359,7 @@ class PointNet2MSG(nn.Module):
     overlap_geometry = True
     # Opt-in (JMB_L0_CHUNKS=8): consume the level-0 FPS output in prefixes while the sampler is still running.  The
     # gates (`wait_indices`) poll a buffer another stream's kernel fills, which needs that kernel to be making progress
-    # concurrently — true on an otherwise idle B200 (the sampler holds 64 of 148 SMs) but not something CUDA guarantees,
+    # concurrently — true on an otherwise idle B200 (the sampler holds 32 of 148 SMs) but not something CUDA guarantees,
     # so the default is 1: level 0 waits for the sampler's completion event like every other level.  The throughput path
     # (`PointRCNN.geometry` + `forward(..., geometry=...)`, bench.py) takes the whole coordinate stage off the critical
     # path instead by computing it one step ahead.
@@ -370,7 +370,7 @@ class PointNet2MSG(nn.Module):
         coordinate chain of all levels (FPS0 -> FPS1 -> ..., the neighbour lists, the interpolation weights) runs on a
         high-priority side stream, one event per level, and the feature chain on the caller's stream waits for the
         level it needs: the narrow, latency-bound FPS kernels and the three_nn searches then overlap the tensor-core
-        work instead of stalling it.  Level 0 goes one step further: its FPS (4 096 dependent iterations on 64 SMs,
+        work instead of stalling it.  Level 0 goes one step further: its FPS (4 096 dependent iterations on 32 SMs,
         the longest kernel of the step) publishes indices as it goes, and the caller's stream consumes them in
         `l0_chunks` prefixes behind `wait_indices` gates (see forward()).  Same kernels, same results."""
         if not (self.overlap_geometry and not self.training and xyz.is_cuda):

@@ -117,7 +117,7 @@ class CapturedPath:
 
 class GeometryAhead:
     """Two batches in flight: while the feature stages of batch k run on the caller's stream, the coordinate-only stage
-    of batch k + 1 (`geometry_fn`: FPS, ball queries, three_nn — a 3.6 ms dependent chain that occupies 64 of the 148
+    of batch k + 1 (`geometry_fn`: FPS, ball queries, three_nn — a 4 ms dependent chain that occupies 32 of the 148
     SMs, pure latency) runs on a side stream, and its result is handed over at the end of the step.
 
         ahead = GeometryAhead(model.geometry, first_batch_points)       # eager: geometry of batch 0
