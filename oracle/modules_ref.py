@@ -144,3 +144,36 @@ def backbone_forward(net, xyz, xy, image_maps, cref):
         l_features[i - 1] = fp_forward(net.FP_modules[i], l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i], cref)
     l_features[0] = ia_fusion_forward(net.final_fusion_img_point, l_features[0], grid_gather(image_maps[1], xy))
     return l_xyz[0], l_features[0]
+
+
+def basic_block(blk, x):
+    """BasicBlock.forward (backbone.py:15-30): conv3x3 -> BatchNorm2d (eval statistics) -> ReLU -> conv3x3 with stride 2,
+    spelled out with functional ops on the block's parameters so that a block whose own forward is routed to the
+    tensor-core convolution cannot end up in its own oracle.  x (B, Cin, H, W) -> (B, Cout, H/2, W/2)."""
+    c1, bn, c2 = blk.conv1, blk.bn1, blk.conv2
+    y = F.conv2d(x, c1.weight, c1.bias, stride=c1.stride, padding=c1.padding)
+    y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, training=False, eps=bn.eps)
+    return F.conv2d(F.relu(y), c2.weight, c2.bias, stride=c2.stride, padding=c2.padding)
+
+
+def image_stack(net, image):
+    """The image branch of PointNet2MSG.forward (backbone.py:170,187-193): the four Img_Block maps and the fused
+    full-resolution map relu(image_fusion_bn(image_fusion_conv(cat_i DeConv_i(img_i)))).  Returns (maps, fused)."""
+    maps, x = [], image
+    for blk in net.Img_Block:
+        x = basic_block(blk, x)
+        maps.append(x)
+    de = torch.cat([F.conv_transpose2d(m, dc.weight, dc.bias, stride=dc.stride) for dc, m in zip(net.DeConv, maps)], dim=1)
+    bn = net.image_fusion_bn
+    fused = F.conv2d(de, net.image_fusion_conv.weight, net.image_fusion_conv.bias)
+    fused = F.relu(F.batch_norm(fused, bn.running_mean, bn.running_var, bn.weight, bn.bias, training=False, eps=bn.eps))
+    return maps, fused
+
+
+def image_decoder_at_points(net, maps, xy):
+    """backbone.py:187-194 on given Img_Block maps: the fused map sampled at the projected points (B, 32, N)."""
+    de = torch.cat([F.conv_transpose2d(m, dc.weight, dc.bias, stride=dc.stride) for dc, m in zip(net.DeConv, maps)], dim=1)
+    bn = net.image_fusion_bn
+    fused = F.conv2d(de, net.image_fusion_conv.weight, net.image_fusion_conv.bias)
+    fused = F.relu(F.batch_norm(fused, bn.running_mean, bn.running_var, bn.weight, bn.bias, training=False, eps=bn.eps))
+    return grid_gather(fused, xy)

@@ -38,11 +38,15 @@ def _xy(B, N, seed=2):
 
 
 def _dense(net, maps, xy):
+    """The reference's dense formulation, from the oracle (functional ops on the module's parameters)."""
+    from oracle import modules_ref
     with torch.no_grad():
         de = torch.cat([dc(m) for dc, m in zip(net.DeConv, maps)], dim=1)
         fused = F.relu(net.image_fusion_bn(net.image_fusion_conv(de)))
-        return F.grid_sample(fused, xy.unsqueeze(1), mode="bilinear", padding_mode="zeros",
-                             align_corners=True).squeeze(2), fused
+        want = modules_ref.image_decoder_at_points(net, maps, xy)
+        assert torch.allclose(want, F.grid_sample(fused, xy.unsqueeze(1), mode="bilinear", padding_mode="zeros",
+                                                  align_corners=True).squeeze(2), rtol=1e-5, atol=1e-6)
+        return want, fused
 
 
 def test_decoder_pack_reproduces_dense_pixels_on_cpu():
@@ -149,8 +153,10 @@ def test_basic_block_on_tensor_cores_matches_torch_fp32(cuda, cin, cout, B, H, W
         blk.bn1.running_var.copy_(torch.linspace(0.6, 1.7, cout))
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, cin, H, W, generator=g)
+    from oracle import modules_ref
     with torch.no_grad():
-        want = blk(x)
+        want = modules_ref.basic_block(blk, x)
+        assert torch.allclose(want, blk(x), rtol=1e-5, atol=1e-6)         # the CPU module forward is the same composition
     blk = blk.to(cuda)
     with torch.no_grad():
         got = blk(x.to(cuda))
