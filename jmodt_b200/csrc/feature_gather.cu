@@ -104,23 +104,18 @@ ia_attention_kernel(int ic, int pc, int rc, int N, const float *__restrict__ img
     for (int half = 0; half < 2; ++half) {
         const int kn = half == 0 ? ic : pc;
         int k = 0;
-        for (; k + 4 <= kn; k += 4) {          // four independent loads in flight
-            const float x0 = __ldg(x + (size_t)k * N), x1 = __ldg(x + (size_t)(k + 1) * N);
-            const float x2 = __ldg(x + (size_t)(k + 2) * N), x3 = __ldg(x + (size_t)(k + 3) * N);
+        for (; k + 8 <= kn; k += 8) {          // eight independent loads in flight: the loop is bound by their latency
+            float xv[8];
 #pragma unroll
-            for (int r4 = 0; r4 < RC; r4 += 4) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(w + (k + 0) * RC + r4);
-                const float4 w1 = *reinterpret_cast<const float4 *>(w + (k + 1) * RC + r4);
-                const float4 w2 = *reinterpret_cast<const float4 *>(w + (k + 2) * RC + r4);
-                const float4 w3v = *reinterpret_cast<const float4 *>(w + (k + 3) * RC + r4);
-                acc[r4 + 0] = fmaf(w0.x, x0, acc[r4 + 0]); acc[r4 + 1] = fmaf(w0.y, x0, acc[r4 + 1]);
-                acc[r4 + 2] = fmaf(w0.z, x0, acc[r4 + 2]); acc[r4 + 3] = fmaf(w0.w, x0, acc[r4 + 3]);
-                acc[r4 + 0] = fmaf(w1.x, x1, acc[r4 + 0]); acc[r4 + 1] = fmaf(w1.y, x1, acc[r4 + 1]);
-                acc[r4 + 2] = fmaf(w1.z, x1, acc[r4 + 2]); acc[r4 + 3] = fmaf(w1.w, x1, acc[r4 + 3]);
-                acc[r4 + 0] = fmaf(w2.x, x2, acc[r4 + 0]); acc[r4 + 1] = fmaf(w2.y, x2, acc[r4 + 1]);
-                acc[r4 + 2] = fmaf(w2.z, x2, acc[r4 + 2]); acc[r4 + 3] = fmaf(w2.w, x2, acc[r4 + 3]);
-                acc[r4 + 0] = fmaf(w3v.x, x3, acc[r4 + 0]); acc[r4 + 1] = fmaf(w3v.y, x3, acc[r4 + 1]);
-                acc[r4 + 2] = fmaf(w3v.z, x3, acc[r4 + 2]); acc[r4 + 3] = fmaf(w3v.w, x3, acc[r4 + 3]);
+            for (int u = 0; u < 8; ++u) xv[u] = __ldg(x + (size_t)(k + u) * N);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int r4 = 0; r4 < RC; r4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(w + (k + u) * RC + r4);
+                    acc[r4 + 0] = fmaf(wv.x, xv[u], acc[r4 + 0]); acc[r4 + 1] = fmaf(wv.y, xv[u], acc[r4 + 1]);
+                    acc[r4 + 2] = fmaf(wv.z, xv[u], acc[r4 + 2]); acc[r4 + 3] = fmaf(wv.w, xv[u], acc[r4 + 3]);
+                }
             }
         }
         for (; k < kn; ++k) {

@@ -156,8 +156,8 @@ class IALayer(nn.Module):
                                                    P["w12"].data_ptr(), P["b12"].data_ptr(), P["w3"].data_ptr(), P["b3"],
                                                    att.data_ptr(), st), "ia_attention")
             return att
-        if B * N >= 8192 and P["w3"].numel() <= 64:
-            # many points, few reduced channels (levels 0, 1 and the final fusion): the attention weight as ONE fp32 SIMT
+        if B * N >= 32768 and P["w3"].numel() <= 64:
+            # many points, few reduced channels (level 0 and the final fusion): the attention weight as ONE fp32 SIMT
             # kernel next to the image projection, on forked streams (runtime.parallel)
             att, conv = runtime.parallel(attention, lambda: tc.mlp_layer(P["conv1"], img_feas))
             return conv * att
