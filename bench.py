@@ -76,6 +76,9 @@ def parse():
                          "instead of one step ahead on a side stream")
     ap.add_argument("--rois", default="synthetic", choices=["synthetic", "proposal"],
                     help="e2e workload: RoIs the per-proposal stage consumes (synthetic cluster boxes, or the proposal layer's output)")
+    ap.add_argument("--serial-e2e", action="store_true",
+                    help="e2e leg: upload, replay and read back one step at a time instead of streaming the copies under the "
+                         "neighbouring steps")
     ap.add_argument("--pairs", type=int, default=1, help="affinity-sharded workload: 128x128 frame pairs per step")
     ap.add_argument("--image-map", default="sparse", choices=["sparse", "dense"],
                     help="e2e workload: sparse = the image decoder (deconv x4 + 1x1 + BN + ReLU + sampling) runs inside the "
@@ -465,15 +468,34 @@ def run_b200(args):
             bp = boundary_pair(out)
             return [out[k].cpu() for k in keys] + ([t.cpu() for t in bp[:3]] if bp is not None else [])
         return [out["empty"].cpu(), out["keep_num"].cpu(), out["final_num"].cpu()] + [x.cpu() for x in out["iou"]]
-    for _ in range(2):
-        e2e_step()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, args.steps // 2)
-    e0.record()
-    for _ in range(n_e2e):
-        res = e2e_step()
-    e1.record()
+    if graph_mode and e2e_mode and not args.serial_e2e:
+        # streamed: the next step's inputs cross PCIe while this one computes, this step's results are read back while the
+        # next one computes (runtime.StreamedPath); every step still moves its own inputs and results
+        from jmodt_b200.runtime import StreamedPath
+
+        def extra(out):
+            bp = boundary_pair(out)
+            return list(bp[:3]) if bp is not None else []
+        sp = StreamedPath(clean, host, ("rcnn_cls", "rcnn_reg", "proposals", "empty", "link", "start", "end"), extra)
+        for _ in range(3):
+            sp.step(host)
+        sp.drain()
+        barrier()
+        e0.record()
+        for _ in range(n_e2e):
+            sp.step(host)
+        res = sp.drain()
+        e1.record()
+    else:
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(n_e2e):
+            res = e2e_step()
+        e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
     h2d = sum(int(t.numel() * t.element_size()) for v in host.values() for t in (v if isinstance(v, list) else [v]))
@@ -567,7 +589,11 @@ def run_b200(args):
                                   "external event nodes, replayed after the timed region") if graph_mode
                                  else "every kernel enqueued from Python each step; per-kernel event pairs inline"},
             "e2e": {"value": proposals_per_step / (e2e_ms * 1e-3), "unit": "proposals/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "mode": ("streamed: pinned host -> device staging on a copy stream under the previous step, results -> "
+                             "pinned host under the next step (runtime.StreamedPath); the timed region ends when the last "
+                             "step's results are on the host") if (graph_mode and e2e_mode and not args.serial_e2e)
+                            else "serial: upload, step, blocking read-back"},
             "gpu_launches": launches,
             "collective": ({"op": "all_gather (NCCL) of each rank's first-frame RCNN features for the shard-boundary affinity pair",
                             "bytes_per_rank": N_ROI * 512 * 4, "median_us": float(np.median(coll_us)) if coll_us else None,

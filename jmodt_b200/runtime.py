@@ -115,6 +115,77 @@ class CapturedPath:
         return self.outputs
 
 
+class StreamedPath:
+    """Host-to-host streaming around a CapturedPath: the inputs of step i + 1 cross PCIe while step i computes, and the
+    results of step i are read back while step i + 1 computes.
+
+        sp = StreamedPath(path, host_inputs, out_keys)
+        for batch in batches:
+            results = sp.step(batch)        # pinned host tensors of the step submitted ONE call earlier (None at first)
+        last = sp.drain()
+
+    Every step still moves its own inputs host -> device (pinned memory -> staging buffers on a copy stream -> the graph's
+    static inputs with a device-side copy in front of the replay) and its own results device -> host (static outputs ->
+    staging on the compute stream, -> pinned host buffers on the copy stream); only the waiting is gone."""
+
+    def __init__(self, path: CapturedPath, host_inputs: Dict[str, torch.Tensor], out_keys, extra_outputs=None):
+        self.path, self.out_keys = path, list(out_keys)
+        self.extra = extra_outputs          # optional fn(outputs) -> list of extra device tensors to read back
+        dev = next(iter(path.inputs.values())).device
+        self.copy = torch.cuda.Stream(device=dev)
+        self.stage_in = {k: torch.empty_like(path.inputs[k]) for k in host_inputs if k in path.inputs}
+        self.in_landed, self.in_consumed = torch.cuda.Event(), torch.cuda.Event()
+        self.in_consumed.record()
+        self.slots, self.pending, self.n = [None, None], [None, None], 0
+
+    def _outputs(self, out):
+        ts = [out[k] for k in self.out_keys]
+        if self.extra is not None:
+            ts += list(self.extra(out))
+        return ts
+
+    def step(self, host_inputs: Dict[str, torch.Tensor]):
+        main = torch.cuda.current_stream()
+        slot = self.n & 1
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.in_consumed)              # the previous step's device-side load has read the staging
+            for k, t in self.stage_in.items():
+                t.copy_(host_inputs[k], non_blocking=True)
+            self.in_landed.record(self.copy)
+        main.wait_event(self.in_landed)
+        self.path.load(self.stage_in)                            # device -> device, in front of the replay
+        self.in_consumed.record(main)
+        out = self.path.replay()
+        ts = self._outputs(out)
+        if self.slots[slot] is None:
+            self.slots[slot] = ([torch.empty_like(t) for t in ts],
+                                [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in ts],
+                                torch.cuda.Event(), torch.cuda.Event())
+        dev_stage, host_out, staged, landed = self.slots[slot]
+        if self.pending[slot] is not None:
+            landed.synchronize()                                 # the host is done waiting for the results of step n - 2
+        torch._foreach_copy_(dev_stage, ts)                      # free the static outputs for the next replay
+        staged.record(main)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(staged)
+            for h, d in zip(host_out, dev_stage):
+                h.copy_(d, non_blocking=True)
+            landed.record(self.copy)
+        self.pending[slot] = host_out
+        self.n += 1
+        prev = self.n & 1                                        # the slot of the step submitted one call earlier
+        if self.pending[prev] is not None and self.n >= 2:
+            self.slots[prev][3].synchronize()
+            return self.pending[prev]
+        return None
+
+    def drain(self):
+        """Results of the last submitted step (waits for its read-back)."""
+        last = (self.n - 1) & 1
+        self.slots[last][3].synchronize()
+        return self.pending[last]
+
+
 class GeometryAhead:
     """Two batches in flight: while the feature stages of batch k run on the caller's stream, the coordinate-only stage
     of batch k + 1 (`geometry_fn`: FPS, ball queries, three_nn — a 4 ms dependent chain that occupies 32 of the 148
